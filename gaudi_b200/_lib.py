@@ -1,0 +1,91 @@
+"""ctypes binding of ``csrc/libgaudi_b200.so`` (the C ABI declared in ``include/gaudi_b200.h``).
+
+There is no fallback: if the shared library is missing it is built with ``make`` (nvcc, sm_100a) and an
+ImportError is raised when that is impossible.  All compute entry points need a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libgaudi_b200.so")
+
+_P = C.c_void_p
+_I = C.c_int
+_F = C.c_float
+_U64 = C.c_ulonglong
+_SZ = C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/gaudi_b200.h one to one
+SIGNATURES = {
+    "gb_abi_version": (_I, []),
+    "gb_last_error": (C.c_char_p, []),
+    "gb_launch_count": (C.c_longlong, [_I]),
+    "gb_denoiser_create": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I, _I, _F, _F, _F, C.POINTER(_P), _I, _P]),
+    "gb_predictor_create": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I, _I, _F, C.POINTER(_P), _I, _P]),
+    "gb_net_destroy": (_I, [_P]),
+    "gb_net_hidden_padded": (_I, [_P]),
+    "gb_tile_pack": (_I, [_P, _I, _P, C.POINTER(_I)]),
+    "gb_graph_create": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gb_graph_destroy": (_I, [_P]),
+    "gb_denoiser_workspace_bytes": (_SZ, [_P, _P]),
+    "gb_predictor_workspace_bytes": (_SZ, [_P, _P, _I]),
+    "gb_denoiser_forward": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _P, _SZ, _P]),
+    "gb_predictor_forward": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _SZ, _P]),
+    "gb_predictor_input_grad": (_I, [_P, _P, _P, _I, _P, _P, _SZ, _P]),
+    "gb_step_sample": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _U64, _U64, _I, _P, _P]),
+    "gb_step_guide": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P]),
+    "gb_decode": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _U64, _U64, _F, _F, _F, _P, _P, _P, _P]),
+    "gb_cog_fix": (_I, [_P, _P, _P, _F, _I, _I, _P]),
+    "gb_noise": (_I, [_P, _P, _I, _I, _I, _F, _U64, _U64, _P]),
+    "gb_sample_loop": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _U64, _P, _P, _SZ, _I, _P]),
+    "gb_sample_loop_workspace_bytes": (_SZ, [_P, _P, _P]),
+}
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a into ``csrc/libgaudi_b200.so`` (nvcc cross-compiles without a GPU)."""
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        raise ImportError("gaudi_b200: libgaudi_b200.so is missing and nvcc is not available to build it")
+    env = dict(os.environ)
+    if shutil.which("nvcc") is None:
+        env["PATH"] = "/usr/local/cuda/bin:" + env.get("PATH", "")
+    cmd = ["make", "-C", CSRC, "-j", str(min(8, os.cpu_count() or 1))]
+    if force:
+        subprocess.run(["make", "-C", CSRC, "clean"], check=True, env=env, capture_output=not verbose)
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise ImportError("gaudi_b200: building libgaudi_b200.so failed:\n" + res.stdout[-4000:] + res.stderr[-4000:])
+    if verbose:
+        print(res.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError here = header/library mismatch: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+class GaudiB200Error(RuntimeError):
+    pass
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise GaudiB200Error(lib().gb_last_error().decode("utf-8", "replace"))

@@ -1,1 +1,376 @@
-"""placeholder (filled in below)"""
+"""Host-side glue between the GaUDI-shaped PyTorch modules and the C ABI (``include/gaudi_b200.h``).
+
+PyTorch is plumbing here: it owns device memory, the current CUDA stream and autograd bookkeeping; every
+arithmetic op of the hot path is a hand-written sm_100a kernel reached through ``ctypes``.
+There is deliberately no CPU / eager fallback: a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .graph import Topology, build_topology
+
+_VP = C.c_void_p
+
+
+def _ptr(t: Optional[torch.Tensor]) -> _VP:
+    return _VP(0) if t is None else _VP(t.data_ptr())
+
+
+def _stream() -> _VP:
+    return _VP(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"gaudi_b200: {what} must be a CUDA tensor (the sm_100a kernels have no CPU fallback)")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# packed-weights handles
+# --------------------------------------------------------------------------------------------------
+class NetHandle:
+    def __init__(self, handle: int, tensors: List[torch.Tensor], versions: Tuple):
+        self.handle = _VP(handle)
+        self.versions = versions
+        self._keep = tensors
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().gb_net_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def _param_list_denoiser(egnn) -> List[torch.Tensor]:
+    ps = [egnn.embedding.weight, egnn.embedding.bias, egnn.embedding_out.weight, egnn.embedding_out.bias]
+    for b in range(egnn.n_layers):
+        blk = getattr(egnn, f"e_block_{b}")
+        for s in range(blk.n_layers):
+            g = getattr(blk, f"gcl_{s}")
+            ps += [g.edge_mlp[0].weight, g.edge_mlp[0].bias, g.edge_mlp[2].weight, g.edge_mlp[2].bias,
+                   g.node_mlp[0].weight, g.node_mlp[0].bias, g.node_mlp[2].weight, g.node_mlp[2].bias]
+            if g.attention:
+                ps += [g.att_mlp[0].weight, g.att_mlp[0].bias]
+        e = blk.gcl_equiv
+        ps += [e.coord_mlp[0].weight, e.coord_mlp[0].bias, e.coord_mlp[2].weight, e.coord_mlp[2].bias,
+               e.coord_mlp[4].weight]
+    return ps
+
+
+def _param_list_predictor(egnn) -> List[torch.Tensor]:
+    ps = [egnn.embedding.weight, egnn.embedding.bias, egnn.embedding_out.weight, egnn.embedding_out.bias]
+    for l in range(egnn.n_layers):
+        g = getattr(egnn, f"gcl_{l}")
+        ps += [g.edge_mlp[0].weight, g.edge_mlp[0].bias, g.edge_mlp[2].weight, g.edge_mlp[2].bias,
+               g.node_mlp[0].weight, g.node_mlp[0].bias, g.node_mlp[2].weight, g.node_mlp[2].bias,
+               g.coord_mlp[0].weight, g.coord_mlp[0].bias, g.coord_mlp[2].weight]
+        if g.attention:
+            ps += [g.att_mlp[0].weight, g.att_mlp[0].bias]
+    return ps
+
+
+def _versions(ps: List[torch.Tensor]) -> Tuple:
+    return tuple((p.data_ptr(), p._version) for p in ps)
+
+
+def denoiser_handle(dyn) -> NetHandle:
+    """Packed-weights handle of an ``EGNN_dynamics`` (re-packed when parameters were reloaded / moved)."""
+    ps = _param_list_denoiser(dyn.egnn)
+    _need_cuda(ps[0], "denoiser parameters")
+    ver = _versions(ps)
+    h = dyn.__dict__.get("_gb_handle")
+    if h is None or h.versions != ver:
+        tens = [_f32c(p) for p in ps]
+        arr = (_VP * len(tens))(*[t.data_ptr() for t in tens])
+        out = _VP(0)
+        hy = dyn.hyper
+        _lib.check(_lib.lib().gb_denoiser_create(
+            C.byref(out), dyn.in_node_nf - 1, hy["hidden_nf"], hy["n_layers"], hy["inv_sublayers"],
+            int(hy["attention"]), int(hy["tanh"]), hy["coords_range"], hy["norm_constant"],
+            hy["normalization_factor"], arr, len(tens), _stream()))
+        h = NetHandle(out.value, tens, ver)
+        dyn.__dict__["_gb_handle"] = h
+    return h
+
+
+def predictor_handle(pred) -> NetHandle:
+    ps = _param_list_predictor(pred.egnn)
+    _need_cuda(ps[0], "predictor parameters")
+    ver = _versions(ps)
+    h = pred.__dict__.get("_gb_handle")
+    if h is None or h.versions != ver:
+        tens = [_f32c(p) for p in ps]
+        arr = (_VP * len(tens))(*[t.data_ptr() for t in tens])
+        out = _VP(0)
+        hy = pred.hyper
+        _lib.check(_lib.lib().gb_predictor_create(
+            C.byref(out), hy["in_node_nf"] - 1, hy["out_nf"], hy["hidden_nf"], hy["n_layers"], int(hy["attention"]),
+            int(hy["tanh"]), hy["coords_range"], arr, len(tens), _stream()))
+        h = NetHandle(out.value, tens, ver)
+        pred.__dict__["_gb_handle"] = h
+    return h
+
+
+# --------------------------------------------------------------------------------------------------
+# graph handles (cached per mask pair)
+# --------------------------------------------------------------------------------------------------
+class GraphHandle:
+    def __init__(self, topo: Topology):
+        self.topo = topo
+        out = _VP(0)
+        _lib.check(_lib.lib().gb_graph_create(
+            C.byref(out), topo.B, topo.N, topo.n_edges, topo.n_tiles, topo.n_tc, _ptr(topo.rowptr), _ptr(topo.erow),
+            _ptr(topo.ecol), _ptr(topo.tile_ptr), _ptr(topo.tc_ptr), _ptr(topo.tc_node), _ptr(topo.tc_start),
+            _ptr(topo.cperm), _ptr(topo.node_mask)))
+        self.handle = out
+
+    def __del__(self):
+        try:
+            _lib.lib().gb_graph_destroy(self.handle)
+        except Exception:
+            pass
+
+
+_graph_cache: Dict[Tuple, GraphHandle] = {}
+_GRAPH_CACHE_MAX = 8
+
+
+def graph_for(node_mask: torch.Tensor, edge_mask: torch.Tensor, B: int, N: int) -> GraphHandle:
+    _need_cuda(node_mask, "node_mask")
+    _need_cuda(edge_mask, "edge_mask")
+    key = (node_mask.data_ptr(), node_mask._version, edge_mask.data_ptr(), edge_mask._version, B, N,
+           node_mask.device.index)
+    g = _graph_cache.get(key)
+    if g is None:
+        if len(_graph_cache) >= _GRAPH_CACHE_MAX:
+            _graph_cache.pop(next(iter(_graph_cache)))
+        g = GraphHandle(build_topology(node_mask, edge_mask, B, N))
+        g._masks = (node_mask, edge_mask)          # keep the keyed storage alive so data_ptr stays unique
+        _graph_cache[key] = g
+    return g
+
+
+# --------------------------------------------------------------------------------------------------
+# workspaces (grown on demand, one per purpose and device)
+# --------------------------------------------------------------------------------------------------
+class Workspace:
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+        self.generation = 0
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = None
+            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+_ws: Dict[Tuple[str, int], Workspace] = {}
+
+
+def workspace(kind: str, device) -> Workspace:
+    key = (kind, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _ws:
+        _ws[key] = Workspace()
+    return _ws[key]
+
+
+def release_workspaces() -> None:
+    _ws.clear()
+    _graph_cache.clear()
+
+
+# --------------------------------------------------------------------------------------------------
+# top-level ops
+# --------------------------------------------------------------------------------------------------
+def _time_tensor(t, B: int, device) -> Tuple[torch.Tensor, int]:
+    t = torch.as_tensor(t, dtype=torch.float32, device=device)
+    if t.numel() == 1:
+        return t.reshape(1).contiguous(), 0
+    if t.numel() != B:
+        raise ValueError(f"t must have 1 or B={B} elements, got {tuple(t.shape)}")
+    return t.reshape(B).contiguous(), 1
+
+
+def denoiser_forward(dyn, t, xh: torch.Tensor, node_mask: torch.Tensor, edge_mask: torch.Tensor,
+                     scrub_all: bool = False, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """EGNN_dynamics._forward (edm/egnn/models.py:83-152)."""
+    _need_cuda(xh, "xh")
+    B, N, D = xh.shape
+    net = denoiser_handle(dyn)
+    g = graph_for(node_mask, edge_mask, B, N)
+    z = _f32c(xh)
+    tt, per_mol = _time_tensor(t, B, xh.device)
+    eps = torch.empty_like(z)
+    nbytes = _lib.lib().gb_denoiser_workspace_bytes(net.handle, g.handle)
+    ws = workspace("den", xh.device).get(nbytes, xh.device)
+    _lib.check(_lib.lib().gb_denoiser_forward(net.handle, g.handle, _ptr(z), _ptr(tt), per_mol, _ptr(eps),
+                                              int(scrub_all), _ptr(stats), _ptr(ws), ws.numel(), _stream()))
+    return eps
+
+
+class _PredictorFn(torch.autograd.Function):
+    """pred = EGNN_predictor(xh); backward = hand-written input-gradient kernels (no weight gradients)."""
+
+    @staticmethod
+    def forward(ctx, xh, pred_module, node_mask, edge_mask, t):
+        B, N, D = xh.shape
+        net = predictor_handle(pred_module)
+        g = graph_for(node_mask, edge_mask, B, N)
+        z = _f32c(xh)
+        tt, per_mol = _time_tensor(t, B, xh.device)
+        need_grad = bool(ctx.needs_input_grad[0])
+        out = torch.empty(B, pred_module.hyper["out_nf"], dtype=torch.float32, device=xh.device)
+        nbytes = _lib.lib().gb_predictor_workspace_bytes(net.handle, g.handle, int(need_grad))
+        wsp = workspace("pred_grad" if need_grad else "pred", xh.device)
+        ws = wsp.get(nbytes, xh.device)
+        _lib.check(_lib.lib().gb_predictor_forward(net.handle, g.handle, _ptr(z), _ptr(tt), per_mol, _ptr(out),
+                                                   int(need_grad), _ptr(ws), ws.numel(), _stream()))
+        if need_grad:
+            wsp.generation += 1
+            ctx.gen = wsp.generation
+            ctx.wsp, ctx.net, ctx.g, ctx.shape = wsp, net, g, (B, N, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_pred):
+        wsp = ctx.wsp
+        if wsp.generation != ctx.gen:
+            raise RuntimeError("gaudi_b200: the predictor workspace was overwritten by a later forward; "
+                               "call backward before running the predictor again")
+        B, N, D = ctx.shape
+        gp = _f32c(g_pred)
+        gz = torch.empty(B, N, D, dtype=torch.float32, device=gp.device)
+        ws = wsp.buf
+        _lib.check(_lib.lib().gb_predictor_input_grad(ctx.net.handle, ctx.g.handle, _ptr(gp), 0, _ptr(gz), _ptr(ws),
+                                                      ws.numel(), _stream()))
+        return gz, None, None, None, None
+
+
+def predictor_forward(pred_module, xh, node_mask, edge_mask, t) -> torch.Tensor:
+    """EGNN_predictor.forward (edm/egnn_predictor/models.py:433-457), differentiable w.r.t. ``xh``."""
+    _need_cuda(xh, "xh")
+    return _PredictorFn.apply(xh, pred_module, node_mask, edge_mask, t)
+
+
+def predictor_value_and_grad(pred_module, xh, node_mask, edge_mask, t, g_pred_row: torch.Tensor):
+    """(pred, d<g_pred_row, sum_b pred_b>/dxh) without autograd: the affine-target fast path."""
+    _need_cuda(xh, "xh")
+    B, N, D = xh.shape
+    net = predictor_handle(pred_module)
+    g = graph_for(node_mask, edge_mask, B, N)
+    z = _f32c(xh)
+    tt, per_mol = _time_tensor(t, B, xh.device)
+    out = torch.empty(B, pred_module.hyper["out_nf"], dtype=torch.float32, device=xh.device)
+    nbytes = _lib.lib().gb_predictor_workspace_bytes(net.handle, g.handle, 1)
+    wsp = workspace("pred_grad", xh.device)
+    ws = wsp.get(nbytes, xh.device)
+    wsp.generation += 1
+    L = _lib.lib()
+    _lib.check(L.gb_predictor_forward(net.handle, g.handle, _ptr(z), _ptr(tt), per_mol, _ptr(out), 1, _ptr(ws),
+                                      ws.numel(), _stream()))
+    gz = torch.empty_like(z)
+    w = _f32c(g_pred_row).reshape(-1)
+    _lib.check(L.gb_predictor_input_grad(net.handle, g.handle, _ptr(w), 1, _ptr(gz), _ptr(ws), ws.numel(), _stream()))
+    return out, gz
+
+
+# ---- step pieces -------------------------------------------------------------------------------------
+def step_sample(zt, eps, noise, coef, node_mask_flat, project: bool, seed: int = 0, draw: int = 0) -> torch.Tensor:
+    B, N, D = zt.shape
+    zs = torch.empty_like(zt)
+    _lib.check(_lib.lib().gb_step_sample(_ptr(zt), _ptr(eps), _ptr(noise), _ptr(coef), _ptr(node_mask_flat), B, N, D,
+                                         seed, draw, int(project), _ptr(zs), _stream()))
+    return zs
+
+
+def step_guide(zs_pre, grad, coef, node_mask_flat, max_norm: float = 10.0) -> torch.Tensor:
+    B, N, D = zs_pre.shape
+    zs = torch.empty_like(zs_pre)
+    _lib.check(_lib.lib().gb_step_guide(_ptr(zs_pre), _ptr(grad), _ptr(coef), _ptr(node_mask_flat), B, N, D,
+                                        float(max_norm), _ptr(zs), _stream()))
+    return zs
+
+
+def decode(z0, eps, noise, coef, node_mask_flat, norm_x, norm_h, bias_h, seed: int = 0, draw: int = 0):
+    B, N, D = z0.shape
+    x = torch.empty(B, N, 3, dtype=torch.float32, device=z0.device)
+    one_hot = torch.empty(B, N, D - 3, dtype=torch.float32, device=z0.device)
+    cog = torch.zeros(1, dtype=torch.float32, device=z0.device)
+    L = _lib.lib()
+    _lib.check(L.gb_decode(_ptr(z0), _ptr(eps), _ptr(noise), _ptr(coef), _ptr(node_mask_flat), B, N, D, seed, draw,
+                           float(norm_x), float(norm_h), float(bias_h), _ptr(x), _ptr(one_hot), _ptr(cog), _stream()))
+    return x, one_hot, cog
+
+
+def cog_fix(x, node_mask_flat, cog, thresh: float = 5e-2) -> None:
+    B, N, _ = x.shape
+    _lib.check(_lib.lib().gb_cog_fix(_ptr(x), _ptr(node_mask_flat), _ptr(cog), float(thresh), B, N, _stream()))
+
+
+def noise(node_mask_flat, B: int, N: int, D: int, std: float, seed: int, draw: int) -> torch.Tensor:
+    out = torch.empty(B, N, D, dtype=torch.float32, device=node_mask_flat.device)
+    _lib.check(_lib.lib().gb_noise(_ptr(out), _ptr(node_mask_flat), B, N, D, float(std), seed, draw, _stream()))
+    return out
+
+
+def sample_loop(dyn, pred_module, node_mask, edge_mask, z, T: int, s_hi: int, s_lo: int, sched, tvals,
+                target_w: Optional[torch.Tensor], noise_all: Optional[torch.Tensor], seed: int,
+                stats: Optional[torch.Tensor], use_graph: bool) -> None:
+    """In-place reverse diffusion of ``z`` over steps s_hi-1..s_lo (gb_sample_loop)."""
+    B, N, D = z.shape
+    den = denoiser_handle(dyn)
+    prd = predictor_handle(pred_module) if pred_module is not None else None
+    g = graph_for(node_mask, edge_mask, B, N)
+    L = _lib.lib()
+    nbytes = L.gb_sample_loop_workspace_bytes(den.handle, prd.handle if prd else _VP(0), g.handle)
+    ws = workspace("loop", z.device).get(nbytes, z.device)
+    _lib.check(L.gb_sample_loop(den.handle, prd.handle if prd else _VP(0), g.handle, _ptr(z), T, s_hi, s_lo,
+                                _ptr(sched), _ptr(tvals), _ptr(target_w), _ptr(noise_all), seed, _ptr(stats),
+                                _ptr(ws), ws.numel(), int(use_graph), _stream()))
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(_lib.lib().gb_launch_count(int(reset)))
+
+
+# ---- module-level forwards (sub-module API surface) -------------------------------------------------
+def _unsupported(name: str):
+    raise NotImplementedError(
+        f"gaudi_b200: stand-alone {name}.forward is not exposed; the fused kernels are reached through "
+        "EGNN_dynamics._forward / EGNN_predictor.forward (same parameters, same state_dict)")
+
+
+def gcl_forward(mod, h, edge_index, edge_attr, node_mask, edge_mask):
+    _unsupported("GCL")
+
+
+def equiv_update_forward(mod, h, coord, edge_index, coord_diff, edge_attr, node_mask, edge_mask):
+    _unsupported("EquivariantUpdate")
+
+
+def equiv_block_forward(mod, h, x, edge_index, node_mask, edge_mask, edge_attr):
+    _unsupported("EquivariantBlock")
+
+
+def egnn_forward(mod, h, x, edge_index, node_mask, edge_mask):
+    _unsupported("EGNN")
+
+
+def e_gcl_forward(mod, h, edge_index, coord, edge_attr, node_mask, edge_mask):
+    _unsupported("E_GCL")
+
+
+def pred_egnn_forward(mod, h, x, edges, edge_attr, node_mask, edge_mask):
+    _unsupported("EGNN (predictor)")

@@ -1,0 +1,125 @@
+/* gaudi_b200 -- C ABI of the B200-native guided-sampling hot path of GaUDI.
+ *
+ * The reference (tomer196/GaUDI) has no FFI: its boundary is the Python module API
+ * (SURVEY.md section 8b).  This header is the C boundary a maintainer would bind underneath that API
+ * (ctypes stub in INTEGRATION.md); every entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C types, raw DEVICE pointers (fp32 / int32) unless a parameter says "host"
+ *   - every function returns 0 on success, non-zero on error; gb_last_error() gives the thread-local message
+ *   - "setup" functions may allocate device memory and synchronise; "hot path" functions never allocate,
+ *     never synchronise, and only enqueue work on the given stream (CUDA-graph capturable)
+ *   - tensors are contiguous, row-major, with the reference's shapes:
+ *       z / eps / grad  [B, N, D]  D = 3 + F      node_mask [B*N]      t  one float, or B floats
+ *   - stream is a cudaStream_t passed as void*
+ */
+#ifndef GAUDI_B200_H
+#define GAUDI_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gb_net gb_net;       /* packed weights of one network (denoiser or predictor) */
+typedef struct gb_graph gb_graph;   /* compacted edge structure of one (node_mask, edge_mask) pair */
+
+int gb_abi_version(void);
+const char* gb_last_error(void);
+/* number of kernels launched by this library on the calling thread since the last reset (bench.py's gpu_launches) */
+long long gb_launch_count(int reset);
+
+/* ---- setup: networks --------------------------------------------------------------------------------
+ * params: host array of DEVICE pointers to the fp32 parameters in state_dict order, without the
+ * "buffer"/"gamma.gamma" entries.
+ * denoiser (EGNN_dynamics.egnn, edm/egnn/egnn_new.py:238-321):
+ *   embedding.{weight,bias}, embedding_out.{weight,bias}, then per e_block_i:
+ *     per gcl_s: edge_mlp.0.{w,b} edge_mlp.2.{w,b} node_mlp.0.{w,b} node_mlp.2.{w,b} [att_mlp.0.{w,b}]
+ *     gcl_equiv: coord_mlp.0.{w,b} coord_mlp.2.{w,b} coord_mlp.4.weight
+ * predictor (EGNN_predictor.egnn, edm/egnn_predictor/models.py:492-560):
+ *   embedding.{w,b}, embedding_out.{w,b}, then per gcl_i:
+ *     edge_mlp.0.{w,b} edge_mlp.2.{w,b} node_mlp.0.{w,b} node_mlp.2.{w,b} coord_mlp.0.{w,b} coord_mlp.2.weight [att_mlp.0.{w,b}]
+ */
+int gb_denoiser_create(gb_net** out, int in_node_nf, int hidden_nf, int n_layers, int inv_sublayers, int attention,
+                       int use_tanh, float coords_range, float norm_constant, float normalization_factor,
+                       const float* const* params, int n_params, void* stream);
+int gb_predictor_create(gb_net** out, int in_node_nf, int out_nf, int hidden_nf, int n_layers, int attention,
+                        int use_tanh, float coords_range, const float* const* params, int n_params, void* stream);
+int gb_net_destroy(gb_net* net);
+int gb_net_hidden_padded(const gb_net* net);
+
+/* ---- setup: graph topology (replaces get_adj_matrix, edm/egnn/models.py:154-175, and the per-call
+ * h[row]/h[col] index tensors).  All arrays are DEVICE int32, borrowed for the lifetime of the handle.
+ *   rowptr[n_nodes+1], erow/ecol[n_edges]: CSR of the edges with edge_mask != 0 in dense row-major order
+ *   tile_ptr[n_tiles+1]: node boundaries of GEMM tiles (<=128 edges and <=128 nodes each, see gb_tile_pack)
+ *   tc_ptr[n_tiles+1], tc_node[n_tc], tc_start[n_tc+1], cperm[n_edges]: each tile's edges grouped by column node */
+int gb_tile_pack(const int32_t* rowptr_host, int n_nodes, int32_t* tile_ptr_host_out, int* n_tiles_out);
+int gb_graph_create(gb_graph** out, int B, int N, int n_edges, int n_tiles, int n_tc, const int32_t* rowptr,
+                    const int32_t* erow, const int32_t* ecol, const int32_t* tile_ptr, const int32_t* tc_ptr,
+                    const int32_t* tc_node, const int32_t* tc_start, const int32_t* cperm, const float* node_mask);
+int gb_graph_destroy(gb_graph* g);
+
+/* ---- workspace sizes (bytes of device scratch the hot-path calls need) */
+size_t gb_denoiser_workspace_bytes(const gb_net* net, const gb_graph* g);
+size_t gb_predictor_workspace_bytes(const gb_net* net, const gb_graph* g, int with_grad);
+
+/* ---- hot path: networks ---------------------------------------------------------------------------------
+ * gb_denoiser_forward   EGNN_dynamics._forward (edm/egnn/models.py:83-152) = phi of en_diffusion.py:352-355.
+ *   scrub_all != 0 also applies the guided step's eps.nan_to_num(0.) (en_diffusion.py:881).
+ *   stats (nullable, 8 floats, atomic-max accumulated): [0] max|z_x| [1] max|sum_n z_x| [2] max|eps_x|
+ *   [3] max|sum_n eps_x| [4] max|z*(1-mask)| -- the quantities of assert_mean_zero_with_mask / assert_correctly_masked
+ *   (edm/equivariant_diffusion/utils.py:52-65), checked by the caller once after the loop.
+ * gb_predictor_forward  EGNN_predictor.forward (edm/egnn_predictor/models.py:433-457). save_for_grad keeps the
+ *   activations the input-gradient pass needs inside the workspace.
+ * gb_predictor_input_grad  d(sum_b <g_pred_b, pred_b>)/dz, replaces autograd.grad at en_diffusion.py:903.
+ *   g_pred is [B,out] (or [out] shared by all molecules when g_pred_broadcast != 0).  Must follow a
+ *   gb_predictor_forward(save_for_grad=1) on the same workspace. */
+int gb_denoiser_forward(const gb_net* net, const gb_graph* g, const float* z, const float* t, int t_per_mol,
+                        float* eps, int scrub_all, float* stats, void* workspace, size_t workspace_bytes, void* stream);
+int gb_predictor_forward(const gb_net* net, const gb_graph* g, const float* z, const float* t, int t_per_mol,
+                         float* pred, int save_for_grad, void* workspace, size_t workspace_bytes, void* stream);
+int gb_predictor_input_grad(const gb_net* net, const gb_graph* g, const float* g_pred, int g_pred_broadcast,
+                            float* g_z, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- hot path: reverse-diffusion step pieces --------------------------------------------------------------
+ * coef: 3 device floats of the step  {alpha_t|s, sigma2_t|s/alpha_t|s/sigma_t, sigma_t|s*sigma_s/sigma_t}
+ *       (en_diffusion.py:869-894), pre-computed by the caller with the reference's fp32 op order.
+ * noise: injected [B,N,D] tensor (already masked / centred, parity mode) or NULL -> Philox(seed, draw).
+ * gb_step_sample  zs = zt/coef[0] - coef[1]*eps + coef[2]*noise ; project != 0 removes the centre of gravity of the
+ *                 x part (sample_p_zs_given_zt, en_diffusion.py:831-851); project == 0 is the pre-guidance z_s (:888-897)
+ * gb_step_guide   clip(grad, 10) -> remove CoG -> zs = zs_pre - coef[2]*grad -> remove CoG -> nan_to_num (:905-934)
+ * gb_decode       sample_p_xh_given_z0 (:533-560): coef = {sigma_0, alpha_0, exp(0.5*gamma_0)}; writes x [B,N,3],
+ *                 one_hot [B,N,F] and atomically maxes |sum_n x| into cog_max (device float, nullable)
+ * gb_cog_fix      re-projects x when *cog_max > thresh (:1059-1065)
+ * gb_noise        sample_combined_position_feature_noise (:937-956) from Philox */
+int gb_step_sample(const float* zt, const float* eps, const float* noise, const float* coef, const float* node_mask,
+                   int B, int N, int D, unsigned long long seed, unsigned long long draw, int project, float* zs,
+                   void* stream);
+int gb_step_guide(const float* zs_pre, const float* grad, const float* coef, const float* node_mask, int B, int N,
+                  int D, float max_norm, float* zs, void* stream);
+int gb_decode(const float* z0, const float* eps, const float* noise, const float* coef, const float* node_mask, int B,
+              int N, int D, unsigned long long seed, unsigned long long draw, float norm_x, float norm_h, float bias_h,
+              float* x, float* one_hot, float* cog_max, void* stream);
+int gb_cog_fix(float* x, const float* node_mask, const float* cog_max, float thresh, int B, int N, void* stream);
+int gb_noise(float* out, const float* node_mask, int B, int N, int D, float std, unsigned long long seed,
+             unsigned long long draw, void* stream);
+
+/* ---- hot path: whole loop ----------------------------------------------------------------------------------
+ * gb_sample_loop  EnVariationalDiffusion.sample / sample_guidance (en_diffusion.py:958-1067) for steps
+ *   s = s_hi-1 ... s_lo (t = s+1), in place on z.  pred == NULL -> unguided.  Guidance target must be affine in the
+ *   predictor outputs: energy_b = <target_w, pred_b> (+const); target_w [out] already multiplied by `scale`.
+ *   sched: device [T][3] step coefficients; tvals: device [T+1] with tvals[k] = float(k)/T.
+ *   noise: NULL (Philox; draw index of step s is T - s) or injected [T+2,B,N,D] indexed the same way.
+ *   stats: nullable [T][8] per-step invariant maxima (see gb_denoiser_forward).
+ *   use_graph != 0 captures one step into a CUDA graph and replays it (launch-bound small batches). */
+int gb_sample_loop(const gb_net* den, const gb_net* pred, const gb_graph* g, float* z, int T, int s_hi, int s_lo,
+                   const float* sched, const float* tvals, const float* target_w, const float* noise,
+                   unsigned long long seed, float* stats, void* workspace, size_t workspace_bytes, int use_graph,
+                   void* stream);
+size_t gb_sample_loop_workspace_bytes(const gb_net* den, const gb_net* pred, const gb_graph* g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAUDI_B200_H */
