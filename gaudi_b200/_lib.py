@@ -44,6 +44,7 @@ SIGNATURES = {
     "gb_noise": (_I, [_P, _P, _I, _I, _I, _F, _U64, _U64, _P]),
     "gb_sample_loop": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _U64, _P, _P, _SZ, _I, _P]),
     "gb_sample_loop_workspace_bytes": (_SZ, [_P, _P, _P]),
+    "gb_profile_kernel": (_I, [_P, _P, _I, _I, _P, _SZ, _I, _P]),
 }
 
 

@@ -666,3 +666,64 @@ extern "C" int gb_sample_loop(const gb_net* den, const gb_net* pred, const gb_gr
     if (own_stream) cudaStreamDestroy(cs);
     return check_launch("sample_loop(graph)");
 }
+
+// ------------------------------------------------------------------------------------------------------
+// measurement aid: re-launch ONE kernel of the path `repeats` times on the workspace left behind by the last
+// forward / input-gradient call, so that bench.py can bracket exactly that kernel with CUDA events.
+//   which: 0 denoiser GCL edge kernel, 1 denoiser EquivariantUpdate edge kernel (workspace of gb_denoiser_forward)
+//          2 predictor edge forward (saving), 3 predictor edge backward, 4 node MLP first Linear (predictor
+//          workspace after gb_predictor_forward(save)+gb_predictor_input_grad)
+// ------------------------------------------------------------------------------------------------------
+extern "C" int gb_profile_kernel(const gb_net* n, const gb_graph* gg, int which, int layer, void* ws, size_t ws_bytes,
+                                 int repeats, void* stream) {
+    if (!n || !gg || !ws) return fail("null argument");
+    const Graph& g = gg->g;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (layer < 0 || layer >= n->L) return fail("bad layer");
+    if (which <= 1) {
+        if (n->kind != 0) return fail("which=0/1 need a denoiser handle");
+        Bump b(ws, ws_bytes); DenWs w; carve_den(b, n, g, w);
+        if (b.off > ws_bytes) return fail("workspace too small");
+        for (int r = 0; r < repeats; ++r) {
+            DenEdgeArgs a;
+            memset(&a, 0, sizeof(a));
+            a.g = g; a.P = w.P; a.attention = which == 0 ? n->attention : 0; a.use_tanh = n->use_tanh;
+            a.norm_constant = n->norm_constant; a.normf = n->normf; a.coords_range = n->coords_range;
+            a.x = w.x0; a.x0 = w.x0;
+            if (which == 0) {
+                const DenGcl& G = n->gcl[(size_t)layer * n->n_sub];
+                a.ext = n->p(G.e.l1_ext); a.wt2 = n->p(G.e.l2_wt); a.b2 = n->p(G.e.l2_b); a.vecw = n->p(G.att_w); a.att_b = G.att_b;
+                a.agg = w.agg;
+            } else {
+                const DenEquiv& E = n->eq[layer];
+                a.ext = n->p(E.c.l1_ext); a.wt2 = n->p(E.c.l2_wt); a.b2 = n->p(E.c.l2_b); a.vecw = n->p(E.last_w);
+                a.x_out = w.xb;
+            }
+            launch_den_edge(n->HP, which, a, s); GB_LAUNCHED(1);
+        }
+        return check_launch("profile den_edge");
+    }
+    if (n->kind != 1) return fail("which=2..4 need a predictor handle");
+    Bump b(ws, ws_bytes); PredWs w; carve_pred(b, n, g, true, w);
+    if (b.off > ws_bytes) return fail("workspace too small");
+    const PredLayer& Lr = n->pl[layer];
+    for (int r = 0; r < repeats; ++r) {
+        if (which == 2) {
+            PredEdgeArgs a = pred_edge_args(n, Lr, g, w, layer, true);
+            a.x_out = w.gx2;                 // scratch target: keep the saved coordinates of layer+1 intact
+            launch_pred_edge_fwd(n->HP, true, a, s);
+        } else if (which == 3) {
+            PredEdgeArgs e = pred_edge_args(n, Lr, g, w, layer, true);
+            e.w2_nt = n->p(Lr.e.l2_nt); e.wc_nt = n->p(Lr.c_nt);
+            e.g_agg = w.gcat + n->HP; e.ld_gagg = 2 * n->HP; e.g_xout = w.gx; e.g_Pa = w.gPa; e.g_Pb = w.gPb; e.g_x = w.gx2; e.g_attr = w.gattr;
+            launch_pred_edge_bwd(n->HP, e, s);
+        } else {
+            LinArgs a = lin_base(g.n_nodes);
+            a.A1 = w.h; a.lda1 = n->HP; a.K1 = n->HP; a.A2 = w.agg; a.lda2 = n->HP; a.K2 = n->HP;
+            a.wt = n->p(Lr.n.l1_wt); a.bias = n->p(Lr.n.l1_b); a.out = w.s; a.ldo = n->HP; a.epi = EPI_SILU;
+            launch_lin(n->HP, a, s);
+        }
+        GB_LAUNCHED(1);
+    }
+    return check_launch("profile pred kernel");
+}

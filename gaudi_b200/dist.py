@@ -1,0 +1,92 @@
+"""Multi-GPU: the molecule batch shards trivially (no op couples molecules).
+
+One process per GPU (``torch.distributed``, NCCL over NVLink on the GPU box, gloo in the CPU tests).  Each rank
+samples its contiguous chunk of ``nodesxsample`` with its own seed (``seed + rank``) and a single all-gather of the
+generated coordinates, one-hot ring types and node masks follows the loop; there is no per-step communication
+(the reference has no distributed sampling at all: ``MyDataParallel`` forwards ``sample_guidance`` to the bare
+module, models_edm.py:13-18).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as tdist
+
+
+def shard_bounds(total: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous, near-equal chunks [lo, hi) per rank; the first ``total % world`` ranks get one extra item."""
+    base, extra = divmod(total, world)
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def world() -> Tuple[int, int]:
+    if tdist.is_available() and tdist.is_initialized():
+        return tdist.get_rank(), tdist.get_world_size()
+    return 0, 1
+
+
+def gather_padded(t: torch.Tensor, counts: Sequence[int], pad_nodes: Optional[int] = None) -> torch.Tensor:
+    """all_gather of per-rank tensors [b_r, N_r, C] into [sum b_r, N_max, C] (zero padded) on every rank."""
+    rank, ws = world()
+    if ws == 1:
+        return t
+    bmax = max(counts)
+    nmax = pad_nodes if pad_nodes is not None else t.shape[1]
+    buf = t.new_zeros((bmax, nmax) + tuple(t.shape[2:]))
+    buf[: t.shape[0], : t.shape[1]] = t
+    outs = [torch.empty_like(buf) for _ in range(ws)]
+    tdist.all_gather(outs, buf.contiguous())
+    return torch.cat([o[:c] for o, c in zip(outs, counts)], dim=0)
+
+
+def sample_guidance_sharded(args, model, target_function, nodesxsample: torch.Tensor, scale=1.0, std=1.0,
+                            seed: int = 0, noise=None, sampler=None):
+    """``sampling_edm.sample_guidance`` over all ranks: returns the FULL (x, one_hot, node_mask) on every rank.
+
+    ``sampler`` defaults to ``gaudi_b200.sampling.sample_guidance``; ``noise`` (parity mode) is the injected
+    [T+2, B_total, N, D] tensor, sliced per rank.
+    """
+    from . import sampling
+    rank, ws = world()
+    bounds = shard_bounds(len(nodesxsample), ws)
+    lo, hi = bounds[rank]
+    counts = [b - a for a, b in bounds]
+    nmax_global = int(torch.as_tensor(nodesxsample).max().item())
+    local = nodesxsample[lo:hi]
+    fn = sampler or sampling.sample_guidance
+    if hi > lo:
+        inner = getattr(model, "module", model)
+        if noise is None:
+            inner.seed = int(seed) + rank
+        local_noise = None
+        if noise is not None:                         # padded to the local max the same way the masks are
+            nloc = int(local.max().item())
+            local_noise = noise[:, lo:hi, :nloc].contiguous()
+        x, one_hot, node_mask, _ = fn(args, model, target_function, local, scale=scale, std=std, noise=local_noise)
+    else:
+        dev = args.device
+        x = torch.zeros(0, 1, 3, device=dev); one_hot = torch.zeros(0, 1, 1, device=dev); node_mask = torch.zeros(0, 1, 1, device=dev)
+    orient = 2 if args.dataset != "cata" else 1
+    pad = nmax_global * orient
+    if orient == 2 and x.shape[1] != pad and x.shape[0] > 0:
+        # ring nodes then orientation nodes: re-pad each half separately
+        h = x.shape[1] // 2
+        def repad(t):
+            out = t.new_zeros((t.shape[0], pad) + tuple(t.shape[2:]))
+            out[:, :h] = t[:, :h]; out[:, nmax_global:nmax_global + h] = t[:, h:]
+            return out
+        x, one_hot, node_mask = repad(x), repad(one_hot), repad(node_mask)
+    F = one_hot.shape[2]
+    if ws > 1:                                        # empty ranks must still agree on the feature width
+        ft = torch.tensor([F], device=x.device)
+        tdist.all_reduce(ft, op=tdist.ReduceOp.MAX)
+        F = int(ft.item())
+        if one_hot.shape[0] == 0:
+            one_hot = one_hot.new_zeros(0, 1, F)
+    return (gather_padded(x, counts, pad), gather_padded(one_hot, counts, pad), gather_padded(node_mask, counts, pad))

@@ -119,6 +119,12 @@ int gb_sample_loop(const gb_net* den, const gb_net* pred, const gb_graph* g, flo
                    void* stream);
 size_t gb_sample_loop_workspace_bytes(const gb_net* den, const gb_net* pred, const gb_graph* g);
 
+/* ---- measurement aid (bench.py roofline leg): re-launch ONE kernel `repeats` times on the workspace left by the
+ * last forward / input-gradient call.  which: 0 denoiser GCL edge, 1 denoiser EquivariantUpdate edge (denoiser
+ * workspace); 2 predictor edge forward, 3 predictor edge backward, 4 node-MLP Linear (predictor grad workspace). */
+int gb_profile_kernel(const gb_net* net, const gb_graph* g, int which, int layer, void* workspace,
+                      size_t workspace_bytes, int repeats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
