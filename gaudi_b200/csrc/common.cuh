@@ -18,6 +18,7 @@
 #define GB_MS 132        // smem stride of one k-row of the A tile (floats)
 #define GB_KC 16         // k-rows of Wt per pipeline stage
 #define GB_STAGES 4
+#define GB_FFMA2 1       // packed fma.rn.f32x2 in the tile GEMM (halves FP32 issue slots; same IEEE fma per lane)
 
 namespace gb {
 
@@ -35,6 +36,18 @@ __device__ __forceinline__ void silu_both(float x, float& y, float& dy) {
     float s = sigmoid_f(x);
     y = x * s;
     dy = s * (1.f + x * (1.f - s));
+}
+
+// packed FP32 FMA (sm_100+ FFMA2): (d0,d1) += (a,a) * (b0,b1) in one issue slot
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%2, %2};\n\t"
+        "mov.b64 rb, {%3, %4};\n\t"
+        "mov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(d0), "+f"(d1)
+        : "f"(a), "f"(b0), "f"(b1));
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -113,7 +126,11 @@ __device__ __forceinline__ void gemm_consume(const float* __restrict__ A_s, int 
         mbar_wait(&pipe.full[slot], round & 1);
         const float* w_base = pipe.ring + (size_t)slot * GB_KC * HP + warp * CW;
         if (rows == GB_KC) {
-#pragma unroll
+#ifndef GB_GEMM_UNROLL
+#define GB_GEMM_UNROLL 16
+#endif
+            constexpr int kUnroll = GB_GEMM_UNROLL;
+#pragma unroll kUnroll
             for (int kk = 0; kk < GB_KC; ++kk) {
                 const float4 a = *reinterpret_cast<const float4*>(a_base + (k0 + kk) * GB_MS);
                 float b[CW];
@@ -122,6 +139,15 @@ __device__ __forceinline__ void gemm_consume(const float* __restrict__ A_s, int 
                     const float4 t = *reinterpret_cast<const float4*>(w_base + kk * HP + c);
                     b[c] = t.x; b[c + 1] = t.y; b[c + 2] = t.z; b[c + 3] = t.w;
                 }
+#ifdef GB_FFMA2
+#pragma unroll
+                for (int c = 0; c < CW; c += 2) {
+                    ffma2(acc[0][c], acc[0][c + 1], a.x, b[c], b[c + 1]);
+                    ffma2(acc[1][c], acc[1][c + 1], a.y, b[c], b[c + 1]);
+                    ffma2(acc[2][c], acc[2][c + 1], a.z, b[c], b[c + 1]);
+                    ffma2(acc[3][c], acc[3][c + 1], a.w, b[c], b[c + 1]);
+                }
+#else
 #pragma unroll
                 for (int c = 0; c < CW; ++c) {
                     acc[0][c] = fmaf(a.x, b[c], acc[0][c]);
@@ -129,6 +155,7 @@ __device__ __forceinline__ void gemm_consume(const float* __restrict__ A_s, int 
                     acc[2][c] = fmaf(a.z, b[c], acc[2][c]);
                     acc[3][c] = fmaf(a.w, b[c], acc[3][c]);
                 }
+#endif
             }
         } else {
             for (int kk = 0; kk < rows; ++kk) {
