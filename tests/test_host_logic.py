@@ -1,0 +1,253 @@
+"""CPU tests of the host-side logic: masks, compacted topology, tiling, C-ABI symbol export, module surface,
+schedule table, affine targets, batch sharding (gloo, world_size 2).  No kernel is launched here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import gaudi_b200 as gb
+import gaudi_oracle as O
+from gaudi_b200 import _lib, dist, graph
+from helpers import META, build_models, golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- masks ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ds", ["cata", "hetro"])
+def test_build_masks_bit_exact_vs_reference(ds):
+    g = golden(f"masks_{ds}.npz")
+    nx = torch.from_numpy(g["nodesxsample"])
+    nm, em = gb.build_masks(nx, int(nx.max()), ds != "cata")
+    assert nm.dtype == torch.float32 and em.dtype == torch.float32
+    assert torch.equal(nm, torch.from_numpy(g["node_mask"]))
+    assert torch.equal(em, torch.from_numpy(g["edge_mask"]))
+
+
+def test_node2edge_mask_matches_oracle_for_ragged_sizes():
+    nx = torch.tensor([1, 2, 5, 11, 3])
+    nm_o, em_o = O.build_masks(nx, 11, False)
+    em = gb.node2edge_mask(nm_o.squeeze(2))
+    assert torch.equal(em.reshape(-1, 1), em_o)
+
+
+# ---- topology ---------------------------------------------------------------------------------------------------
+def _numpy_topology(nm, em, B, N):
+    em = em.reshape(B * N, N).numpy()
+    rows, cols = [], []
+    rowptr = [0]
+    for node in range(B * N):
+        for j in range(N):
+            if em[node, j] != 0:
+                rows.append(node)
+                cols.append((node // N) * N + j)
+        rowptr.append(len(rows))
+    return np.array(rowptr), np.array(rows), np.array(cols)
+
+
+@pytest.mark.parametrize("ds,sizes", [("cata", [11, 10, 9, 11, 7, 2, 1]), ("hetro", [10, 8, 10, 3, 1, 9, 9, 10])])
+def test_topology_matches_numpy_restatement_and_invariants(ds, sizes):
+    nx = torch.tensor(sizes)
+    nm, em = gb.build_masks(nx, int(nx.max()), ds != "cata")
+    B, N = nm.shape[0], nm.shape[1]
+    t = graph.build_topology(nm, em, B, N)
+    rowptr, rows, cols = _numpy_topology(nm, em, B, N)
+    assert np.array_equal(t.rowptr.numpy(), rowptr)
+    assert np.array_equal(t.erow.numpy(), rows) and np.array_equal(t.ecol.numpy(), cols)
+    assert t.n_edges == len(rows) == int(em.sum())
+    # same order as the reference's dense edge list restricted to edge_mask != 0
+    r_all, c_all = O.dense_edges(B, N)
+    keep = em.reshape(-1) != 0
+    assert np.array_equal(r_all[keep].numpy(), rows) and np.array_equal(c_all[keep].numpy(), cols)
+    tp = t.tile_ptr.numpy()
+    assert tp[0] == 0 and tp[-1] == B * N and np.all(np.diff(tp) > 0)
+    for a, b in zip(tp[:-1], tp[1:]):
+        assert rowptr[b] - rowptr[a] <= graph.TILE and b - a <= graph.TILE
+    # column grouping: every tile's cperm is a permutation of its local rows, grouped by ascending column node
+    tc_ptr, tc_node, tc_start, cperm = (x.numpy() for x in (t.tc_ptr, t.tc_node, t.tc_start, t.cperm))
+    assert tc_start[-1] == t.n_edges
+    for ti, (a, b) in enumerate(zip(tp[:-1], tp[1:])):
+        e0, e1 = rowptr[a], rowptr[b]
+        assert sorted(cperm[e0:e1].tolist()) == list(range(e1 - e0))
+        seen = 0
+        for k in range(tc_ptr[ti], tc_ptr[ti + 1]):
+            p0, p1 = tc_start[k], tc_start[k + 1]
+            assert p0 == e0 + seen
+            assert np.all(cols[e0 + cperm[p0:p1]] == tc_node[k])
+            seen += p1 - p0
+        assert seen == e1 - e0
+        nodes = tc_node[tc_ptr[ti]:tc_ptr[ti + 1]]
+        assert np.all(np.diff(nodes) > 0)
+
+
+def test_tile_pack_edge_cases():
+    assert graph.tile_pack(np.array([0], dtype=np.int32)).tolist() == [0]                       # empty batch
+    assert graph.tile_pack(np.array([0, 0, 0, 0], dtype=np.int32)).tolist() == [0, 3]          # nodes without edges
+    rp = np.arange(0, 129 * 100 + 1, 100, dtype=np.int32)                                        # 100 edges per node
+    tp = graph.tile_pack(rp)
+    assert np.all(np.diff(tp) == 1)
+    with pytest.raises(_lib.GaudiB200Error):
+        graph.tile_pack(np.array([0, 129], dtype=np.int32))                                      # a row segment cannot be split
+    many = np.zeros(1000, dtype=np.int32)                                                        # 999 empty nodes: <=128 nodes per tile
+    assert np.all(np.diff(graph.tile_pack(many)) <= 128)
+
+
+def test_non_binary_edge_mask_is_rejected():
+    nm, em = gb.build_masks(torch.tensor([3, 2]), 3, False)
+    with pytest.raises(ValueError):
+        graph.build_topology(nm, em * 0.5, 2, 3)
+
+
+# ---- C ABI ----------------------------------------------------------------------------------------------------------
+def test_library_exports_every_symbol_declared_in_the_header():
+    header = open(os.path.join(ROOT, "include", "gaudi_b200.h")).read()
+    declared = set(re.findall(r"\b(gb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/gaudi_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.gb_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (gb_[a-z0-9_]+)", out))
+    assert declared <= exported
+
+
+def test_compute_paths_fail_loudly_without_cuda():
+    args, model, pred, prop = build_models("cata", "cpu", hidden=(64, 64), layers=(1, 1))
+    nm, em = gb.build_masks(torch.tensor([3, 2]), 3, False)
+    z = torch.zeros(2, 3, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.phi(z, torch.zeros(1), nm, em, None)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pred(z, nm, em, torch.zeros(1))
+    assert "oracle" not in "".join(sys.modules[m].__file__ or "" for m in list(sys.modules) if m.startswith("gaudi_b200."))
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "gaudi_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "gaudi_oracle" not in src and "oracle/" not in src, f
+
+
+# ---- module surface -----------------------------------------------------------------------------------------------------
+def test_module_signatures_and_checkpoint_prefix_round_trip(tmp_path):
+    a = gb.args_edm(device="cpu", dp=True, nf=64, n_layers=2)
+    from argparse import Namespace
+    ds = Namespace(num_node_features=1, num_targets=5, mean=torch.zeros(5), std=torch.ones(5))
+    model, nodes_dist, prop = gb.get_model(a, Namespace(dataset=ds))
+    assert isinstance(model, gb.MyDataParallel)
+    keys = list(model.state_dict())
+    assert keys[0] == "module.buffer" and keys[1] == "module.gamma.gamma"
+    assert "module.dynamics.egnn.e_block_0.gcl_0.edge_mlp.0.weight" in keys
+    assert model.state_dict()["module.dynamics.egnn.e_block_0.gcl_0.edge_mlp.0.weight"].shape == (64, 130)
+    assert model.state_dict()["module.gamma.gamma"].shape == (1001,)
+    torch.save(model.state_dict(), tmp_path / "model.pt")
+    a2 = gb.args_edm(device="cpu", dp=False, nf=64, n_layers=2, restore=True, exp_dir=str(tmp_path))
+    bare, _, _ = gb.get_model(a2, Namespace(dataset=ds))
+    assert torch.equal(bare.dynamics.egnn.embedding.weight, model.module.dynamics.egnn.embedding.weight)
+    assert callable(model.sample) and callable(model.sample_guidance)        # resolved through __getattr__
+    p = gb.get_cond_predictor_model(gb.prediction_args(device="cpu", dp=False, nf=64, n_layers=2), ds)
+    assert list(p.state_dict())[:2] == ["egnn.embedding.weight", "egnn.embedding.bias"]
+    assert p.egnn.gcl_0.coords_range == 4.0 / 2
+    assert int(nodes_dist.sample(5).max()) <= 11
+
+
+def test_unsupported_configurations_raise():
+    with pytest.raises(NotImplementedError):
+        gb.EGNN_dynamics(in_node_nf=1, mode="gnn_dynamics")
+    with pytest.raises(NotImplementedError):
+        gb.GCL(8, 8, 8, 1.0, "mean")
+    with pytest.raises(ValueError):
+        gb.PredefinedNoiseSchedule("linear", 10, 1e-5)
+    with pytest.raises(ValueError):                       # check_issues_norm_values (en_diffusion.py:336-350)
+        dyn = gb.EGNN_dynamics(in_node_nf=1, hidden_nf=8, n_layers=1)
+        gb.EnVariationalDiffusion(dyn, 1, 3, noise_schedule="polynomial_2", noise_precision=1e-2, loss_type="l2",
+                                  norm_values=(1.0, 100.0, 1.0), include_charges=False)
+
+
+def test_schedule_table_matches_oracle_bitwise():
+    args, model, pred, prop = build_models("cata", "cpu", hidden=(64, 64), layers=(1, 1))
+    sched, tvals, dec = model._tables(torch.device("cpu"))
+    gamma = O.polynomial_gamma(1000, 1e-5, 2.0)
+    assert torch.equal(model.gamma.gamma.detach(), gamma)
+    for s in (0, 1, 499, 998, 999):
+        sc = O.step_scalars(gamma, s)
+        assert torch.equal(sched[s], torch.stack([sc["alpha_ts"], sc["eps_coef"], sc["sigma"]]))
+        assert float(tvals[s + 1]) == float(O.time_value(s + 1, 1000))
+    assert float(dec[2]) == float(torch.exp(-(-0.5 * gamma[0])))
+
+
+def test_affine_target_weights_reproduce_the_reference_closures():
+    class FakePred:
+        hyper = {"out_nf": 5}
+
+        def __call__(self, z, nm, em, t):
+            return z
+    prop = gb.DistributionProperty(META["prop_mean"], META["prop_std"])
+    p = torch.randn(7, 5)
+    assert torch.allclose(gb.AffineTarget.max_gap(FakePred())(p, None, None, None), -p[:, 1])
+    q = prop.unnormalize(p)
+    assert torch.allclose(gb.AffineTarget.opv(FakePred(), prop)(p, None, None, None), q[:, 3] + q[:, 2] + 3 * q[:, 0], atol=1e-6)
+
+
+# ---- sharding ---------------------------------------------------------------------------------------------------------------
+def test_shard_bounds_cover_and_balance():
+    for total in (0, 1, 7, 8, 100000):
+        for world in (1, 2, 3, 8):
+            b = dist.shard_bounds(total, world)
+            assert b[0][0] == 0 and b[-1][1] == total and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as tdist
+sys.path.insert(0, os.environ["GB_ROOT"])
+import gaudi_b200 as gb
+from gaudi_b200 import dist
+tdist.init_process_group("gloo")
+rank, ws = tdist.get_rank(), tdist.get_world_size()
+args = gb.args_edm(device="cpu", dataset=os.environ["GB_DS"])
+nx = torch.tensor([3, 2, 4, 1, 2])
+calls = []
+def fake_sampler(args, model, tf, local, scale=1, std=1.0, noise=None):
+    nm, em = gb.build_masks(local, int(local.max()), args.dataset != "cata")
+    x = nm.repeat(1, 1, 3) * (100.0 * rank + local.view(-1, 1, 1).float())
+    oh = nm.repeat(1, 1, 2)
+    calls.append(len(local))
+    return x, oh, nm, em
+class M: seed = None
+m = M()
+x, oh, nm = dist.sample_guidance_sharded(args, m, None, nx, seed=7, sampler=fake_sampler)
+mult = 2 if args.dataset != "cata" else 1
+assert x.shape == (5, 4 * mult, 3) and oh.shape == (5, 4 * mult, 2) and nm.shape == (5, 4 * mult, 1), (x.shape, oh.shape)
+assert m.seed == 7 + rank
+lo, hi = dist.shard_bounds(5, ws)[rank]
+assert calls == [hi - lo]
+ref_nm, _ = gb.build_masks(nx, 4, args.dataset != "cata")
+assert torch.equal(nm, ref_nm), "gathered node masks must equal the single-process masks"
+owner = torch.tensor([0, 0, 0, 1, 1]) if ws == 2 else torch.zeros(5)
+assert torch.equal(x[:, 0, 0], 100.0 * owner + nx.float())
+tdist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+@pytest.mark.parametrize("ds", ["cata", "hetro"])
+def test_sharded_sampling_gathers_full_batch_world_size_2(tmp_path, ds):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, GB_ROOT=ROOT, GB_DS=ds, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533" if ds == "cata" else "29534")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", env["MASTER_PORT"], str(script)],
+                         env=env, capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert res.stdout.count("ok") == 2
