@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -53,16 +54,18 @@ extern "C" long long gb_launch_count(int reset) {
 struct EdgeMlpW {           // first Linear factorised per node (2 column blocks), second Linear packed^T
     size_t l1_wt, l1_b, l1_ext, l2_wt, l2_b;
     size_t l1_nt, l2_nt;    // un-transposed copies for the input-gradient pass (predictor only)
+    size_t l1_tc, l2_tc, l1_nt_tc, l2_nt_tc;   // tensor-core images of the same blocks
 };
-struct NodeMlpW { size_t l1_wt, l1_b, l2_wt, l2_b, l1_nt, l2_nt; };
+struct NodeMlpW { size_t l1_wt, l1_b, l2_wt, l2_b, l1_nt, l2_nt, l1_tc, l2_tc, l1_nt_tc, l2_nt_tc; };
 struct DenGcl { EdgeMlpW e; NodeMlpW n; size_t att_w; float att_b; };
 struct DenEquiv { EdgeMlpW c; size_t last_w; };
-struct PredLayer { EdgeMlpW e; NodeMlpW n; size_t att_w; float att_b; size_t c_wt, c_b, c_nt, c_last; };
+struct PredLayer { EdgeMlpW e; NodeMlpW n; size_t att_w; float att_b; size_t c_wt, c_b, c_nt, c_last, c_tc, c_nt_tc; };
 
 struct gb_net {
     int kind;               // 0 denoiser, 1 predictor
     int F, H, HP, L, n_sub, out_nf, attention, use_tanh;
     float coords_range, norm_constant, normf;
+    int tc_lin = 0, tc_den = 0, tc_pred = 0;   // which kernel families run on tcgen05 (GAUDI_B200_GEMM)
     float* buf = nullptr;
     size_t n_floats = 0;
     size_t emb_w, emb_b, out_w, out_b;      // raw (unpacked) small heads
@@ -103,6 +106,24 @@ struct Packer {
         pack_at(o + sz, w, ld, k1, n1, Kv, Nv, Kp, transpose);
         return o;
     }
+    // tensor-core image of ONE [Nv x Kv] block: atoms(Kv) x [hi|lo][NP][32]
+    size_t tc_size(int K) const { return (size_t)((K + 31) / 32) * 2 * tc_np(net->HP) * 32; }
+    void tc_at(size_t dst, const float* w, int ld, int k_off, int n_off, int Kv, int Nv, int Kp, int transpose) {
+        if (!dry) { launch_pack_tc(net->buf + dst, w, ld, k_off, n_off, Kv, Nv, tc_np(net->HP), (Kp + 31) / 32, transpose, s); GB_LAUNCHED(1); }
+    }
+    // transpose==1: forward use (k = input column, n = output row); 0: dgrad use (k = output row, n = input column)
+    size_t tc_block(const float* w, int ld, int k_off, int n_off, int Kv, int Nv, int transpose) {
+        size_t o = take(tc_size(net->HP));
+        tc_at(o, w, ld, transpose ? k_off : k_off, n_off, Kv, Nv, net->HP, transpose ? 0 : 1);
+        return o;
+    }
+    size_t tc_block2(const float* w, int ld, int k0, int n0, int k1, int n1, int Kv, int Nv, int transpose) {
+        const size_t sz = tc_size(net->HP);
+        size_t o = take(2 * sz);
+        tc_at(o, w, ld, k0, n0, Kv, Nv, net->HP, transpose ? 0 : 1);
+        tc_at(o + sz, w, ld, k1, n1, Kv, Nv, net->HP, transpose ? 0 : 1);
+        return o;
+    }
     size_t vec(const float* v, int n, int np) {      // zero-padded copy of a vector
         size_t o = take(np);
         if (!dry) {
@@ -115,6 +136,7 @@ struct Packer {
     void edge_l1(EdgeMlpW& e, const float* w, const float* b, bool want_nt) {
         const int H = net->H, HP = net->HP, ld = 2 * H + 2;
         e.l1_wt = block2(w, ld, 0, 0, H, 0, H, H, HP, 1);      // column blocks W_a^T | W_b^T
+        e.l1_tc = tc_block2(w, ld, 0, 0, H, 0, H, H, 1);
         e.l1_b = vec(b, H, 2 * HP);                            // (b | 0)
         e.l1_ext = take(2 * HP);
         if (!dry) {
@@ -126,23 +148,28 @@ struct Packer {
         e.l1_nt = 0;
         if (want_nt) {                                          // [2HP][HP]: rows = output index, W_a then W_b
             e.l1_nt = block2(w, ld, 0, 0, 0, H, H, H, HP, 0);
+            e.l1_nt_tc = tc_block2(w, ld, 0, 0, 0, H, H, H, 0);
         }
     }
-    void square(size_t& wt, size_t& bias, size_t* nt, const float* w, const float* b) {
+    void square(size_t& wt, size_t& bias, size_t* nt, const float* w, const float* b, size_t* tcw = nullptr, size_t* tcnt = nullptr) {
         const int H = net->H, HP = net->HP;
         wt = block(w, H, 0, 0, H, H, HP, 1);
         bias = vec(b, H, HP);
         if (nt) *nt = block(w, H, 0, 0, H, H, HP, 0);
+        if (tcw) *tcw = tc_block(w, H, 0, 0, H, H, 1);
+        if (tcnt) *tcnt = tc_block(w, H, 0, 0, H, H, 0);
     }
     void node_mlp(NodeMlpW& n, const float* w1, const float* b1, const float* w2, const float* b2, bool want_nt) {
         const int H = net->H, HP = net->HP;
         n.l1_wt = block2(w1, 2 * H, 0, 0, H, 0, H, H, HP, 1);   // rows k<HP: h part, rows HP..2HP: agg part
+        n.l1_tc = tc_block2(w1, 2 * H, 0, 0, H, 0, H, H, 1);
         n.l1_b = vec(b1, H, HP);
         n.l1_nt = 0; n.l2_nt = 0;
         if (want_nt) {                                           // two column blocks [HP][HP]: W[:, :H], W[:, H:]
             n.l1_nt = block2(w1, 2 * H, 0, 0, 0, H, H, H, HP, 0);
+            n.l1_nt_tc = tc_block2(w1, 2 * H, 0, 0, 0, H, H, H, 0);
         }
-        square(n.l2_wt, n.l2_b, want_nt ? &n.l2_nt : nullptr, w2, b2);
+        square(n.l2_wt, n.l2_b, want_nt ? &n.l2_nt : nullptr, w2, b2, &n.l2_tc, want_nt ? &n.l2_nt_tc : nullptr);
     }
 };
 
@@ -153,7 +180,24 @@ int read_scalar(const float* dev, float* out, cudaStream_t s) {
 }
 }  // namespace
 
+static void parse_gemm_mode(gb_net* net) {
+    // GAUDI_B200_GEMM = "tc" (default: every converted kernel family on tcgen05) | "fp32" | comma list of lin,den,pred
+    const char* e = getenv("GAUDI_B200_GEMM");
+    std::string m = e ? e : "tc";
+    const bool all = (m == "tc" || m == "all");
+    net->tc_lin = all || m.find("lin") != std::string::npos;
+    net->tc_den = all || m.find("den") != std::string::npos;
+    net->tc_pred = all || m.find("pred") != std::string::npos;
+    if (m == "fp32") net->tc_lin = net->tc_den = net->tc_pred = 0;
+}
+
+static void run_lin(const gb_net* n, LinArgs& a, cudaStream_t s) {
+    if (n->tc_lin && a.wt_tc) launch_lin_tc(n->HP, a, a.wt_tc, s);
+    else launch_lin(n->HP, a, s);
+}
+
 static int build_net(gb_net* net, const float* const* P, int n_params, cudaStream_t s) {
+    parse_gemm_mode(net);
     const int H = net->H;
     for (int pass = 0; pass < 2; ++pass) {
         Packer pk{net, s};
@@ -172,7 +216,7 @@ static int build_net(gb_net* net, const float* const* P, int n_params, cudaStrea
                 for (int q = 0; q < net->n_sub; ++q) {
                     DenGcl& G = net->gcl[(size_t)b * net->n_sub + q];
                     pk.edge_l1(G.e, P[i], P[i + 1], false);
-                    pk.square(G.e.l2_wt, G.e.l2_b, nullptr, P[i + 2], P[i + 3]);
+                    pk.square(G.e.l2_wt, G.e.l2_b, nullptr, P[i + 2], P[i + 3], &G.e.l2_tc);
                     pk.node_mlp(G.n, P[i + 4], P[i + 5], P[i + 6], P[i + 7], false);
                     i += 8;
                     if (net->attention) {
@@ -183,7 +227,7 @@ static int build_net(gb_net* net, const float* const* P, int n_params, cudaStrea
                 }
                 DenEquiv& E = net->eq[b];
                 pk.edge_l1(E.c, P[i], P[i + 1], false);
-                pk.square(E.c.l2_wt, E.c.l2_b, nullptr, P[i + 2], P[i + 3]);
+                pk.square(E.c.l2_wt, E.c.l2_b, nullptr, P[i + 2], P[i + 3], &E.c.l2_tc);
                 E.last_w = pk.vec(P[i + 4], H, net->HP);
                 i += 5;
             }
@@ -192,9 +236,9 @@ static int build_net(gb_net* net, const float* const* P, int n_params, cudaStrea
             for (int l = 0; l < net->L; ++l) {
                 PredLayer& Lr = net->pl[l];
                 pk.edge_l1(Lr.e, P[i], P[i + 1], true);
-                pk.square(Lr.e.l2_wt, Lr.e.l2_b, &Lr.e.l2_nt, P[i + 2], P[i + 3]);
+                pk.square(Lr.e.l2_wt, Lr.e.l2_b, &Lr.e.l2_nt, P[i + 2], P[i + 3], &Lr.e.l2_tc, &Lr.e.l2_nt_tc);
                 pk.node_mlp(Lr.n, P[i + 4], P[i + 5], P[i + 6], P[i + 7], true);
-                pk.square(Lr.c_wt, Lr.c_b, &Lr.c_nt, P[i + 8], P[i + 9]);
+                pk.square(Lr.c_wt, Lr.c_b, &Lr.c_nt, P[i + 8], P[i + 9], &Lr.c_tc, &Lr.c_nt_tc);
                 Lr.c_last = pk.vec(P[i + 10], H, net->HP);
                 i += 11;
                 if (net->attention) {
@@ -356,22 +400,22 @@ static LinArgs lin_base(int M) {
 // P = h @ [W_a^T | W_b^T] + (b | 0)
 static void lin_P(const gb_net* n, const EdgeMlpW& e, const float* h, float* P, int M, cudaStream_t s) {
     LinArgs a = lin_base(M);
-    a.A1 = h; a.lda1 = n->HP; a.K1 = n->HP; a.wt = n->p(e.l1_wt); a.bias = n->p(e.l1_b);
+    a.A1 = h; a.lda1 = n->HP; a.K1 = n->HP; a.wt = n->p(e.l1_wt); a.wt_tc = n->p(e.l1_tc); a.bias = n->p(e.l1_b);
     a.out = P; a.ldo = 2 * n->HP; a.ncb = 2;
-    launch_lin(n->HP, a, s); GB_LAUNCHED(1);
+    run_lin(n, a, s); GB_LAUNCHED(1);
 }
 // h_new = (h + W2 SiLU(W1 [h, agg] + b1) + b2) * mask ; optionally keeps the pre-activation
 static void node_update(const gb_net* n, const NodeMlpW& w, const float* h, const float* agg, float* hid, float* h_new,
                         float* pre_save, const Graph& g, cudaStream_t s) {
     LinArgs a = lin_base(g.n_nodes);
     a.A1 = h; a.lda1 = n->HP; a.K1 = n->HP; a.A2 = agg; a.lda2 = n->HP; a.K2 = n->HP;
-    a.wt = n->p(w.l1_wt); a.bias = n->p(w.l1_b); a.out = hid; a.ldo = n->HP; a.epi = EPI_SILU;
+    a.wt = n->p(w.l1_wt); a.wt_tc = n->p(w.l1_tc); a.bias = n->p(w.l1_b); a.out = hid; a.ldo = n->HP; a.epi = EPI_SILU;
     a.out2 = pre_save; a.ldo2 = n->HP;
-    launch_lin(n->HP, a, s);
+    run_lin(n, a, s);
     LinArgs c = lin_base(g.n_nodes);
-    c.A1 = hid; c.lda1 = n->HP; c.K1 = n->HP; c.wt = n->p(w.l2_wt); c.bias = n->p(w.l2_b);
+    c.A1 = hid; c.lda1 = n->HP; c.K1 = n->HP; c.wt = n->p(w.l2_wt); c.wt_tc = n->p(w.l2_tc); c.bias = n->p(w.l2_b);
     c.out = h_new; c.ldo = n->HP; c.epi = EPI_RES_MASK; c.res = h; c.ldr = n->HP; c.mask = g.node_mask;
-    launch_lin(n->HP, c, s);
+    run_lin(n, c, s);
     GB_LAUNCHED(2);
 }
 
@@ -399,7 +443,8 @@ static int denoiser_forward_impl(const gb_net* n, const Graph& g, const float* z
             a.vecw = n->p(G.att_w); a.att_b = G.att_b; a.attention = n->attention; a.use_tanh = n->use_tanh;
             a.norm_constant = n->norm_constant; a.normf = n->normf; a.coords_range = n->coords_range;
             a.x = xc; a.x0 = w.x0; a.agg = w.agg;
-            launch_den_edge(n->HP, 0, a, s); GB_LAUNCHED(1);
+            if (n->tc_den) launch_den_edge_tc(n->HP, 0, a, n->p(G.e.l2_tc), s); else launch_den_edge(n->HP, 0, a, s);
+            GB_LAUNCHED(1);
             node_update(n, G.n, h, w.agg, w.s, h2, nullptr, g, s);
             float* tmp = h; h = h2; h2 = tmp;
             const EdgeMlpW& next = (q + 1 < n->n_sub) ? n->gcl[(size_t)blk * n->n_sub + q + 1].e : n->eq[blk].c;
@@ -412,7 +457,8 @@ static int denoiser_forward_impl(const gb_net* n, const Graph& g, const float* z
         a.vecw = n->p(E.last_w); a.attention = 0; a.use_tanh = n->use_tanh;
         a.norm_constant = n->norm_constant; a.normf = n->normf; a.coords_range = n->coords_range;
         a.x = xc; a.x0 = w.x0; a.x_out = xn;
-        launch_den_edge(n->HP, 1, a, s); GB_LAUNCHED(1);
+        if (n->tc_den) launch_den_edge_tc(n->HP, 1, a, n->p(E.c.l2_tc), s); else launch_den_edge(n->HP, 1, a, s);
+        GB_LAUNCHED(1);
         xc = xn; xn = (xn == w.xa) ? w.xb : w.xa;
         if (blk + 1 < n->L) lin_P(n, n->gcl[(size_t)(blk + 1) * n->n_sub].e, h, w.P, g.n_nodes, s);
     }
@@ -508,14 +554,14 @@ static int predictor_grad_impl(const gb_net* n, const Graph& g, const float* g_p
         const PredLayer& Lr = n->pl[l];
         // g_pre4 = ((gh*mask) W4) * SiLU'(pre4)
         LinArgs a = lin_base(g.n_nodes);
-        a.A1 = gh; a.lda1 = HP; a.K1 = HP; a.rowscale = g.node_mask; a.wt = n->p(Lr.n.l2_nt);
+        a.A1 = gh; a.lda1 = HP; a.K1 = HP; a.rowscale = g.node_mask; a.wt = n->p(Lr.n.l2_nt); a.wt_tc = n->p(Lr.n.l2_nt_tc);
         a.out = w.gpre4; a.ldo = HP; a.epi = EPI_MUL_DSILU; a.aux = w.pre4 + (size_t)l * nn * HP; a.ldaux = HP;
-        launch_lin(HP, a, s);
+        run_lin(n, a, s);
         // gcat = g_pre4 W3  -> [:, :HP] (+ gh*mask) = dL/dh (direct), [:, HP:] = dL/dagg
         LinArgs c = lin_base(g.n_nodes);
-        c.A1 = w.gpre4; c.lda1 = HP; c.K1 = HP; c.wt = n->p(Lr.n.l1_nt); c.ncb = 2; c.out = w.gcat; c.ldo = 2 * HP;
+        c.A1 = w.gpre4; c.lda1 = HP; c.K1 = HP; c.wt = n->p(Lr.n.l1_nt); c.wt_tc = n->p(Lr.n.l1_nt_tc); c.ncb = 2; c.out = w.gcat; c.ldo = 2 * HP;
         c.epi = EPI_ADD_RES; c.res = gh; c.ldr = HP; c.mask = g.node_mask; c.res_cb = 0;
-        launch_lin(HP, c, s);
+        run_lin(n, c, s);
         cudaMemsetAsync(w.gPb, 0, nn * HP * sizeof(float), s);
         cudaMemsetAsync(gx2, 0, nn * 3 * sizeof(float), s);
         PredEdgeArgs e = pred_edge_args(n, Lr, g, w, l, true);
@@ -524,9 +570,9 @@ static int predictor_grad_impl(const gb_net* n, const Graph& g, const float* g_p
         launch_pred_edge_bwd(HP, e, s);
         // gh_l = gcat[:, :HP] + gPa W1a + gPb W1b
         LinArgs d = lin_base(g.n_nodes);
-        d.A1 = w.gPa; d.lda1 = HP; d.K1 = HP; d.A2 = w.gPb; d.lda2 = HP; d.K2 = HP; d.wt = n->p(Lr.e.l1_nt);
+        d.A1 = w.gPa; d.lda1 = HP; d.K1 = HP; d.A2 = w.gPb; d.lda2 = HP; d.K2 = HP; d.wt = n->p(Lr.e.l1_nt); d.wt_tc = n->p(Lr.e.l1_nt_tc);
         d.out = gh2; d.ldo = HP; d.epi = EPI_ADD_RES; d.res = w.gcat; d.ldr = 2 * HP;
-        launch_lin(HP, d, s);
+        run_lin(n, d, s);
         GB_LAUNCHED(4);
         float* tmp = gh; gh = gh2; gh2 = tmp;
         tmp = gx; gx = gx2; gx2 = tmp;
@@ -699,7 +745,9 @@ extern "C" int gb_profile_kernel(const gb_net* n, const gb_graph* gg, int which,
                 a.ext = n->p(E.c.l1_ext); a.wt2 = n->p(E.c.l2_wt); a.b2 = n->p(E.c.l2_b); a.vecw = n->p(E.last_w);
                 a.x_out = w.xb;
             }
-            launch_den_edge(n->HP, which, a, s); GB_LAUNCHED(1);
+            const float* img = which == 0 ? n->p(n->gcl[(size_t)layer * n->n_sub].e.l2_tc) : n->p(n->eq[layer].c.l2_tc);
+            if (n->tc_den) launch_den_edge_tc(n->HP, which, a, img, s); else launch_den_edge(n->HP, which, a, s);
+            GB_LAUNCHED(1);
         }
         return check_launch("profile den_edge");
     }
@@ -720,8 +768,8 @@ extern "C" int gb_profile_kernel(const gb_net* n, const gb_graph* gg, int which,
         } else {
             LinArgs a = lin_base(g.n_nodes);
             a.A1 = w.h; a.lda1 = n->HP; a.K1 = n->HP; a.A2 = w.agg; a.lda2 = n->HP; a.K2 = n->HP;
-            a.wt = n->p(Lr.n.l1_wt); a.bias = n->p(Lr.n.l1_b); a.out = w.s; a.ldo = n->HP; a.epi = EPI_SILU;
-            launch_lin(n->HP, a, s);
+            a.wt = n->p(Lr.n.l1_wt); a.wt_tc = n->p(Lr.n.l1_tc); a.bias = n->p(Lr.n.l1_b); a.out = w.s; a.ldo = n->HP; a.epi = EPI_SILU;
+            run_lin(n, a, s);
         }
         GB_LAUNCHED(1);
     }

@@ -36,6 +36,7 @@ struct LinArgs {
     const float* A2; int lda2; int K2;      // optional K-concatenated second input (K2 = 0: none)
     const float* rowscale;                  // optional [M]: A rows are multiplied by it while loading
     const float* wt;                        // packed [ncb][(K1+K2)][HP]
+    const float* wt_tc;                     // tensor-core image [ncb][atoms(K1)+atoms(K2)][hi|lo][NP][32] (swizzled) or null
     const float* bias;                      // [ncb*HP] or null
     float* out; int ldo;
     float* out2; int ldo2;                  // EPI_SILU: optional copy of the pre-activation
@@ -46,6 +47,10 @@ struct LinArgs {
     int res_cb;                             // EPI_ADD_RES: column block that receives the residual (-1: all)
 };
 void launch_lin(int HP, const LinArgs& a, cudaStream_t s);
+// tcgen05 / 3xTF32 version (tc_lin_kernel.cu); H = row stride / hidden width of the node tensors (== HP)
+void launch_lin_tc(int H, const LinArgs& a, const float* wimg, cudaStream_t s);
+int tc_np(int H);
+void launch_pack_tc(float* dst, const float* src, int ld, int k_off, int n_off, int Kv, int Nv, int NP, int atoms, int transpose, cudaStream_t s);
 
 // tiny-K input embedding of both networks:  h0 = W [feat*mask , t] + b ;  x = z[:, :3]*mask
 struct EmbedInArgs {
@@ -82,6 +87,7 @@ struct DenEdgeArgs {
     float* x_out;              // mode 1 out [n_nodes, 3]
 };
 void launch_den_edge(int HP, int mode, const DenEdgeArgs& a, cudaStream_t s);
+void launch_den_edge_tc(int H, int mode, const DenEdgeArgs& a, const float* wimg, cudaStream_t s);
 
 // ---- predictor E_GCL edge kernels ---------------------------------------------------------------
 struct PredEdgeArgs {

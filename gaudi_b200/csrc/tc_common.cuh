@@ -1,0 +1,109 @@
+// tcgen05 / TMEM helpers for the tensor-core tile GEMM (sm_100a).
+//
+// Operand format: kind::tf32, both operands K-major in shared memory with the 128-byte swizzle
+// (canonical UMMA layout  Swizzle<3,4,3> o ((8,n),(4,2)) : rows of 128 B = 32 fp32, 8-row groups of 1024 B).
+// Element (row r, 16-byte chunk c of its 128-byte row) lives at  base + (r/8)*1024 + (r%8)*128 + ((c ^ (r%8))*16).
+// One "K-atom" is a [rows x 32] block; one tcgen05.mma consumes K = 8 (32 bytes), so an atom feeds 4 MMAs whose
+// descriptors differ by +32 bytes in the start address.
+//
+// Accuracy: error-compensated 3xTF32.  x = hi + lo with hi = x & 0xffffe000 (exactly a TF32 value) and lo = x - hi;
+//   a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi   (dropped term ~2^-22 relative), accumulated in FP32 in TMEM.
+#pragma once
+#include "common.cuh"
+
+namespace gb {
+namespace tc {
+
+constexpr int ATOM_K = 32;                 // fp32 elements per 128-byte swizzle row
+constexpr int ATOM_ROW_BYTES = 128;
+
+__device__ __forceinline__ uint32_t swz_offset(int r, int c) {      // byte offset of 16-byte chunk c of row r inside an atom
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_128B, SBO = 1024 B.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);          // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                               // leading byte offset (unused for swizzled K-major), bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset between 8-row groups, bits [32,46)
+    d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell), bits [46,48)
+    d |= (uint64_t)2 << 61;                               // layout type SWIZZLE_128B, bits [61,64)
+    return d;
+}
+// 32-bit instruction descriptor (cute::UMMA::InstrDescriptor): TF32 x TF32 -> F32, K-major A and B, M = 128.
+__host__ __device__ constexpr uint32_t instr_desc_tf32(int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (tensor core / TMA reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {     // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {       // same warp that allocated
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+
+// 32 lanes x 32 columns of fp32: thread t of the warp receives row (lane group base + t), columns [col, col+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Write 4 consecutive fp32 (one 16-byte chunk c of row r) of an A atom as the hi / lo split.
+__device__ __forceinline__ void store_split(unsigned char* atom_hi, unsigned char* atom_lo, int r, int c, float4 x) {
+    float4 h, l;
+    h.x = tf32_hi(x.x); h.y = tf32_hi(x.y); h.z = tf32_hi(x.z); h.w = tf32_hi(x.w);
+    l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+    const uint32_t off = swz_offset(r, c);
+    *reinterpret_cast<float4*>(atom_hi + off) = h;
+    *reinterpret_cast<float4*>(atom_lo + off) = l;
+}
+
+}  // namespace tc
+}  // namespace gb
