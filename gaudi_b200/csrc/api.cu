@@ -511,7 +511,9 @@ static int predictor_forward_impl(const gb_net* n, const Graph& g, const float* 
     for (int l = 0; l < n->L; ++l) {
         const PredLayer& Lr = n->pl[l];
         PredEdgeArgs a = pred_edge_args(n, Lr, g, w, l, save != 0);
-        launch_pred_edge_fwd(n->HP, save != 0, a, s); GB_LAUNCHED(1);
+        if (n->tc_pred) launch_pred_edge_fwd_tc(n->HP, save != 0, a, n->p(Lr.e.l2_tc), n->p(Lr.c_tc), s);
+        else launch_pred_edge_fwd(n->HP, save != 0, a, s);
+        GB_LAUNCHED(1);
         node_update(n, Lr.n, h, w.agg, w.s, h2, save ? w.pre4 + (size_t)l * nn * n->HP : nullptr, g, s);
         float* tmp = h; h = h2; h2 = tmp;
         if (l + 1 < n->L) lin_P(n, n->pl[l + 1].e, h, w.P, g.n_nodes, s);
@@ -567,7 +569,8 @@ static int predictor_grad_impl(const gb_net* n, const Graph& g, const float* g_p
         PredEdgeArgs e = pred_edge_args(n, Lr, g, w, l, true);
         e.w2_nt = n->p(Lr.e.l2_nt); e.wc_nt = n->p(Lr.c_nt);
         e.g_agg = w.gcat + HP; e.ld_gagg = 2 * HP; e.g_xout = gx; e.g_Pa = w.gPa; e.g_Pb = w.gPb; e.g_x = gx2; e.g_attr = w.gattr;
-        launch_pred_edge_bwd(HP, e, s);
+        if (n->tc_pred) launch_pred_edge_bwd_tc(HP, e, n->p(Lr.c_nt_tc), n->p(Lr.e.l2_nt_tc), s);
+        else launch_pred_edge_bwd(HP, e, s);
         // gh_l = gcat[:, :HP] + gPa W1a + gPb W1b
         LinArgs d = lin_base(g.n_nodes);
         d.A1 = w.gPa; d.lda1 = HP; d.K1 = HP; d.A2 = w.gPb; d.lda2 = HP; d.K2 = HP; d.wt = n->p(Lr.e.l1_nt); d.wt_tc = n->p(Lr.e.l1_nt_tc);
@@ -759,12 +762,14 @@ extern "C" int gb_profile_kernel(const gb_net* n, const gb_graph* gg, int which,
         if (which == 2) {
             PredEdgeArgs a = pred_edge_args(n, Lr, g, w, layer, true);
             a.x_out = w.gx2;                 // scratch target: keep the saved coordinates of layer+1 intact
-            launch_pred_edge_fwd(n->HP, true, a, s);
+            if (n->tc_pred) launch_pred_edge_fwd_tc(n->HP, true, a, n->p(Lr.e.l2_tc), n->p(Lr.c_tc), s);
+            else launch_pred_edge_fwd(n->HP, true, a, s);
         } else if (which == 3) {
             PredEdgeArgs e = pred_edge_args(n, Lr, g, w, layer, true);
             e.w2_nt = n->p(Lr.e.l2_nt); e.wc_nt = n->p(Lr.c_nt);
             e.g_agg = w.gcat + n->HP; e.ld_gagg = 2 * n->HP; e.g_xout = w.gx; e.g_Pa = w.gPa; e.g_Pb = w.gPb; e.g_x = w.gx2; e.g_attr = w.gattr;
-            launch_pred_edge_bwd(n->HP, e, s);
+            if (n->tc_pred) launch_pred_edge_bwd_tc(n->HP, e, n->p(Lr.c_nt_tc), n->p(Lr.e.l2_nt_tc), s);
+            else launch_pred_edge_bwd(n->HP, e, s);
         } else {
             LinArgs a = lin_base(g.n_nodes);
             a.A1 = w.h; a.lda1 = n->HP; a.K1 = n->HP; a.A2 = w.agg; a.lda2 = n->HP; a.K2 = n->HP;

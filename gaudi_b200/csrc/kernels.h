@@ -114,6 +114,8 @@ struct PredEdgeArgs {
 };
 void launch_pred_edge_fwd(int HP, bool save, const PredEdgeArgs& a, cudaStream_t s);
 void launch_pred_edge_bwd(int HP, const PredEdgeArgs& a, cudaStream_t s);
+void launch_pred_edge_fwd_tc(int H, bool save, const PredEdgeArgs& a, const float* w2img, const float* wcimg, cudaStream_t s);
+void launch_pred_edge_bwd_tc(int H, const PredEdgeArgs& a, const float* wcimg_nt, const float* w2img_nt, cudaStream_t s);
 
 size_t tile_kernel_smem_bytes(int HP);
 

@@ -1,0 +1,563 @@
+// Tensor-core (tcgen05, 3xTF32) versions of the predictor E_GCL edge kernels -- same contract and same saved-activation
+// layouts as pred_edge.cu (forward: gcl.py:225-279; backward: the hand-written reverse pass replacing autograd).
+//
+// thread = edge row; 8 worker warps in two halves, half h owns the 16-column chunks ch == h (mod 2) both when building
+// A K-atoms (chunk ch = 16-byte chunks 4h..4h+3 of atom ch/2) and in the epilogues, so every atom is built by all 256
+// workers.  Two accumulators live in TMEM (columns [0,NP) and [256,256+NP)): the epilogue of GEMM 1 produces the A
+// atoms of GEMM 2 on the fly, chunk by chunk, while the MMA warp consumes them.
+#include "tc_common.cuh"
+#include "kernels.h"
+
+namespace gb {
+using namespace tc;
+
+template <int NP>
+struct TcPredCfg {
+    static constexpr int S = 2;
+    static constexpr int A_BYTES = 128 * ATOM_ROW_BYTES;
+    static constexpr int W_BYTES = NP * ATOM_ROW_BYTES;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+    static constexpr int MAXCH = (NP + 15) / 16;
+    static constexpr int MYCH = (MAXCH + 1) / 2;
+    static constexpr int EF_STRIDE = 17;
+    static constexpr int SCRATCH = 6 * NP * 4 + 4 * 128 * 4 + 2 * 128 * EF_STRIDE * 4 + 129 * 4 + 128 * 3 * 4 + 64;
+    static constexpr int SMEM = S * STAGE_BYTES + 1024 + 256 + SCRATCH;
+    static constexpr int D2_COL = 256;
+};
+
+__device__ __forceinline__ void nbar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+struct TcPipe {      // shared bookkeeping of the atom ring (same counter sequence in every role)
+    unsigned char* base; uint64_t *full_a, *full_w, *empty; int stage_bytes, S;
+};
+
+// one GEMM worth of MMAs: na atoms from the ring into accumulator d_tmem
+template <int NP>
+__device__ __forceinline__ void mma_gemm(const TcPipe& p, uint32_t& it, int na, int H, uint32_t d_tmem) {
+    using CF = TcPredCfg<NP>;
+    constexpr uint32_t idesc = instr_desc_tf32(NP);
+    for (int j = 0; j < na; ++j, ++it) {
+        const uint32_t s = it % CF::S, r = it / CF::S;
+        const int kvalid = H - j * ATOM_K;
+        const int ksteps = kvalid >= ATOM_K ? 4 : (kvalid + 7) / 8;
+        mbar_wait(&p.full_a[s], r & 1);
+        mbar_wait(&p.full_w[s], r & 1);
+        fence_after_sync();
+        const uint32_t a_hi = smem_u32(p.base + s * CF::STAGE_BYTES), a_lo = a_hi + CF::A_BYTES;
+        const uint32_t w_hi = a_hi + 2 * CF::A_BYTES, w_lo = w_hi + CF::W_BYTES;
+        for (int kk = 0; kk < ksteps; ++kk) {
+            const uint32_t ko = kk * 32;
+            mma_tf32(d_tmem, smem_desc(a_lo + ko), smem_desc(w_hi + ko), idesc, (j | kk) != 0);
+            mma_tf32(d_tmem, smem_desc(a_hi + ko), smem_desc(w_lo + ko), idesc, 1);
+            mma_tf32(d_tmem, smem_desc(a_hi + ko), smem_desc(w_hi + ko), idesc, 1);
+        }
+        mma_commit(&p.empty[s]);
+    }
+}
+
+template <int NP>
+__device__ __forceinline__ void tma_gemm(const TcPipe& p, uint32_t& it, int na, const float* wimg) {
+    using CF = TcPredCfg<NP>;
+    const size_t atom_floats = (size_t)2 * NP * ATOM_K;
+    for (int j = 0; j < na; ++j, ++it) {
+        const uint32_t s = it % CF::S, r = it / CF::S;
+        if (r > 0) mbar_wait(&p.empty[s], (r - 1) & 1);
+        mbar_arrive_expect_tx(&p.full_w[s], 2 * CF::W_BYTES);
+        bulk_g2s(p.base + s * CF::STAGE_BYTES + 2 * CF::A_BYTES, wimg + (size_t)j * atom_floats, 2 * CF::W_BYTES, &p.full_w[s]);
+    }
+}
+
+// worker side: publish this thread's 16 columns (4 x float4) of atom `it` (half h writes 16-byte chunks 4h..4h+3)
+template <int NP>
+__device__ __forceinline__ void put_chunk(const TcPipe& p, uint32_t it, int r, int half, const float4 (&x)[4]) {
+    using CF = TcPredCfg<NP>;
+    const uint32_t s = it % CF::S, rr = it / CF::S;
+    if (rr > 0) mbar_wait(&p.empty[s], (rr - 1) & 1);
+    unsigned char* a_hi = p.base + s * CF::STAGE_BYTES;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) store_split(a_hi, a_hi + CF::A_BYTES, r, 4 * half + c, x[c]);
+    fence_proxy_async();
+    mbar_arrive(&p.full_a[s]);
+}
+
+// ==================================================================================================================
+// forward
+// ==================================================================================================================
+template <int NP, bool SAVE>
+__global__ void __launch_bounds__(320, 1) tc_pred_edge_fwd_kernel(PredEdgeArgs a, const float* __restrict__ w2img,
+                                                                   const float* __restrict__ wcimg, int H) {
+    using CF = TcPredCfg<NP>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::S * CF::STAGE_BYTES);
+    TcPipe p{base, bars, bars + CF::S, bars + 2 * CF::S, CF::STAGE_BYTES, CF::S};
+    uint64_t* d1_full = bars + 3 * CF::S; uint64_t* d2_full = d1_full + 1; uint64_t* d_empty = d2_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 1);
+    float* vec_s = reinterpret_cast<float*>(base + CF::S * CF::STAGE_BYTES + 256);    // [6][NP]: w_r, w_a, b2, att_w, bc, wc_last
+    float* red_s = vec_s + 6 * NP;                                                       // [2][2][128]
+    float* ef_s = red_s + 4 * 128;                                                       // [2][128][17]
+    int* seg_s = reinterpret_cast<int*>(ef_s + 2 * 128 * CF::EF_STRIDE);
+    float* tr_s = reinterpret_cast<float*>(seg_s + 129);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < CF::S; ++s) { mbar_init(&p.full_a[s], 256); mbar_init(&p.full_w[s], 1); mbar_init(&p.empty[s], 1); }
+        mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d_empty, 256);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    for (int i = tid; i < NP; i += blockDim.x) {
+        const bool v = i < H;
+        vec_s[i] = v ? a.ext[i] : 0.f; vec_s[NP + i] = v ? a.ext[H + i] : 0.f; vec_s[2 * NP + i] = v ? a.b2[i] : 0.f;
+        vec_s[3 * NP + i] = v ? a.att_w[i] : 0.f; vec_s[4 * NP + i] = v ? a.bc[i] : 0.f; vec_s[5 * NP + i] = v ? a.wc_last[i] : 0.f;
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const Graph& g = a.g;
+    const int na = (H + ATOM_K - 1) / ATOM_K;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) { tma_gemm<NP>(p, it, na, w2img); tma_gemm<NP>(p, it, na, wcimg); }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t it = 0, tcnt = 0;
+            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
+                if (tcnt > 0) mbar_wait(d_empty, (tcnt - 1) & 1);
+                fence_after_sync();
+                mma_gemm<NP>(p, it, na, H, tmem_base);
+                mma_commit(d1_full);
+                mma_gemm<NP>(p, it, na, H, tmem_base + CF::D2_COL);
+                mma_commit(d2_full);
+            }
+        }
+    } else {
+        const int group = warp & 3, half = (warp - 2) >> 2;
+        const int r = group * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(group * 32) << 16);
+        const int nchunks = (H + 15) / 16;
+        float* my_ef = ef_s + half * 128 * CF::EF_STRIDE;
+        uint32_t tcnt = 0;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
+            const int node_lo = g.tile_ptr[tile], node_hi = g.tile_ptr[tile + 1];
+            const int nn = node_hi - node_lo;
+            const int e_lo = g.rowptr[node_lo], ne = g.rowptr[node_hi] - e_lo;
+            const bool valid = r < ne;
+            int rown = 0, coln = 0; float rad = 0.f, a0 = 0.f, ux = 0.f, uy = 0.f, uz = 0.f;
+            if (valid) {
+                const int e = e_lo + r;
+                rown = g.erow[e]; coln = g.ecol[e];
+                const float dx = a.x[3 * rown] - a.x[3 * coln], dy = a.x[3 * rown + 1] - a.x[3 * coln + 1], dz = a.x[3 * rown + 2] - a.x[3 * coln + 2];
+                rad = dx * dx + dy * dy + dz * dz;
+                const float inv = 1.f / (sqrtf(rad + 1e-8f) + 1.f);
+                ux = dx * inv; uy = dy * inv; uz = dz * inv;
+                const float ex = a.x0[3 * rown] - a.x0[3 * coln], ey = a.x0[3 * rown + 1] - a.x0[3 * coln + 1], ez = a.x0[3 * rown + 2] - a.x0[3 * coln + 2];
+                a0 = ex * ex + ey * ey + ez * ez;
+            }
+            if (half == 0) for (int i = r; i <= nn; i += 128) seg_s[i] = g.rowptr[node_lo + i] - e_lo;
+            const uint32_t it0 = tcnt * 2 * na;
+            // ---- GEMM 1 operand: s1 = SiLU(pre1); SiLU'(pre1) is saved ----
+            const float* pa_row = a.P + (size_t)rown * (2 * H);
+            const float* pb_row = a.P + (size_t)coln * (2 * H) + H;
+            for (int j = 0; j < na; ++j) {
+                float4 x[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int k0 = j * ATOM_K + 16 * half + 4 * c;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), dv = v;
+                    if (valid && k0 < H) {
+                        const float4 pa = __ldg(reinterpret_cast<const float4*>(pa_row + k0));
+                        const float4 pb = __ldg(reinterpret_cast<const float4*>(pb_row + k0));
+                        const float4 wr = *reinterpret_cast<const float4*>(vec_s + k0);
+                        const float4 wa = *reinterpret_cast<const float4*>(vec_s + NP + k0);
+                        silu_both(pa.x + pb.x + wr.x * rad + wa.x * a0, v.x, dv.x);
+                        silu_both(pa.y + pb.y + wr.y * rad + wa.y * a0, v.y, dv.y);
+                        silu_both(pa.z + pb.z + wr.z * rad + wa.z * a0, v.z, dv.z);
+                        silu_both(pa.w + pb.w + wr.w * rad + wa.w * a0, v.w, dv.w);
+                    }
+                    x[c] = v;
+                    if (SAVE && k0 < H) *reinterpret_cast<float4*>(a.sv_d1 + (((size_t)tile * (H / 4) + (k0 >> 2)) * 128 + r) * 4) = dv;
+                }
+                put_chunk<NP>(p, it0 + j, r, half, x);
+            }
+            // ---- epilogue 1: q = SiLU(pre2), attention gate ----
+            mbar_wait(d1_full, tcnt & 1);
+            fence_after_sync();
+            float q[CF::MYCH][16];
+            float part = 0.f;
+#pragma unroll
+            for (int ci = 0; ci < CF::MYCH; ++ci) {
+                const int ch = half + 2 * ci;
+                if (ch < nchunks) {
+                    tmem_ld16(lane_addr + ch * 16, q[ci]);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int c = ch * 16 + e;
+                        const float pre = q[ci][e] + vec_s[2 * NP + c];
+                        if (SAVE && c < H) a.sv_pre2[((size_t)tile * H + c) * 128 + r] = pre;
+                        const float v = silu_f(pre);
+                        q[ci][e] = v;
+                        part = fmaf(vec_s[3 * NP + c], v, part);
+                    }
+                }
+            }
+            red_s[half * 128 + r] = part;
+            nbar(1, 256);
+            const float gate = a.attention ? sigmoid_f(red_s[r] + red_s[128 + r] + a.att_b) : 1.f;
+            // ---- gated edge feature: segment sums -> agg, and operand atoms of GEMM 2 ----
+#pragma unroll
+            for (int ci = 0; ci < CF::MYCH; ++ci) {
+                const int ch = half + 2 * ci;
+                if (ch < nchunks) {
+                    float4 x[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        x[c] = make_float4(q[ci][4 * c] * gate, q[ci][4 * c + 1] * gate, q[ci][4 * c + 2] * gate, q[ci][4 * c + 3] * gate);
+                        if (!valid) x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        my_ef[r * CF::EF_STRIDE + 4 * c] = x[c].x; my_ef[r * CF::EF_STRIDE + 4 * c + 1] = x[c].y;
+                        my_ef[r * CF::EF_STRIDE + 4 * c + 2] = x[c].z; my_ef[r * CF::EF_STRIDE + 4 * c + 3] = x[c].w;
+                    }
+                    put_chunk<NP>(p, it0 + na + (ch >> 1), r, half, x);
+                    nbar(2 + half, 128);
+                    for (int nl = r >> 4; nl < nn; nl += 8) {
+                        const int col = r & 15, c = ch * 16 + col;
+                        float sum = 0.f;
+                        for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += my_ef[mm * CF::EF_STRIDE + col];
+                        if (c < H) a.agg[(size_t)(node_lo + nl) * H + c] = sum;
+                    }
+                    nbar(2 + half, 128);
+                } else if (2 * ci + half < 2 * na) {
+                    // chunk beyond the hidden width but inside the last atom: publish zeros so the atom completes
+                    float4 x[4] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+                    put_chunk<NP>(p, it0 + na + ((2 * ci + half) >> 1), r, half, x);
+                }
+            }
+            // ---- epilogue 2: coordinate head ----
+            mbar_wait(d2_full, tcnt & 1);
+            fence_after_sync();
+            float phi_part = 0.f;
+#pragma unroll 1
+            for (int ch = half; ch < nchunks; ch += 2) {
+                float v[16];
+                tmem_ld16(lane_addr + CF::D2_COL + ch * 16, v);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int c = ch * 16 + e;
+                    float s3, d3;
+                    silu_both(v[e] + vec_s[4 * NP + c], s3, d3);
+                    if (SAVE && c < H) a.sv_d3[((size_t)tile * H + c) * 128 + r] = d3;
+                    phi_part = fmaf(vec_s[5 * NP + c], s3, phi_part);
+                }
+            }
+            fence_before_sync();
+            mbar_arrive(d_empty);
+            red_s[256 + half * 128 + r] = phi_part;
+            nbar(1, 256);
+            if (half == 0) {
+                const float phi = red_s[256 + r] + red_s[384 + r];
+                const float tau = a.use_tanh ? tanhf(phi) : phi;
+                if (SAVE && valid) a.sv_tau[e_lo + r] = tau;
+                if (a.use_tanh) { tr_s[3 * r] = ux * tau * a.coords_range; tr_s[3 * r + 1] = uy * tau * a.coords_range; tr_s[3 * r + 2] = uz * tau * a.coords_range; }
+                else { tr_s[3 * r] = ux * tau; tr_s[3 * r + 1] = uy * tau; tr_s[3 * r + 2] = uz * tau; }
+            }
+            nbar(1, 256);
+            for (int idx = half * 128 + r; idx < nn * 3; idx += 256) {
+                const int nl = idx / 3, d = idx - 3 * nl;
+                float sum = 0.f;
+                for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += tr_s[3 * mm + d];
+                const int node = node_lo + nl;
+                a.x_out[3 * node + d] = (a.x[3 * node + d] + sum) * g.node_mask[node];
+            }
+            nbar(1, 256);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ==================================================================================================================
+// backward (input gradient only)
+// ==================================================================================================================
+template <int NP>
+__global__ void __launch_bounds__(320, 1) tc_pred_edge_bwd_kernel(PredEdgeArgs a, const float* __restrict__ wcimg_nt,
+                                                                   const float* __restrict__ w2img_nt, int H) {
+    using CF = TcPredCfg<NP>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::S * CF::STAGE_BYTES);
+    TcPipe p{base, bars, bars + CF::S, bars + 2 * CF::S, CF::STAGE_BYTES, CF::S};
+    uint64_t* d1_full = bars + 3 * CF::S; uint64_t* d2_full = d1_full + 1; uint64_t* d_empty = d2_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 1);
+    float* vec_s = reinterpret_cast<float*>(base + CF::S * CF::STAGE_BYTES + 256);    // [6][NP]: w_r, w_a, b2(unused), att_w, bc(unused), wc_last
+    float* red_s = vec_s + 6 * NP;                                                       // [4][128]
+    float* ef_s = red_s + 4 * 128;                                                       // [2][128][17]
+    int* seg_s = reinterpret_cast<int*>(ef_s + 2 * 128 * CF::EF_STRIDE);
+    float* gd_s = reinterpret_cast<float*>(seg_s + 129);                                 // [128][3]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < CF::S; ++s) { mbar_init(&p.full_a[s], 256); mbar_init(&p.full_w[s], 1); mbar_init(&p.empty[s], 1); }
+        mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d_empty, 256);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    for (int i = tid; i < NP; i += blockDim.x) {
+        const bool v = i < H;
+        vec_s[i] = v ? a.ext[i] : 0.f; vec_s[NP + i] = v ? a.ext[H + i] : 0.f;
+        vec_s[3 * NP + i] = v ? a.att_w[i] : 0.f; vec_s[5 * NP + i] = v ? a.wc_last[i] : 0.f;
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const Graph& g = a.g;
+    const int na = (H + ATOM_K - 1) / ATOM_K;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) { tma_gemm<NP>(p, it, na, wcimg_nt); tma_gemm<NP>(p, it, na, w2img_nt); }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t it = 0, tcnt = 0;
+            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
+                if (tcnt > 0) mbar_wait(d_empty, (tcnt - 1) & 1);
+                fence_after_sync();
+                mma_gemm<NP>(p, it, na, H, tmem_base);
+                mma_commit(d1_full);
+                mma_gemm<NP>(p, it, na, H, tmem_base + CF::D2_COL);
+                mma_commit(d2_full);
+            }
+        }
+    } else {
+        const int group = warp & 3, half = (warp - 2) >> 2;
+        const int r = group * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(group * 32) << 16);
+        const int nchunks = (H + 15) / 16;
+        float* my_ef = ef_s + half * 128 * CF::EF_STRIDE;
+        uint32_t tcnt = 0;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
+            const int node_lo = g.tile_ptr[tile], node_hi = g.tile_ptr[tile + 1];
+            const int nn = node_hi - node_lo;
+            const int e_lo = g.rowptr[node_lo], ne = g.rowptr[node_hi] - e_lo;
+            const bool valid = r < ne;
+            int rown = 0, coln = 0;
+            float gphi = 0.f, nrm = 1.f, dx = 0.f, dy = 0.f, dz = 0.f, gux = 0.f, guy = 0.f, guz = 0.f;
+            if (valid) {
+                const int e = e_lo + r;
+                rown = g.erow[e]; coln = g.ecol[e];
+                dx = a.x[3 * rown] - a.x[3 * coln]; dy = a.x[3 * rown + 1] - a.x[3 * coln + 1]; dz = a.x[3 * rown + 2] - a.x[3 * coln + 2];
+                nrm = sqrtf(dx * dx + dy * dy + dz * dz + 1e-8f);
+                const float inv = 1.f / (nrm + 1.f);
+                const float mk = g.node_mask[rown];
+                const float gx = a.g_xout[3 * rown] * mk, gy = a.g_xout[3 * rown + 1] * mk, gz = a.g_xout[3 * rown + 2] * mk;
+                const float tau = a.sv_tau[e];
+                const float gdotu = (gx * dx + gy * dy + gz * dz) * inv;
+                if (a.use_tanh) { gphi = gdotu * a.coords_range * (1.f - tau * tau); const float sc = tau * a.coords_range; gux = gx * sc; guy = gy * sc; guz = gz * sc; }
+                else { gphi = gdotu; gux = gx * tau; guy = gy * tau; guz = gz * tau; }
+            }
+            if (half == 0) for (int i = r; i <= nn; i += 128) seg_s[i] = g.rowptr[node_lo + i] - e_lo;
+            const uint32_t it0 = tcnt * 2 * na;
+            // ---- GEMM 1 operand: g_pre3 = g_phi * w_c * SiLU'(pre3) ----
+            for (int j = 0; j < na; ++j) {
+                float4 x[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int k0 = j * ATOM_K + 16 * half + 4 * c;
+                    float t[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (k0 < H) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) t[e] = gphi * vec_s[5 * NP + k0 + e] * __ldg(a.sv_d3 + ((size_t)tile * H + k0 + e) * 128 + r);
+                    }
+                    x[c] = make_float4(t[0], t[1], t[2], t[3]);
+                }
+                put_chunk<NP>(p, it0 + j, r, half, x);
+            }
+            // ---- epilogue 1: g_ef = coordinate branch + aggregation branch; attention backward ----
+            mbar_wait(d1_full, tcnt & 1);
+            fence_after_sync();
+            float gef[CF::MYCH][16];
+            float plog = 0.f, pdot = 0.f;
+            const float* ga_row = a.g_agg + (size_t)rown * a.ld_gagg;
+#pragma unroll
+            for (int ci = 0; ci < CF::MYCH; ++ci) {
+                const int ch = half + 2 * ci;
+                if (ch < nchunks) {
+                    tmem_ld16(lane_addr + ch * 16, gef[ci]);
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const int c0 = ch * 16 + 4 * c4;
+                        if (c0 < H) {
+                            const float4 ga = __ldg(reinterpret_cast<const float4*>(ga_row + c0));
+                            const float gadd[4] = {ga.x, ga.y, ga.z, ga.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float qv = silu_f(__ldg(a.sv_pre2 + ((size_t)tile * H + c0 + e) * 128 + r));
+                                const float gv = gef[ci][4 * c4 + e] + gadd[e];
+                                gef[ci][4 * c4 + e] = gv;
+                                plog = fmaf(vec_s[3 * NP + c0 + e], qv, plog);
+                                pdot = fmaf(gv, qv, pdot);
+                            }
+                        }
+                    }
+                }
+            }
+            red_s[half * 128 + r] = plog;
+            red_s[256 + half * 128 + r] = pdot;
+            nbar(1, 256);
+            float gate = 1.f, kap = 0.f;
+            if (a.attention) {
+                gate = sigmoid_f(red_s[r] + red_s[128 + r] + a.att_b);
+                kap = (red_s[256 + r] + red_s[384 + r]) * gate * (1.f - gate);
+            }
+            // ---- GEMM 2 operand: g_pre2 = (g_ef gate + kappa w_att) SiLU'(pre2) ----
+#pragma unroll
+            for (int ci = 0; ci < CF::MYCH; ++ci) {
+                const int ch = half + 2 * ci;
+                if (2 * ci + half < 2 * na) {
+                    float4 x[4];
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const int c0 = ch * 16 + 4 * c4;
+                        float t[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (ch < nchunks && c0 < H && valid) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float pre = __ldg(a.sv_pre2 + ((size_t)tile * H + c0 + e) * 128 + r);
+                                t[e] = (gef[ci][4 * c4 + e] * gate + kap * vec_s[3 * NP + c0 + e]) * dsilu_f(pre);
+                            }
+                        }
+                        x[c4] = make_float4(t[0], t[1], t[2], t[3]);
+                    }
+                    put_chunk<NP>(p, it0 + na + ((2 * ci + half) >> 1), r, half, x);
+                }
+            }
+            // ---- epilogue 2: g_pre1 = g_s1 * SiLU'(pre1); row / column sums; geometry gradients ----
+            mbar_wait(d2_full, tcnt & 1);
+            fence_after_sync();
+            float pr = 0.f, pa = 0.f;
+            const int t0 = g.tc_ptr[tile], t1 = g.tc_ptr[tile + 1];
+#pragma unroll 1
+            for (int ch = half; ch < nchunks; ch += 2) {
+                float v[16];
+                tmem_ld16(lane_addr + CF::D2_COL + ch * 16, v);
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const int c0 = ch * 16 + 4 * c4;
+                    float4 d1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c0 < H) d1 = __ldg(reinterpret_cast<const float4*>(a.sv_d1 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4));
+                    const float gp[4] = {v[4 * c4] * d1.x, v[4 * c4 + 1] * d1.y, v[4 * c4 + 2] * d1.z, v[4 * c4 + 3] * d1.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        my_ef[r * CF::EF_STRIDE + 4 * c4 + e] = valid ? gp[e] : 0.f;
+                        if (c0 < H) { pr = fmaf(vec_s[c0 + e], gp[e], pr); pa = fmaf(vec_s[NP + c0 + e], gp[e], pa); }
+                    }
+                }
+                nbar(2 + half, 128);
+                const int col = r & 15, c = ch * 16 + col;
+                for (int nl = r >> 4; nl < nn; nl += 8) {
+                    float sum = 0.f;
+                    for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += my_ef[mm * CF::EF_STRIDE + col];
+                    if (c < H) a.g_Pa[(size_t)(node_lo + nl) * H + c] = sum;
+                }
+                for (int ti = t0 + (r >> 4); ti < t1; ti += 8) {
+                    float sum = 0.f;
+                    for (int q = g.tc_start[ti]; q < g.tc_start[ti + 1]; ++q) sum += my_ef[g.cperm[q] * CF::EF_STRIDE + col];
+                    if (c < H) atomicAdd(a.g_Pb + (size_t)g.tc_node[ti] * H + c, sum);
+                }
+                nbar(2 + half, 128);
+            }
+            fence_before_sync();
+            mbar_arrive(d_empty);
+            red_s[half * 128 + r] = pr;
+            red_s[256 + half * 128 + r] = pa;
+            nbar(1, 256);
+            if (half == 0) {
+                const float g_r = red_s[r] + red_s[128 + r], g_a = red_s[256 + r] + red_s[384 + r];
+                float gdx = 0.f, gdy = 0.f, gdz = 0.f;
+                if (valid) {
+                    a.g_attr[e_lo + r] += g_a;
+                    const float inv = 1.f / (nrm + 1.f);
+                    const float k2 = (gux * dx + guy * dy + guz * dz) * inv * inv / nrm;
+                    gdx = 2.f * g_r * dx + gux * inv - k2 * dx;
+                    gdy = 2.f * g_r * dy + guy * inv - k2 * dy;
+                    gdz = 2.f * g_r * dz + guz * inv - k2 * dz;
+                    atomicAdd(a.g_x + 3 * coln, -gdx); atomicAdd(a.g_x + 3 * coln + 1, -gdy); atomicAdd(a.g_x + 3 * coln + 2, -gdz);
+                }
+                gd_s[3 * r] = gdx; gd_s[3 * r + 1] = gdy; gd_s[3 * r + 2] = gdz;
+            }
+            nbar(1, 256);
+            for (int idx = half * 128 + r; idx < nn * 3; idx += 256) {
+                const int nl = idx / 3, d = idx - 3 * nl;
+                const int node = node_lo + nl;
+                float sum = a.g_xout[3 * node + d] * g.node_mask[node];
+                for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += gd_s[3 * mm + d];
+                atomicAdd(a.g_x + 3 * node + d, sum);
+            }
+            nbar(1, 256);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+template <int NP>
+static void launch_bwd_t(const PredEdgeArgs& a, const float* wcimg_nt, const float* w2img_nt, int H, cudaStream_t s) {
+    using CF = TcPredCfg<NP>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(tc_pred_edge_bwd_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM);
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = a.g.n_tiles < sms ? a.g.n_tiles : sms;
+    tc_pred_edge_bwd_kernel<NP><<<grid, 320, CF::SMEM, s>>>(a, wcimg_nt, w2img_nt, H);
+}
+
+void launch_pred_edge_bwd_tc(int H, const PredEdgeArgs& a, const float* wcimg_nt, const float* w2img_nt, cudaStream_t s) {
+    if (a.g.n_tiles <= 0) return;
+    switch (tc_np(H)) {
+        case 64: launch_bwd_t<64>(a, wcimg_nt, w2img_nt, H, s); break;
+        case 192: launch_bwd_t<192>(a, wcimg_nt, w2img_nt, H, s); break;
+        case 208: launch_bwd_t<208>(a, wcimg_nt, w2img_nt, H, s); break;
+        default: launch_bwd_t<256>(a, wcimg_nt, w2img_nt, H, s); break;
+    }
+}
+
+template <int NP>
+static void launch_fwd_t(bool save, const PredEdgeArgs& a, const float* w2img, const float* wcimg, int H, cudaStream_t s) {
+    using CF = TcPredCfg<NP>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(tc_pred_edge_fwd_kernel<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM);
+        cudaFuncSetAttribute(tc_pred_edge_fwd_kernel<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM);
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = a.g.n_tiles < sms ? a.g.n_tiles : sms;
+    if (save) tc_pred_edge_fwd_kernel<NP, true><<<grid, 320, CF::SMEM, s>>>(a, w2img, wcimg, H);
+    else tc_pred_edge_fwd_kernel<NP, false><<<grid, 320, CF::SMEM, s>>>(a, w2img, wcimg, H);
+}
+
+void launch_pred_edge_fwd_tc(int H, bool save, const PredEdgeArgs& a, const float* w2img, const float* wcimg, cudaStream_t s) {
+    if (a.g.n_tiles <= 0) return;
+    switch (tc_np(H)) {
+        case 64: launch_fwd_t<64>(save, a, w2img, wcimg, H, s); break;
+        case 192: launch_fwd_t<192>(save, a, w2img, wcimg, H, s); break;
+        case 208: launch_fwd_t<208>(save, a, w2img, wcimg, H, s); break;
+        default: launch_fwd_t<256>(save, a, w2img, wcimg, H, s); break;
+    }
+}
+
+}  // namespace gb
