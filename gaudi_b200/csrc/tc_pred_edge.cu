@@ -17,10 +17,13 @@ struct TcPredCfg {
     static constexpr int A_BYTES = 128 * ATOM_ROW_BYTES;
     static constexpr int W_BYTES = NP * ATOM_ROW_BYTES;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+    static constexpr int NPARTS = 4;                          // worker parts of 4 warps; part p owns 16-column chunks ch == p (mod 4)
+    static constexpr int NWORK = 128 * NPARTS;
+    static constexpr int THREADS = 64 + NWORK;
     static constexpr int MAXCH = (NP + 15) / 16;
-    static constexpr int MYCH = (MAXCH + 1) / 2;
+    static constexpr int MYCH = (MAXCH + NPARTS - 1) / NPARTS;
     static constexpr int EF_STRIDE = 17;
-    static constexpr int SCRATCH = 6 * NP * 4 + 4 * 128 * 4 + 2 * 128 * EF_STRIDE * 4 + 129 * 4 + 128 * 3 * 4 + 64;
+    static constexpr int SCRATCH = 6 * NP * 4 + 4 * NPARTS * 128 * 4 + NPARTS * 128 * EF_STRIDE * 4 + 129 * 4 + 128 * 3 * 4 + 64;
     static constexpr int SMEM = S * STAGE_BYTES + 1024 + 256 + SCRATCH;
     static constexpr int D2_COL = 256;
 };
@@ -67,7 +70,7 @@ __device__ __forceinline__ void tma_gemm(const TcPipe& p, uint32_t& it, int na, 
     }
 }
 
-// worker side: publish this thread's 16 columns (4 x float4) of atom `it` (half h writes 16-byte chunks 4h..4h+3)
+// worker side: publish this thread's 16 columns (4 x float4) of atom `it` (chunk parity h writes 16-byte chunks 4h..4h+3)
 template <int NP>
 __device__ __forceinline__ void put_chunk(const TcPipe& p, uint32_t it, int r, int half, const float4 (&x)[4]) {
     using CF = TcPredCfg<NP>;
@@ -84,7 +87,7 @@ __device__ __forceinline__ void put_chunk(const TcPipe& p, uint32_t it, int r, i
 // forward
 // ==================================================================================================================
 template <int NP, bool SAVE>
-__global__ void __launch_bounds__(320, 1) tc_pred_edge_fwd_kernel(PredEdgeArgs a, const float* __restrict__ w2img,
+__global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_kernel(PredEdgeArgs a, const float* __restrict__ w2img,
                                                                    const float* __restrict__ wcimg, int H) {
     using CF = TcPredCfg<NP>;
     extern __shared__ unsigned char smem_raw[];
@@ -95,14 +98,14 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_fwd_kernel(PredEdgeArgs a
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 1);
     float* vec_s = reinterpret_cast<float*>(base + CF::S * CF::STAGE_BYTES + 256);    // [6][NP]: w_r, w_a, b2, att_w, bc, wc_last
     float* red_s = vec_s + 6 * NP;                                                       // [2][2][128]
-    float* ef_s = red_s + 4 * 128;                                                       // [2][128][17]
-    int* seg_s = reinterpret_cast<int*>(ef_s + 2 * 128 * CF::EF_STRIDE);
+    float* ef_s = red_s + 4 * CF::NPARTS * 128;                                                       // [2][128][17]
+    int* seg_s = reinterpret_cast<int*>(ef_s + CF::NPARTS * 128 * CF::EF_STRIDE);
     float* tr_s = reinterpret_cast<float*>(seg_s + 129);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < CF::S; ++s) { mbar_init(&p.full_a[s], 256); mbar_init(&p.full_w[s], 1); mbar_init(&p.empty[s], 1); }
-        mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d_empty, 256);
+        mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d_empty, CF::NWORK);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -136,11 +139,11 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_fwd_kernel(PredEdgeArgs a
             }
         }
     } else {
-        const int group = warp & 3, half = (warp - 2) >> 2;
+        const int group = warp & 3, part = (warp - 2) >> 2, half = part & 1;
         const int r = group * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(group * 32) << 16);
         const int nchunks = (H + 15) / 16;
-        float* my_ef = ef_s + half * 128 * CF::EF_STRIDE;
+        float* my_ef = ef_s + part * 128 * CF::EF_STRIDE;
         uint32_t tcnt = 0;
         for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
             const int node_lo = g.tile_ptr[tile], node_hi = g.tile_ptr[tile + 1];
@@ -158,12 +161,12 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_fwd_kernel(PredEdgeArgs a
                 const float ex = a.x0[3 * rown] - a.x0[3 * coln], ey = a.x0[3 * rown + 1] - a.x0[3 * coln + 1], ez = a.x0[3 * rown + 2] - a.x0[3 * coln + 2];
                 a0 = ex * ex + ey * ey + ez * ez;
             }
-            if (half == 0) for (int i = r; i <= nn; i += 128) seg_s[i] = g.rowptr[node_lo + i] - e_lo;
+            if (part == 0) for (int i = r; i <= nn; i += 128) seg_s[i] = g.rowptr[node_lo + i] - e_lo;
             const uint32_t it0 = tcnt * 2 * na;
             // ---- GEMM 1 operand: s1 = SiLU(pre1); SiLU'(pre1) is saved ----
             const float* pa_row = a.P + (size_t)rown * (2 * H);
             const float* pb_row = a.P + (size_t)coln * (2 * H) + H;
-            for (int j = 0; j < na; ++j) {
+            for (int j = part >> 1; j < na; j += 2) {
                 float4 x[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -188,10 +191,10 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_fwd_kernel(PredEdgeArgs a
             mbar_wait(d1_full, tcnt & 1);
             fence_after_sync();
             float q[CF::MYCH][16];
-            float part = 0.f;
+            float psum = 0.f;
 #pragma unroll
             for (int ci = 0; ci < CF::MYCH; ++ci) {
-                const int ch = half + 2 * ci;
+                const int ch = part + CF::NPARTS * ci;
                 if (ch < nchunks) {
                     tmem_ld16(lane_addr + ch * 16, q[ci]);
 #pragma unroll
@@ -201,17 +204,17 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_fwd_kernel(PredEdgeArgs a
                         if (SAVE && c < H) a.sv_pre2[((size_t)tile * H + c) * 128 + r] = pre;
                         const float v = silu_f(pre);
                         q[ci][e] = v;
-                        part = fmaf(vec_s[3 * NP + c], v, part);
+                        psum = fmaf(vec_s[3 * NP + c], v, psum);
                     }
                 }
             }
-            red_s[half * 128 + r] = part;
-            nbar(1, 256);
-            const float gate = a.attention ? sigmoid_f(red_s[r] + red_s[128 + r] + a.att_b) : 1.f;
+            red_s[part * 128 + r] = psum;
+            nbar(1, CF::NWORK);
+            const float gate = a.attention ? sigmoid_f(red_s[r] + red_s[128 + r] + red_s[256 + r] + red_s[384 + r] + a.att_b) : 1.f;
             // ---- gated edge feature: segment sums -> agg, and operand atoms of GEMM 2 ----
 #pragma unroll
             for (int ci = 0; ci < CF::MYCH; ++ci) {
-                const int ch = half + 2 * ci;
+                const int ch = part + CF::NPARTS * ci;
                 if (ch < nchunks) {
                     float4 x[4];
 #pragma unroll
@@ -222,18 +225,18 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_fwd_kernel(PredEdgeArgs a
                         my_ef[r * CF::EF_STRIDE + 4 * c + 2] = x[c].z; my_ef[r * CF::EF_STRIDE + 4 * c + 3] = x[c].w;
                     }
                     put_chunk<NP>(p, it0 + na + (ch >> 1), r, half, x);
-                    nbar(2 + half, 128);
+                    nbar(2 + part, 128);
                     for (int nl = r >> 4; nl < nn; nl += 8) {
                         const int col = r & 15, c = ch * 16 + col;
                         float sum = 0.f;
                         for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += my_ef[mm * CF::EF_STRIDE + col];
                         if (c < H) a.agg[(size_t)(node_lo + nl) * H + c] = sum;
                     }
-                    nbar(2 + half, 128);
-                } else if (2 * ci + half < 2 * na) {
+                    nbar(2 + part, 128);
+                } else if (ch < 2 * na) {
                     // chunk beyond the hidden width but inside the last atom: publish zeros so the atom completes
                     float4 x[4] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-                    put_chunk<NP>(p, it0 + na + ((2 * ci + half) >> 1), r, half, x);
+                    put_chunk<NP>(p, it0 + na + (ch >> 1), r, half, x);
                 }
             }
             // ---- epilogue 2: coordinate head ----
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_fwd_kernel(PredEdgeArgs a
             fence_after_sync();
             float phi_part = 0.f;
 #pragma unroll 1
-            for (int ch = half; ch < nchunks; ch += 2) {
+            for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
                 float v[16];
                 tmem_ld16(lane_addr + CF::D2_COL + ch * 16, v);
 #pragma unroll
@@ -255,24 +258,24 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_fwd_kernel(PredEdgeArgs a
             }
             fence_before_sync();
             mbar_arrive(d_empty);
-            red_s[256 + half * 128 + r] = phi_part;
-            nbar(1, 256);
-            if (half == 0) {
-                const float phi = red_s[256 + r] + red_s[384 + r];
+            red_s[512 + part * 128 + r] = phi_part;
+            nbar(1, CF::NWORK);
+            if (part == 0) {
+                const float phi = red_s[512 + r] + red_s[640 + r] + red_s[768 + r] + red_s[896 + r];
                 const float tau = a.use_tanh ? tanhf(phi) : phi;
                 if (SAVE && valid) a.sv_tau[e_lo + r] = tau;
                 if (a.use_tanh) { tr_s[3 * r] = ux * tau * a.coords_range; tr_s[3 * r + 1] = uy * tau * a.coords_range; tr_s[3 * r + 2] = uz * tau * a.coords_range; }
                 else { tr_s[3 * r] = ux * tau; tr_s[3 * r + 1] = uy * tau; tr_s[3 * r + 2] = uz * tau; }
             }
-            nbar(1, 256);
-            for (int idx = half * 128 + r; idx < nn * 3; idx += 256) {
+            nbar(1, CF::NWORK);
+            for (int idx = part * 128 + r; idx < nn * 3; idx += CF::NWORK) {
                 const int nl = idx / 3, d = idx - 3 * nl;
                 float sum = 0.f;
                 for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += tr_s[3 * mm + d];
                 const int node = node_lo + nl;
                 a.x_out[3 * node + d] = (a.x[3 * node + d] + sum) * g.node_mask[node];
             }
-            nbar(1, 256);
+            nbar(1, CF::NWORK);
         }
     }
     fence_before_sync();
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_fwd_kernel(PredEdgeArgs a
 // backward (input gradient only)
 // ==================================================================================================================
 template <int NP>
-__global__ void __launch_bounds__(320, 1) tc_pred_edge_bwd_kernel(PredEdgeArgs a, const float* __restrict__ wcimg_nt,
+__global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_kernel(PredEdgeArgs a, const float* __restrict__ wcimg_nt,
                                                                    const float* __restrict__ w2img_nt, int H) {
     using CF = TcPredCfg<NP>;
     extern __shared__ unsigned char smem_raw[];
@@ -295,14 +298,14 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_bwd_kernel(PredEdgeArgs a
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 1);
     float* vec_s = reinterpret_cast<float*>(base + CF::S * CF::STAGE_BYTES + 256);    // [6][NP]: w_r, w_a, b2(unused), att_w, bc(unused), wc_last
     float* red_s = vec_s + 6 * NP;                                                       // [4][128]
-    float* ef_s = red_s + 4 * 128;                                                       // [2][128][17]
-    int* seg_s = reinterpret_cast<int*>(ef_s + 2 * 128 * CF::EF_STRIDE);
+    float* ef_s = red_s + 4 * CF::NPARTS * 128;                                                       // [2][128][17]
+    int* seg_s = reinterpret_cast<int*>(ef_s + CF::NPARTS * 128 * CF::EF_STRIDE);
     float* gd_s = reinterpret_cast<float*>(seg_s + 129);                                 // [128][3]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < CF::S; ++s) { mbar_init(&p.full_a[s], 256); mbar_init(&p.full_w[s], 1); mbar_init(&p.empty[s], 1); }
-        mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d_empty, 256);
+        mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d_empty, CF::NWORK);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -336,11 +339,11 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_bwd_kernel(PredEdgeArgs a
             }
         }
     } else {
-        const int group = warp & 3, half = (warp - 2) >> 2;
+        const int group = warp & 3, part = (warp - 2) >> 2, half = part & 1;
         const int r = group * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(group * 32) << 16);
         const int nchunks = (H + 15) / 16;
-        float* my_ef = ef_s + half * 128 * CF::EF_STRIDE;
+        float* my_ef = ef_s + part * 128 * CF::EF_STRIDE;
         uint32_t tcnt = 0;
         for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
             const int node_lo = g.tile_ptr[tile], node_hi = g.tile_ptr[tile + 1];
@@ -362,10 +365,10 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_bwd_kernel(PredEdgeArgs a
                 if (a.use_tanh) { gphi = gdotu * a.coords_range * (1.f - tau * tau); const float sc = tau * a.coords_range; gux = gx * sc; guy = gy * sc; guz = gz * sc; }
                 else { gphi = gdotu; gux = gx * tau; guy = gy * tau; guz = gz * tau; }
             }
-            if (half == 0) for (int i = r; i <= nn; i += 128) seg_s[i] = g.rowptr[node_lo + i] - e_lo;
+            if (part == 0) for (int i = r; i <= nn; i += 128) seg_s[i] = g.rowptr[node_lo + i] - e_lo;
             const uint32_t it0 = tcnt * 2 * na;
             // ---- GEMM 1 operand: g_pre3 = g_phi * w_c * SiLU'(pre3) ----
-            for (int j = 0; j < na; ++j) {
+            for (int j = part >> 1; j < na; j += 2) {
                 float4 x[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_bwd_kernel(PredEdgeArgs a
             const float* ga_row = a.g_agg + (size_t)rown * a.ld_gagg;
 #pragma unroll
             for (int ci = 0; ci < CF::MYCH; ++ci) {
-                const int ch = half + 2 * ci;
+                const int ch = part + CF::NPARTS * ci;
                 if (ch < nchunks) {
                     tmem_ld16(lane_addr + ch * 16, gef[ci]);
 #pragma unroll
@@ -408,19 +411,19 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_bwd_kernel(PredEdgeArgs a
                     }
                 }
             }
-            red_s[half * 128 + r] = plog;
-            red_s[256 + half * 128 + r] = pdot;
-            nbar(1, 256);
+            red_s[part * 128 + r] = plog;
+            red_s[512 + part * 128 + r] = pdot;
+            nbar(1, CF::NWORK);
             float gate = 1.f, kap = 0.f;
             if (a.attention) {
-                gate = sigmoid_f(red_s[r] + red_s[128 + r] + a.att_b);
-                kap = (red_s[256 + r] + red_s[384 + r]) * gate * (1.f - gate);
+                gate = sigmoid_f(red_s[r] + red_s[128 + r] + red_s[256 + r] + red_s[384 + r] + a.att_b);
+                kap = (red_s[512 + r] + red_s[640 + r] + red_s[768 + r] + red_s[896 + r]) * gate * (1.f - gate);
             }
             // ---- GEMM 2 operand: g_pre2 = (g_ef gate + kappa w_att) SiLU'(pre2) ----
 #pragma unroll
             for (int ci = 0; ci < CF::MYCH; ++ci) {
-                const int ch = half + 2 * ci;
-                if (2 * ci + half < 2 * na) {
+                const int ch = part + CF::NPARTS * ci;
+                if (ch < 2 * na) {
                     float4 x[4];
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
@@ -435,7 +438,7 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_bwd_kernel(PredEdgeArgs a
                         }
                         x[c4] = make_float4(t[0], t[1], t[2], t[3]);
                     }
-                    put_chunk<NP>(p, it0 + na + ((2 * ci + half) >> 1), r, half, x);
+                    put_chunk<NP>(p, it0 + na + (ch >> 1), r, half, x);
                 }
             }
             // ---- epilogue 2: g_pre1 = g_s1 * SiLU'(pre1); row / column sums; geometry gradients ----
@@ -444,7 +447,7 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_bwd_kernel(PredEdgeArgs a
             float pr = 0.f, pa = 0.f;
             const int t0 = g.tc_ptr[tile], t1 = g.tc_ptr[tile + 1];
 #pragma unroll 1
-            for (int ch = half; ch < nchunks; ch += 2) {
+            for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
                 float v[16];
                 tmem_ld16(lane_addr + CF::D2_COL + ch * 16, v);
 #pragma unroll
@@ -459,7 +462,7 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_bwd_kernel(PredEdgeArgs a
                         if (c0 < H) { pr = fmaf(vec_s[c0 + e], gp[e], pr); pa = fmaf(vec_s[NP + c0 + e], gp[e], pa); }
                     }
                 }
-                nbar(2 + half, 128);
+                nbar(2 + part, 128);
                 const int col = r & 15, c = ch * 16 + col;
                 for (int nl = r >> 4; nl < nn; nl += 8) {
                     float sum = 0.f;
@@ -471,15 +474,16 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_bwd_kernel(PredEdgeArgs a
                     for (int q = g.tc_start[ti]; q < g.tc_start[ti + 1]; ++q) sum += my_ef[g.cperm[q] * CF::EF_STRIDE + col];
                     if (c < H) atomicAdd(a.g_Pb + (size_t)g.tc_node[ti] * H + c, sum);
                 }
-                nbar(2 + half, 128);
+                nbar(2 + part, 128);
             }
             fence_before_sync();
             mbar_arrive(d_empty);
-            red_s[half * 128 + r] = pr;
-            red_s[256 + half * 128 + r] = pa;
-            nbar(1, 256);
-            if (half == 0) {
-                const float g_r = red_s[r] + red_s[128 + r], g_a = red_s[256 + r] + red_s[384 + r];
+            red_s[1024 + part * 128 + r] = pr;
+            red_s[1536 + part * 128 + r] = pa;
+            nbar(1, CF::NWORK);
+            if (part == 0) {
+                const float g_r = red_s[1024 + r] + red_s[1152 + r] + red_s[1280 + r] + red_s[1408 + r];
+                const float g_a = red_s[1536 + r] + red_s[1664 + r] + red_s[1792 + r] + red_s[1920 + r];
                 float gdx = 0.f, gdy = 0.f, gdz = 0.f;
                 if (valid) {
                     a.g_attr[e_lo + r] += g_a;
@@ -492,15 +496,15 @@ __global__ void __launch_bounds__(320, 1) tc_pred_edge_bwd_kernel(PredEdgeArgs a
                 }
                 gd_s[3 * r] = gdx; gd_s[3 * r + 1] = gdy; gd_s[3 * r + 2] = gdz;
             }
-            nbar(1, 256);
-            for (int idx = half * 128 + r; idx < nn * 3; idx += 256) {
+            nbar(1, CF::NWORK);
+            for (int idx = part * 128 + r; idx < nn * 3; idx += CF::NWORK) {
                 const int nl = idx / 3, d = idx - 3 * nl;
                 const int node = node_lo + nl;
                 float sum = a.g_xout[3 * node + d] * g.node_mask[node];
                 for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += gd_s[3 * mm + d];
                 atomicAdd(a.g_x + 3 * node + d, sum);
             }
-            nbar(1, 256);
+            nbar(1, CF::NWORK);
         }
     }
     fence_before_sync();
@@ -520,7 +524,7 @@ static void launch_bwd_t(const PredEdgeArgs& a, const float* wcimg_nt, const flo
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = a.g.n_tiles < sms ? a.g.n_tiles : sms;
-    tc_pred_edge_bwd_kernel<NP><<<grid, 320, CF::SMEM, s>>>(a, wcimg_nt, w2img_nt, H);
+    tc_pred_edge_bwd_kernel<NP><<<grid, CF::THREADS, CF::SMEM, s>>>(a, wcimg_nt, w2img_nt, H);
 }
 
 void launch_pred_edge_bwd_tc(int H, const PredEdgeArgs& a, const float* wcimg_nt, const float* w2img_nt, cudaStream_t s) {
@@ -546,8 +550,8 @@ static void launch_fwd_t(bool save, const PredEdgeArgs& a, const float* w2img, c
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = a.g.n_tiles < sms ? a.g.n_tiles : sms;
-    if (save) tc_pred_edge_fwd_kernel<NP, true><<<grid, 320, CF::SMEM, s>>>(a, w2img, wcimg, H);
-    else tc_pred_edge_fwd_kernel<NP, false><<<grid, 320, CF::SMEM, s>>>(a, w2img, wcimg, H);
+    if (save) tc_pred_edge_fwd_kernel<NP, true><<<grid, CF::THREADS, CF::SMEM, s>>>(a, w2img, wcimg, H);
+    else tc_pred_edge_fwd_kernel<NP, false><<<grid, CF::THREADS, CF::SMEM, s>>>(a, w2img, wcimg, H);
 }
 
 void launch_pred_edge_fwd_tc(int H, bool save, const PredEdgeArgs& a, const float* w2img, const float* wcimg, cudaStream_t s) {
