@@ -18,10 +18,13 @@ struct TcEdgeCfg {
     static constexpr int A_BYTES = 128 * ATOM_ROW_BYTES;
     static constexpr int W_BYTES = NP * ATOM_ROW_BYTES;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+    static constexpr int NPARTS = 4;                         // worker parts of 4 warps; part p owns 16-column chunks ch == p (mod 4)
+    static constexpr int NWORK = 128 * NPARTS;
+    static constexpr int THREADS = 64 + NWORK;
     static constexpr int MAXCH = (NP + 15) / 16;             // 16-column chunks
-    static constexpr int MYCH = (MAXCH + 1) / 2;             // chunks per worker half
+    static constexpr int MYCH = (MAXCH + NPARTS - 1) / NPARTS;
     static constexpr int EF_STRIDE = 17;
-    static constexpr int SCRATCH = 6 * NP * 4 + 2 * 128 * 4 + 2 * 128 * EF_STRIDE * 4 + 129 * 4 + 128 * 3 * 4 + 64;
+    static constexpr int SCRATCH = 6 * NP * 4 + NPARTS * 128 * 4 + NPARTS * 128 * EF_STRIDE * 4 + 129 * 4 + 128 * 3 * 4 + 64;
     static constexpr int SMEM = S * STAGE_BYTES + 1024 + 256 + SCRATCH;
     static constexpr int TMEM_COLS = NP <= 64 ? 64 : 256;
 };
@@ -29,7 +32,7 @@ struct TcEdgeCfg {
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 template <int NP, int MODE>
-__global__ void __launch_bounds__(320, 1) tc_den_edge_kernel(DenEdgeArgs a, const float* __restrict__ wimg, int H) {
+__global__ void __launch_bounds__(TcEdgeCfg<NP>::THREADS, 1) tc_den_edge_kernel(DenEdgeArgs a, const float* __restrict__ wimg, int H) {
     using CF = TcEdgeCfg<NP>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -39,14 +42,14 @@ __global__ void __launch_bounds__(320, 1) tc_den_edge_kernel(DenEdgeArgs a, cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 1);
     float* vec_s = reinterpret_cast<float*>(base + CF::S * CF::STAGE_BYTES + 256);    // [4][NP]: w_r, w_d, b2, vecw
     float* red_s = vec_s + 6 * NP;                                                       // [2][128]
-    float* ef_s = red_s + 2 * 128;                                                       // [2][128][17]
-    int* seg_s = reinterpret_cast<int*>(ef_s + 2 * 128 * CF::EF_STRIDE);                // [129]
+    float* ef_s = red_s + CF::NPARTS * 128;                                              // [NPARTS][128][17]
+    int* seg_s = reinterpret_cast<int*>(ef_s + CF::NPARTS * 128 * CF::EF_STRIDE);        // [129]
     float* tr_s = reinterpret_cast<float*>(seg_s + 129);                                 // [128][3]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < CF::S; ++s) { mbar_init(&full_a[s], 128); mbar_init(&full_w[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(d_full, 1); mbar_init(d_empty, 256);
+        for (int s = 0; s < CF::S; ++s) { mbar_init(&full_a[s], 256); mbar_init(&full_w[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(d_full, 1); mbar_init(d_empty, CF::NWORK);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<CF::TMEM_COLS>(tmem_slot);
@@ -102,12 +105,12 @@ __global__ void __launch_bounds__(320, 1) tc_den_edge_kernel(DenEdgeArgs a, cons
             }
         }
     } else {
-        const int group = warp & 3, half = (warp - 2) >> 2;
+        const int group = warp & 3, part = (warp - 2) >> 2, half = part & 1;
         const int r = group * 32 + lane;                       // tile row == TMEM lane
         const int ht = r;                                      // thread index inside this half (0..127)
         const uint32_t lane_addr = tmem_base + ((uint32_t)(group * 32) << 16);
         const int nchunks = (H + 15) / 16;
-        float* my_ef = ef_s + half * 128 * CF::EF_STRIDE;
+        float* my_ef = ef_s + part * 128 * CF::EF_STRIDE;
         uint32_t tcnt = 0;
         for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
             const int node_lo = g.tile_ptr[tile], node_hi = g.tile_ptr[tile + 1];
@@ -128,17 +131,17 @@ __global__ void __launch_bounds__(320, 1) tc_den_edge_kernel(DenEdgeArgs a, cons
                 }
                 if (MODE == 1 && a.cdiff) { ux = a.cdiff[3 * e]; uy = a.cdiff[3 * e + 1]; uz = a.cdiff[3 * e + 2]; }
             }
-            if (half == 0) for (int i = ht; i <= nn; i += 128) seg_s[i] = g.rowptr[node_lo + i] - e_lo;
+            if (part == 0) for (int i = ht; i <= nn; i += 128) seg_s[i] = g.rowptr[node_lo + i] - e_lo;
             // ---- build activation atoms ----
             const float* pa_row = a.P + (size_t)rown * (2 * H);
             const float* pb_row = a.P + (size_t)coln * (2 * H) + H;
-            for (int j = half; j < na; j += 2) {
+            for (int j = part >> 1; j < na; j += 2) {
                 const uint32_t it = tcnt * na + j;
                 const uint32_t s = it % CF::S, rr = it / CF::S;
-                float4 x[8];
+                float4 x[4];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int k0 = j * ATOM_K + 4 * c;
+                for (int c = 0; c < 4; ++c) {
+                    const int k0 = j * ATOM_K + 16 * half + 4 * c;
                     x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (valid && k0 < H) {
                         const float4 pa = __ldg(reinterpret_cast<const float4*>(pa_row + k0));
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(320, 1) tc_den_edge_kernel(DenEdgeArgs a, cons
                 if (rr > 0) mbar_wait(&empty[s], (rr - 1) & 1);
                 unsigned char* a_hi = base + s * CF::STAGE_BYTES;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) store_split(a_hi, a_hi + CF::A_BYTES, r, c, x[c]);
+                for (int c = 0; c < 4; ++c) store_split(a_hi, a_hi + CF::A_BYTES, r, 4 * half + c, x[c]);
                 fence_proxy_async();
                 mbar_arrive(&full_a[s]);
             }
@@ -162,10 +165,10 @@ __global__ void __launch_bounds__(320, 1) tc_den_edge_kernel(DenEdgeArgs a, cons
             mbar_wait(d_full, tcnt & 1);
             fence_after_sync();
             float m[CF::MYCH][16];
-            float part = 0.f;
+            float psum = 0.f;
 #pragma unroll
             for (int ci = 0; ci < CF::MYCH; ++ci) {
-                const int ch = half + 2 * ci;
+                const int ch = part + CF::NPARTS * ci;
                 if (ch < nchunks) {
                     tmem_ld16(lane_addr + ch * 16, m[ci]);
 #pragma unroll
@@ -173,35 +176,35 @@ __global__ void __launch_bounds__(320, 1) tc_den_edge_kernel(DenEdgeArgs a, cons
                         const int c = ch * 16 + q;
                         const float v = silu_f(m[ci][q] + vec_s[2 * NP + c]);     // padded columns: acc = 0, bias = 0 -> 0
                         m[ci][q] = v;
-                        part = fmaf(vec_s[3 * NP + c], v, part);
+                        psum = fmaf(vec_s[3 * NP + c], v, psum);
                     }
                 }
             }
             fence_before_sync();
             mbar_arrive(d_empty);                               // accumulator is in registers: the next tile's MMAs may start
-            red_s[half * 128 + r] = part;
-            named_bar(1, 256);
-            const float dot = red_s[r] + red_s[128 + r];
+            red_s[part * 128 + r] = psum;
+            named_bar(1, CF::NWORK);
+            const float dot = red_s[r] + red_s[128 + r] + red_s[256 + r] + red_s[384 + r];
             if (MODE == 0) {
                 const float gate = a.attention ? sigmoid_f(dot + a.att_b) : 1.f;
 #pragma unroll
                 for (int ci = 0; ci < CF::MYCH; ++ci) {
-                    const int ch = half + 2 * ci;
+                    const int ch = part + CF::NPARTS * ci;
                     if (ch < nchunks) {                          // uniform across the half
 #pragma unroll
                         for (int q = 0; q < 16; ++q) my_ef[r * CF::EF_STRIDE + q] = m[ci][q] * gate;
-                        named_bar(2 + half, 128);
+                        named_bar(2 + part, 128);
                         for (int nl = ht >> 4; nl < nn; nl += 8) {
                             const int col = ht & 15, c = ch * 16 + col;
                             float sum = 0.f;
                             for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += my_ef[mm * CF::EF_STRIDE + col];
                             if (c < H) a.agg[(size_t)(node_lo + nl) * H + c] = sum / a.normf;
                         }
-                        named_bar(2 + half, 128);
+                        named_bar(2 + part, 128);
                     }
                 }
             } else {
-                if (half == 0) {
+                if (part == 0) {
                     float sc;
                     if (a.use_tanh) {
                         const float th = tanhf(dot);
@@ -211,9 +214,9 @@ __global__ void __launch_bounds__(320, 1) tc_den_edge_kernel(DenEdgeArgs a, cons
                         tr_s[3 * r] = ux * sc; tr_s[3 * r + 1] = uy * sc; tr_s[3 * r + 2] = uz * sc;
                     }
                 }
-                named_bar(1, 256);
-                const int wt = half * 128 + ht;
-                for (int idx = wt; idx < nn * 3; idx += 256) {
+                named_bar(1, CF::NWORK);
+                const int wt = part * 128 + ht;
+                for (int idx = wt; idx < nn * 3; idx += CF::NWORK) {
                     const int nl = idx / 3, d = idx - 3 * nl;
                     float sum = 0.f;
                     for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += tr_s[3 * mm + d];
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(320, 1) tc_den_edge_kernel(DenEdgeArgs a, cons
                     a.x_out[3 * node + d] = (a.x[3 * node + d] + sum / a.normf) * g.node_mask[node];
                 }
             }
-            named_bar(1, 256);                                  // scratch (seg_s, red_s, tr_s) free for the next tile
+            named_bar(1, CF::NWORK);                                  // scratch (seg_s, red_s, tr_s) free for the next tile
         }
     }
     fence_before_sync();
@@ -242,8 +245,8 @@ static void launch_t(int mode, const DenEdgeArgs& a, const float* wimg, int H, c
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = a.g.n_tiles < sms ? a.g.n_tiles : sms;
-    if (mode == 0) tc_den_edge_kernel<NP, 0><<<grid, 320, CF::SMEM, s>>>(a, wimg, H);
-    else tc_den_edge_kernel<NP, 1><<<grid, 320, CF::SMEM, s>>>(a, wimg, H);
+    if (mode == 0) tc_den_edge_kernel<NP, 0><<<grid, CF::THREADS, CF::SMEM, s>>>(a, wimg, H);
+    else tc_den_edge_kernel<NP, 1><<<grid, CF::THREADS, CF::SMEM, s>>>(a, wimg, H);
 }
 
 void launch_den_edge_tc(int H, int mode, const DenEdgeArgs& a, const float* wimg, cudaStream_t s) {

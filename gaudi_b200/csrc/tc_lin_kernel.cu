@@ -20,10 +20,13 @@ struct TcLinCfg {
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
     static constexpr int SMEM = S * STAGE_BYTES + 1024 + 256;
     static constexpr int TMEM_COLS = 256;
+    static constexpr int NPARTS = 4;                          // worker parts of 4 warps; part p owns 16-column chunks ch == p (mod 4)
+    static constexpr int NWORK = 128 * NPARTS;
+    static constexpr int THREADS = 64 + NWORK;
 };
 
 template <int NP>
-__global__ void __launch_bounds__(320, 1) tc_lin_kernel(LinArgs a, const float* __restrict__ wimg, int H) {
+__global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, 1) tc_lin_kernel(LinArgs a, const float* __restrict__ wimg, int H) {
     using CF = TcLinCfg<NP>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -34,8 +37,8 @@ __global__ void __launch_bounds__(320, 1) tc_lin_kernel(LinArgs a, const float* 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < CF::S; ++s) { mbar_init(&full_a[s], 128); mbar_init(&full_w[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(d_full, 1); mbar_init(d_empty, 256);
+        for (int s = 0; s < CF::S; ++s) { mbar_init(&full_a[s], 256); mbar_init(&full_w[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(d_full, 1); mbar_init(d_empty, CF::NWORK);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<CF::TMEM_COLS>(tmem_slot);
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(320, 1) tc_lin_kernel(LinArgs a, const float* 
             }
         }
     } else {
-        const int group = warp & 3, half = (warp - 2) >> 2;
+        const int group = warp & 3, part = (warp - 2) >> 2, half = part & 1;
         const int r = group * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(group * 32) << 16);
         const int nchunks = (H + 15) / 16;
@@ -99,25 +102,26 @@ __global__ void __launch_bounds__(320, 1) tc_lin_kernel(LinArgs a, const float* 
             const bool rvalid = row < a.M;
             const float rs = (rvalid && a.rowscale) ? __ldg(a.rowscale + row) : 1.f;
             // ---- build the A atoms owned by this half ----
-            for (int j = half; j < na; j += 2) {
+            for (int j = part >> 1; j < na; j += 2) {
                 const uint32_t it = tcnt * na + j;
                 const uint32_t s = it % CF::S, rr = it / CF::S;
                 const bool first = j < na1;
                 const float* src = first ? a.A1 + (size_t)row * a.lda1 + j * ATOM_K : a.A2 + (size_t)row * a.lda2 + (j - na1) * ATOM_K;
                 const int kvalid = first ? a.K1 - j * ATOM_K : a.K2 - (j - na1) * ATOM_K;
-                float4 x[8];
+                float4 x[4];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
+                for (int c = 0; c < 4; ++c) {
+                    const int kc = 16 * half + 4 * c;
                     x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rvalid && 4 * c < kvalid) {
-                        x[c] = __ldg(reinterpret_cast<const float4*>(src + 4 * c));
+                    if (rvalid && kc < kvalid) {
+                        x[c] = __ldg(reinterpret_cast<const float4*>(src + kc));
                         x[c].x *= rs; x[c].y *= rs; x[c].z *= rs; x[c].w *= rs;
                     }
                 }
                 if (rr > 0) mbar_wait(&empty[s], (rr - 1) & 1);
                 unsigned char* a_hi = base + s * CF::STAGE_BYTES;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) store_split(a_hi, a_hi + CF::A_BYTES, r, c, x[c]);
+                for (int c = 0; c < 4; ++c) store_split(a_hi, a_hi + CF::A_BYTES, r, 4 * half + c, x[c]);
                 fence_proxy_async();
                 mbar_arrive(&full_a[s]);
             }
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(320, 1) tc_lin_kernel(LinArgs a, const float* 
             float mk = 1.f;
             if (rvalid && (a.epi == EPI_RES_MASK || (a.epi == EPI_ADD_RES && a.mask))) mk = __ldg(a.mask + row);
             const bool use_res = a.epi == EPI_RES_MASK || (a.epi == EPI_ADD_RES && (a.res_cb < 0 || cb == a.res_cb));
-            for (int ch = half; ch < nchunks; ch += 2) {
+            for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
                 float v[16];
                 tmem_ld16(lane_addr + ch * 16, v);
                 if (!rvalid) continue;
@@ -180,7 +184,7 @@ static void launch_t(const LinArgs& a, const float* wimg, int H, cudaStream_t s)
     int gx = n_tiles;
     const int cap = max(1, sms / a.ncb);
     if (gx > cap) gx = cap;
-    tc_lin_kernel<NP><<<dim3(gx, a.ncb), 320, CF::SMEM, s>>>(a, wimg, H);
+    tc_lin_kernel<NP><<<dim3(gx, a.ncb), CF::THREADS, CF::SMEM, s>>>(a, wimg, H);
 }
 
 int tc_np(int H) { return H <= 64 ? 64 : (H <= 192 ? 192 : (H <= 208 ? 208 : 256)); }

@@ -23,7 +23,7 @@ struct TcPredCfg {
     static constexpr int MAXCH = (NP + 15) / 16;
     static constexpr int MYCH = (MAXCH + NPARTS - 1) / NPARTS;
     static constexpr int EF_STRIDE = 17;
-    static constexpr int SCRATCH = 6 * NP * 4 + 4 * NPARTS * 128 * 4 + NPARTS * 128 * EF_STRIDE * 4 + 129 * 4 + 128 * 3 * 4 + 64;
+    static constexpr int SCRATCH = 6 * NP * 4 + 4 * NPARTS * 128 * 4 + NPARTS * 128 * EF_STRIDE * 4 + 129 * 4 + 128 * 3 * 4 + 64 + 3 * 132 * 4;
     static constexpr int SMEM = S * STAGE_BYTES + 1024 + 256 + SCRATCH;
     static constexpr int D2_COL = 256;
 };
@@ -198,13 +198,18 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
                 if (ch < nchunks) {
                     tmem_ld16(lane_addr + ch * 16, q[ci]);
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const int c = ch * 16 + e;
-                        const float pre = q[ci][e] + vec_s[2 * NP + c];
-                        if (SAVE && c < H) a.sv_pre2[((size_t)tile * H + c) * 128 + r] = pre;
-                        const float v = silu_f(pre);
-                        q[ci][e] = v;
-                        psum = fmaf(vec_s[3 * NP + c], v, psum);
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const int c0 = ch * 16 + 4 * c4;
+                        float pre[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            pre[e] = q[ci][4 * c4 + e] + vec_s[2 * NP + c0 + e];
+                            const float v = silu_f(pre[e]);
+                            q[ci][4 * c4 + e] = v;
+                            psum = fmaf(vec_s[3 * NP + c0 + e], v, psum);
+                        }
+                        if (SAVE && c0 < H)
+                            *reinterpret_cast<float4*>(a.sv_pre2 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4) = make_float4(pre[0], pre[1], pre[2], pre[3]);
                     }
                 }
             }
@@ -248,12 +253,17 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
                 float v[16];
                 tmem_ld16(lane_addr + CF::D2_COL + ch * 16, v);
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const int c = ch * 16 + e;
-                    float s3, d3;
-                    silu_both(v[e] + vec_s[4 * NP + c], s3, d3);
-                    if (SAVE && c < H) a.sv_d3[((size_t)tile * H + c) * 128 + r] = d3;
-                    phi_part = fmaf(vec_s[5 * NP + c], s3, phi_part);
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const int c0 = ch * 16 + 4 * c4;
+                    float d3[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float s3;
+                        silu_both(v[4 * c4 + e] + vec_s[4 * NP + c0 + e], s3, d3[e]);
+                        phi_part = fmaf(vec_s[5 * NP + c0 + e], s3, phi_part);
+                    }
+                    if (SAVE && c0 < H)
+                        *reinterpret_cast<float4*>(a.sv_d3 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4) = make_float4(d3[0], d3[1], d3[2], d3[3]);
                 }
             }
             fence_before_sync();
@@ -301,6 +311,9 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
     float* ef_s = red_s + 4 * CF::NPARTS * 128;                                                       // [2][128][17]
     int* seg_s = reinterpret_cast<int*>(ef_s + CF::NPARTS * 128 * CF::EF_STRIDE);
     float* gd_s = reinterpret_cast<float*>(seg_s + 129);                                 // [128][3]
+    int* cperm_s = reinterpret_cast<int*>(gd_s + 3 * 128);                               // [128] rows grouped by column node
+    int* tcs_s = cperm_s + 132;                                                          // [<=129] group starts (tile local)
+    int* tcn_s = tcs_s + 132;                                                            // [<=128] column node of each group
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -366,6 +379,12 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
                 else { gphi = gdotu; gux = gx * tau; guy = gy * tau; guz = gz * tau; }
             }
             if (part == 0) for (int i = r; i <= nn; i += 128) seg_s[i] = g.rowptr[node_lo + i] - e_lo;
+            const int t0 = g.tc_ptr[tile], t1 = g.tc_ptr[tile + 1], ntc = t1 - t0;
+            if (part == 1) {
+                if (r < ne) cperm_s[r] = g.cperm[e_lo + r];
+                for (int i = r; i <= ntc; i += 128) tcs_s[i] = g.tc_start[t0 + i] - e_lo;
+                for (int i = r; i < ntc; i += 128) tcn_s[i] = g.tc_node[t0 + i];
+            }
             const uint32_t it0 = tcnt * 2 * na;
             // ---- GEMM 1 operand: g_pre3 = g_phi * w_c * SiLU'(pre3) ----
             for (int j = part >> 1; j < na; j += 2) {
@@ -373,12 +392,13 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int k0 = j * ATOM_K + 16 * half + 4 * c;
-                    float t[4] = {0.f, 0.f, 0.f, 0.f};
+                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (k0 < H) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) t[e] = gphi * vec_s[5 * NP + k0 + e] * __ldg(a.sv_d3 + ((size_t)tile * H + k0 + e) * 128 + r);
+                        const float4 d3 = __ldg(reinterpret_cast<const float4*>(a.sv_d3 + (((size_t)tile * (H / 4) + (k0 >> 2)) * 128 + r) * 4));
+                        const float4 wl = *reinterpret_cast<const float4*>(vec_s + 5 * NP + k0);
+                        t = make_float4(gphi * wl.x * d3.x, gphi * wl.y * d3.y, gphi * wl.z * d3.z, gphi * wl.w * d3.w);
                     }
-                    x[c] = make_float4(t[0], t[1], t[2], t[3]);
+                    x[c] = t;
                 }
                 put_chunk<NP>(p, it0 + j, r, half, x);
             }
@@ -398,10 +418,12 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
                         const int c0 = ch * 16 + 4 * c4;
                         if (c0 < H) {
                             const float4 ga = __ldg(reinterpret_cast<const float4*>(ga_row + c0));
+                            const float4 p2 = __ldg(reinterpret_cast<const float4*>(a.sv_pre2 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4));
                             const float gadd[4] = {ga.x, ga.y, ga.z, ga.w};
+                            const float pv[4] = {p2.x, p2.y, p2.z, p2.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                const float qv = silu_f(__ldg(a.sv_pre2 + ((size_t)tile * H + c0 + e) * 128 + r));
+                                const float qv = silu_f(pv[e]);
                                 const float gv = gef[ci][4 * c4 + e] + gadd[e];
                                 gef[ci][4 * c4 + e] = gv;
                                 plog = fmaf(vec_s[3 * NP + c0 + e], qv, plog);
@@ -430,11 +452,11 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
                         const int c0 = ch * 16 + 4 * c4;
                         float t[4] = {0.f, 0.f, 0.f, 0.f};
                         if (ch < nchunks && c0 < H && valid) {
+                            const float4 p2 = __ldg(reinterpret_cast<const float4*>(a.sv_pre2 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4));
+                            const float pv[4] = {p2.x, p2.y, p2.z, p2.w};
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float pre = __ldg(a.sv_pre2 + ((size_t)tile * H + c0 + e) * 128 + r);
-                                t[e] = (gef[ci][4 * c4 + e] * gate + kap * vec_s[3 * NP + c0 + e]) * dsilu_f(pre);
-                            }
+                            for (int e = 0; e < 4; ++e)
+                                t[e] = (gef[ci][4 * c4 + e] * gate + kap * vec_s[3 * NP + c0 + e]) * dsilu_f(pv[e]);
                         }
                         x[c4] = make_float4(t[0], t[1], t[2], t[3]);
                     }
@@ -445,7 +467,6 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
             mbar_wait(d2_full, tcnt & 1);
             fence_after_sync();
             float pr = 0.f, pa = 0.f;
-            const int t0 = g.tc_ptr[tile], t1 = g.tc_ptr[tile + 1];
 #pragma unroll 1
             for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
                 float v[16];
@@ -469,10 +490,10 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
                     for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += my_ef[mm * CF::EF_STRIDE + col];
                     if (c < H) a.g_Pa[(size_t)(node_lo + nl) * H + c] = sum;
                 }
-                for (int ti = t0 + (r >> 4); ti < t1; ti += 8) {
+                for (int ti = r >> 4; ti < ntc; ti += 8) {
                     float sum = 0.f;
-                    for (int q = g.tc_start[ti]; q < g.tc_start[ti + 1]; ++q) sum += my_ef[g.cperm[q] * CF::EF_STRIDE + col];
-                    if (c < H) atomicAdd(a.g_Pb + (size_t)g.tc_node[ti] * H + c, sum);
+                    for (int q = tcs_s[ti]; q < tcs_s[ti + 1]; ++q) sum += my_ef[cperm_s[q] * CF::EF_STRIDE + col];
+                    if (c < H) atomicAdd(a.g_Pb + (size_t)tcn_s[ti] * H + c, sum);
                 }
                 nbar(2 + part, 128);
             }
