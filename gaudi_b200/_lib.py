@@ -45,6 +45,12 @@ SIGNATURES = {
     "gb_sample_loop": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _U64, _P, _P, _SZ, _I, _P]),
     "gb_sample_loop_workspace_bytes": (_SZ, [_P, _P, _P]),
     "gb_profile_kernel": (_I, [_P, _P, _I, _I, _P, _SZ, _I, _P]),
+    "gb_den_gcl_forward": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _SZ, _P]),
+    "gb_den_equiv_forward": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "gb_den_block_forward": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "gb_den_egnn_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "gb_pred_layer_forward": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "gb_pred_egnn_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
 }
 
 

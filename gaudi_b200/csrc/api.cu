@@ -592,6 +592,157 @@ extern "C" int gb_predictor_input_grad(const gb_net* net, const gb_graph* g, con
 }
 
 // ------------------------------------------------------------------------------------------------------
+// sub-module forwards (inference only): GCL / EquivariantUpdate / EquivariantBlock / EGNN / E_GCL / predictor EGNN.
+// Node tensors are [n_nodes, H] with H == padded hidden width (hidden_nf in {64,192,196,256}).
+// ------------------------------------------------------------------------------------------------------
+static int check_layer_api(const gb_net* n, int kind, int layer) {
+    if (!n) return fail("null net");
+    if (n->kind != kind) return fail("wrong network kind for this call");
+    if (n->H != n->HP) return fail("sub-module API needs hidden_nf in {64,192,196,256} (got %d)", n->H);
+    if (layer < 0 || layer >= n->L) return fail("layer index %d out of range", layer);
+    return 0;
+}
+
+static DenEdgeArgs den_args_base(const gb_net* n, const Graph& g) {
+    DenEdgeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = g; a.use_tanh = n->use_tanh; a.norm_constant = n->norm_constant; a.normf = n->normf; a.coords_range = n->coords_range;
+    return a;
+}
+
+static void run_den_gcl(const gb_net* n, const Graph& g, const DenGcl& G, const DenWs& w, const float* h, float* h_out,
+                        const float* x, const float* x0, const float* eattr, const float* d0_edge, cudaStream_t s) {
+    lin_P(n, G.e, h, w.P, g.n_nodes, s);
+    DenEdgeArgs a = den_args_base(n, g);
+    a.P = w.P; a.ext = n->p(G.e.l1_ext); a.wt2 = n->p(G.e.l2_wt); a.b2 = n->p(G.e.l2_b); a.vecw = n->p(G.att_w);
+    a.att_b = G.att_b; a.attention = n->attention; a.x = x; a.x0 = x0; a.eattr = eattr; a.d0_edge = d0_edge; a.agg = w.agg;
+    if (n->tc_den) launch_den_edge_tc(n->HP, 0, a, n->p(G.e.l2_tc), s); else launch_den_edge(n->HP, 0, a, s);
+    GB_LAUNCHED(1);
+    node_update(n, G.n, h, w.agg, w.s, h_out, nullptr, g, s);
+}
+
+static void run_den_equiv(const gb_net* n, const Graph& g, const DenEquiv& E, const DenWs& w, const float* h, const float* x,
+                          const float* x0, const float* cdiff, const float* eattr, const float* d0_edge, float* x_out, cudaStream_t s) {
+    lin_P(n, E.c, h, w.P, g.n_nodes, s);
+    DenEdgeArgs a = den_args_base(n, g);
+    a.P = w.P; a.ext = n->p(E.c.l1_ext); a.wt2 = n->p(E.c.l2_wt); a.b2 = n->p(E.c.l2_b); a.vecw = n->p(E.last_w);
+    a.x = x; a.x0 = x0; a.cdiff = cdiff; a.eattr = eattr; a.d0_edge = d0_edge; a.x_out = x_out;
+    if (n->tc_den) launch_den_edge_tc(n->HP, 1, a, n->p(E.c.l2_tc), s); else launch_den_edge(n->HP, 1, a, s);
+    GB_LAUNCHED(1);
+}
+
+extern "C" int gb_den_gcl_forward(const gb_net* n, const gb_graph* gg, int block, int sub, const float* h_in, const float* eattr,
+                                  float* h_out, void* ws, size_t ws_bytes, void* stream) {
+    if (check_layer_api(n, 0, block)) return 1;
+    if (sub < 0 || sub >= n->n_sub || !gg || !h_in || !eattr || !h_out) return fail("bad argument");
+    Bump b(ws, ws_bytes); DenWs w; carve_den(b, n, gg->g, w);
+    if (b.off > ws_bytes) return fail("workspace too small");
+    run_den_gcl(n, gg->g, n->gcl[(size_t)block * n->n_sub + sub], w, h_in, h_out, nullptr, nullptr, eattr, nullptr, (cudaStream_t)stream);
+    return check_launch("gcl_forward");
+}
+
+extern "C" int gb_den_equiv_forward(const gb_net* n, const gb_graph* gg, int block, const float* h_in, const float* x_in,
+                                    const float* cdiff, const float* eattr, float* x_out, void* ws, size_t ws_bytes, void* stream) {
+    if (check_layer_api(n, 0, block)) return 1;
+    if (!gg || !h_in || !x_in || !cdiff || !eattr || !x_out) return fail("bad argument");
+    Bump b(ws, ws_bytes); DenWs w; carve_den(b, n, gg->g, w);
+    if (b.off > ws_bytes) return fail("workspace too small");
+    run_den_equiv(n, gg->g, n->eq[block], w, h_in, x_in, x_in, cdiff, eattr, nullptr, x_out, (cudaStream_t)stream);
+    return check_launch("equiv_forward");
+}
+
+// EquivariantBlock.forward: h, x -> h', x' with the second edge attribute given per compacted edge
+extern "C" int gb_den_block_forward(const gb_net* n, const gb_graph* gg, int block, const float* h_in, const float* x_in,
+                                    const float* d0_edge, float* h_out, float* x_out, void* ws, size_t ws_bytes, void* stream) {
+    if (check_layer_api(n, 0, block)) return 1;
+    if (!gg || !h_in || !x_in || !d0_edge || !h_out || !x_out) return fail("bad argument");
+    const Graph& g = gg->g; cudaStream_t s = (cudaStream_t)stream;
+    Bump b(ws, ws_bytes); DenWs w; carve_den(b, n, g, w);
+    if (b.off > ws_bytes) return fail("workspace too small");
+    const float* h = h_in;
+    for (int q = 0; q < n->n_sub; ++q) {
+        float* dst = (q + 1 == n->n_sub) ? h_out : ((q & 1) ? w.h2 : w.h);
+        run_den_gcl(n, g, n->gcl[(size_t)block * n->n_sub + q], w, h, dst, x_in, x_in, nullptr, d0_edge, s);
+        h = dst;
+    }
+    run_den_equiv(n, g, n->eq[block], w, h, x_in, x_in, nullptr, nullptr, d0_edge, x_out, s);
+    return check_launch("block_forward");
+}
+
+// EGNN.forward of the denoiser: h_in [n, F+1] (time column included), x_in -> h_out [n, F+1], x_out
+extern "C" int gb_den_egnn_forward(const gb_net* n, const gb_graph* gg, const float* h_in, const float* x_in, float* h_out,
+                                   float* x_out, void* ws, size_t ws_bytes, void* stream) {
+    if (check_layer_api(n, 0, 0)) return 1;
+    if (!gg || !h_in || !x_in || !h_out || !x_out) return fail("bad argument");
+    const Graph& g = gg->g; cudaStream_t s = (cudaStream_t)stream;
+    Bump b(ws, ws_bytes); DenWs w; carve_den(b, n, g, w);
+    if (b.off > ws_bytes) return fail("workspace too small");
+    launch_embed_plain(h_in, n->F + 1, n->p(n->emb_w), n->p(n->emb_b), g.n_nodes, n->H, n->HP, w.h, s); GB_LAUNCHED(1);
+    GB_CUDA(cudaMemcpyAsync(w.x0, x_in, (size_t)g.n_nodes * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    float *h = w.h, *h2 = w.h2; const float* xc = w.x0; float* xn = w.xa;
+    for (int blk = 0; blk < n->L; ++blk) {
+        for (int q = 0; q < n->n_sub; ++q) {
+            run_den_gcl(n, g, n->gcl[(size_t)blk * n->n_sub + q], w, h, h2, xc, w.x0, nullptr, nullptr, s);
+            float* tmp = h; h = h2; h2 = tmp;
+        }
+        float* dst = (blk + 1 == n->L) ? x_out : xn;
+        run_den_equiv(n, g, n->eq[blk], w, h, xc, w.x0, nullptr, nullptr, nullptr, dst, s);
+        xc = dst; xn = (xn == w.xa) ? w.xb : w.xa;
+    }
+    EmbedOutArgs eo{h, n->HP, n->H, n->p(n->out_w), n->p(n->out_b), n->F + 1, g.node_mask, g.n_nodes, h_out, n->F + 1};
+    launch_embed_out(eo, s); GB_LAUNCHED(1);
+    return check_launch("egnn_forward");
+}
+
+// E_GCL.forward: h, coord, edge_attr (per compacted edge) -> h', coord'
+extern "C" int gb_pred_layer_forward(const gb_net* n, const gb_graph* gg, int layer, const float* h_in, const float* x_in,
+                                     const float* a_edge, float* h_out, float* x_out, void* ws, size_t ws_bytes, void* stream) {
+    if (check_layer_api(n, 1, layer)) return 1;
+    if (!gg || !h_in || !x_in || !a_edge || !h_out || !x_out) return fail("bad argument");
+    const Graph& g = gg->g; cudaStream_t s = (cudaStream_t)stream;
+    Bump b(ws, ws_bytes); PredWs w; carve_pred(b, n, g, false, w);
+    if (b.off > ws_bytes) return fail("workspace too small");
+    const PredLayer& Lr = n->pl[layer];
+    lin_P(n, Lr.e, h_in, w.P, g.n_nodes, s);
+    PredEdgeArgs a = pred_edge_args(n, Lr, g, w, 0, false);
+    a.x = x_in; a.x0 = x_in; a.a_edge = a_edge; a.x_out = x_out;
+    if (n->tc_pred) launch_pred_edge_fwd_tc(n->HP, false, a, n->p(Lr.e.l2_tc), n->p(Lr.c_tc), s);
+    else launch_pred_edge_fwd(n->HP, false, a, s);
+    GB_LAUNCHED(1);
+    node_update(n, Lr.n, h_in, w.agg, w.s, h_out, nullptr, g, s);
+    return check_launch("e_gcl_forward");
+}
+
+// predictor EGNN.forward: h_in [n, F+1], x_in, edge_attr per compacted edge -> h_out [n, out_nf] (masked), x_out
+extern "C" int gb_pred_egnn_forward(const gb_net* n, const gb_graph* gg, const float* h_in, const float* x_in, const float* a_edge,
+                                    float* h_out, float* x_out, void* ws, size_t ws_bytes, void* stream) {
+    if (check_layer_api(n, 1, 0)) return 1;
+    if (!gg || !h_in || !x_in || !a_edge || !h_out || !x_out) return fail("bad argument");
+    const Graph& g = gg->g; cudaStream_t s = (cudaStream_t)stream;
+    Bump b(ws, ws_bytes); PredWs w; carve_pred(b, n, g, false, w);
+    if (b.off > ws_bytes) return fail("workspace too small");
+    const size_t nn = g.n_nodes;
+    launch_embed_plain(h_in, n->F + 1, n->p(n->emb_w), n->p(n->emb_b), g.n_nodes, n->H, n->HP, w.h, s); GB_LAUNCHED(1);
+    GB_CUDA(cudaMemcpyAsync(w.x, x_in, nn * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    float *h = w.h, *h2 = w.h2;
+    for (int l = 0; l < n->L; ++l) {
+        const PredLayer& Lr = n->pl[l];
+        lin_P(n, Lr.e, h, w.P, g.n_nodes, s);
+        PredEdgeArgs a = pred_edge_args(n, Lr, g, w, l, false);
+        a.a_edge = a_edge;
+        if (l + 1 == n->L) a.x_out = x_out;
+        if (n->tc_pred) launch_pred_edge_fwd_tc(n->HP, false, a, n->p(Lr.e.l2_tc), n->p(Lr.c_tc), s);
+        else launch_pred_edge_fwd(n->HP, false, a, s);
+        GB_LAUNCHED(1);
+        node_update(n, Lr.n, h, w.agg, w.s, h2, nullptr, g, s);
+        float* tmp = h; h = h2; h2 = tmp;
+    }
+    EmbedOutArgs eo{h, n->HP, n->H, n->p(n->out_w), n->p(n->out_b), n->out_nf, g.node_mask, g.n_nodes, h_out, n->out_nf};
+    launch_embed_out(eo, s); GB_LAUNCHED(1);
+    return check_launch("pred_egnn_forward");
+}
+
+// ------------------------------------------------------------------------------------------------------
 // step pieces
 // ------------------------------------------------------------------------------------------------------
 extern "C" int gb_step_sample(const float* zt, const float* eps, const float* noise, const float* coef,

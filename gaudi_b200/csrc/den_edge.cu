@@ -67,6 +67,7 @@ __global__ void __launch_bounds__((TileCfg<HP>::NW + 1) * 32, 1) den_edge_kernel
                     r = dx * dx + dy * dy + dz * dz;                                  // coord2diff, egnn_new.py:394-400
                     const float ex = a.x0[3 * row] - a.x0[3 * col], ey = a.x0[3 * row + 1] - a.x0[3 * col + 1], ez = a.x0[3 * row + 2] - a.x0[3 * col + 2];
                     d0 = ex * ex + ey * ey + ez * ez;
+                    if (a.d0_edge) d0 = a.d0_edge[e];
                     if (MODE == 1) {
                         const float inv = 1.f / (sqrtf(r + 1e-8f) + a.norm_constant);
                         ux = dx * inv; uy = dy * inv; uz = dz * inv;

@@ -68,6 +68,8 @@ struct EmbedOutArgs {
     float* out; int ldo;
 };
 void launch_embed_out(const EmbedOutArgs& a, cudaStream_t s);
+// plain small-K Linear h0 = W h_in + b (EGNN.forward of the sub-module API)
+void launch_embed_plain(const float* h_in, int K, const float* w, const float* b, int n_nodes, int H, int HP, float* h, cudaStream_t s);
 
 // ---- denoiser edge kernels (GCL message / EquivariantUpdate) -----------------------------------
 struct DenEdgeArgs {
@@ -83,6 +85,7 @@ struct DenEdgeArgs {
     const float* x0;           // coords at network input (second edge attribute)
     const float* eattr;        // optional explicit [n_edges][2] edge attributes (module-level API); else null
     const float* cdiff;        // optional explicit [n_edges][3] coord_diff (module-level API)
+    const float* d0_edge;      // optional explicit second edge attribute per compacted edge (EquivariantBlock.forward)
     float* agg;                // mode 0 out [n_nodes, HP]
     float* x_out;              // mode 1 out [n_nodes, 3]
 };
@@ -100,6 +103,7 @@ struct PredEdgeArgs {
     const float* wc_last;                     // coord_mlp.2 weight [HP]
     int use_tanh; float coords_range;
     const float* x; const float* x0;          // current / input coordinates
+    const float* a_edge;                      // optional explicit edge_attr per compacted edge (E_GCL.forward); else |x0_i-x0_j|^2
     float* agg; float* x_out;                 // forward outputs
     // activations saved for the input-gradient pass (null = inference only)
     float* sv_d1; float* sv_pre2; float* sv_d3; float* sv_tau;   // [n_tiles][HP][128] x3, [n_edges]

@@ -174,6 +174,24 @@ void launch_embed_in(const EmbedInArgs& a, cudaStream_t s) {
     embed_in_kernel<<<blocks, 256, 0, s>>>(a);
 }
 
+__global__ void embed_plain_kernel(const float* h_in, int K, const float* w, const float* b, int n_nodes, int H, int HP, float* h) {
+    const long long total = (long long)n_nodes * HP;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int node = (int)(idx / HP), c = (int)(idx % HP);
+        float v = 0.f;
+        if (c < H) {
+            v = b[c];
+            for (int k = 0; k < K; ++k) v = fmaf(h_in[(size_t)node * K + k], w[(size_t)c * K + k], v);
+        }
+        h[idx] = v;
+    }
+}
+
+void launch_embed_plain(const float* h_in, int K, const float* w, const float* b, int n_nodes, int H, int HP, float* h, cudaStream_t s) {
+    const long long total = (long long)n_nodes * HP;
+    embed_plain_kernel<<<(int)min((long long)148 * 16, (total + 255) / 256), 256, 0, s>>>(h_in, K, w, b, n_nodes, H, HP, h);
+}
+
 __global__ void embed_out_kernel(EmbedOutArgs a) {
     // one warp per node, lanes stride over k; n_out <= 16
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;

@@ -114,6 +114,7 @@ __global__ void __launch_bounds__((TileCfg<HP>::NW + 1) * 32, 1) pred_edge_fwd_k
                 ux = dx * inv; uy = dy * inv; uz = dz * inv;
                 const float ex = a.x0[3 * row] - a.x0[3 * col], ey = a.x0[3 * row + 1] - a.x0[3 * col + 1], ez = a.x0[3 * row + 2] - a.x0[3 * col + 2];
                 a0 = ex * ex + ey * ey + ez * ez;
+                if (a.a_edge) a0 = a.a_edge[e];
             }
             S.row_s[m] = row; S.col_s[m] = col; r_s[m] = r; a0_s[m] = a0;
             u_s[3 * m] = ux; u_s[3 * m + 1] = uy; u_s[3 * m + 2] = uz;

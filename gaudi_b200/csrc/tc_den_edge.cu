@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(TcEdgeCfg<NP>::THREADS, 1) tc_den_edge_kernel(
                     rad = dx * dx + dy * dy + dz * dz;
                     const float ex = a.x0[3 * rown] - a.x0[3 * coln], ey = a.x0[3 * rown + 1] - a.x0[3 * coln + 1], ez = a.x0[3 * rown + 2] - a.x0[3 * coln + 2];
                     d0 = ex * ex + ey * ey + ez * ez;
+                    if (a.d0_edge) d0 = a.d0_edge[e];
                     if (MODE == 1) { const float inv = 1.f / (sqrtf(rad + 1e-8f) + a.norm_constant); ux = dx * inv; uy = dy * inv; uz = dz * inv; }
                 }
                 if (MODE == 1 && a.cdiff) { ux = a.cdiff[3 * e]; uy = a.cdiff[3 * e + 1]; uz = a.cdiff[3 * e + 2]; }

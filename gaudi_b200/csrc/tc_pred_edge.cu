@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
                 ux = dx * inv; uy = dy * inv; uz = dz * inv;
                 const float ex = a.x0[3 * rown] - a.x0[3 * coln], ey = a.x0[3 * rown + 1] - a.x0[3 * coln + 1], ez = a.x0[3 * rown + 2] - a.x0[3 * coln + 2];
                 a0 = ex * ex + ey * ey + ez * ez;
+                if (a.a_edge) a0 = a.a_edge[e];
             }
             if (part == 0) for (int i = r; i <= nn; i += 128) seg_s[i] = g.rowptr[node_lo + i] - e_lo;
             const uint32_t it0 = tcnt * 2 * na;

@@ -65,6 +65,7 @@ class Topology:
     tc_start: torch.Tensor
     cperm: torch.Tensor
     node_mask: torch.Tensor     # flat fp32 [B*N]
+    dense_idx: torch.Tensor = None   # int64 [n_edges]: position of every kept edge in the dense B*N*N list
 
 
 def tile_pack(rowptr_host: np.ndarray) -> np.ndarray:
@@ -112,4 +113,4 @@ def build_topology(node_mask: torch.Tensor, edge_mask: torch.Tensor, B: int, N: 
     tc_ptr = torch.searchsorted(tc_tile.contiguous(), torch.arange(n_tiles + 1, device=dev), right=False)
     i32 = lambda t: t.to(torch.int32).contiguous()
     return Topology(B, N, n_edges, n_tiles, n_tc, i32(rowptr), i32(erow), i32(ecol), i32(tile_ptr), i32(tc_ptr),
-                    i32(tc_node), i32(tc_start), i32(cperm), nm)
+                    i32(tc_node), i32(tc_start), i32(cperm), nm, flat)

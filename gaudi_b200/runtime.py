@@ -345,32 +345,201 @@ def launch_count(reset: bool = False) -> int:
     return int(_lib.lib().gb_launch_count(int(reset)))
 
 
-# ---- module-level forwards (sub-module API surface) -------------------------------------------------
-def _unsupported(name: str):
-    raise NotImplementedError(
-        f"gaudi_b200: stand-alone {name}.forward is not exposed; the fused kernels are reached through "
-        "EGNN_dynamics._forward / EGNN_predictor.forward (same parameters, same state_dict)")
+# ---- module-level forwards (sub-module API surface, inference only) ---------------------------------
+def _dummy_linear(out_f, in_f, device, bias=True):
+    w = torch.zeros(out_f, in_f, dtype=torch.float32, device=device)
+    return [w, torch.zeros(out_f, dtype=torch.float32, device=device)] if bias else [w]
+
+
+def _gcl_params(g):
+    ps = [g.edge_mlp[0].weight, g.edge_mlp[0].bias, g.edge_mlp[2].weight, g.edge_mlp[2].bias,
+          g.node_mlp[0].weight, g.node_mlp[0].bias, g.node_mlp[2].weight, g.node_mlp[2].bias]
+    if g.attention:
+        ps += [g.att_mlp[0].weight, g.att_mlp[0].bias]
+    return ps
+
+
+def _equiv_params(e):
+    return [e.coord_mlp[0].weight, e.coord_mlp[0].bias, e.coord_mlp[2].weight, e.coord_mlp[2].bias, e.coord_mlp[4].weight]
+
+
+def _sub_handle(mod, kind: str, ps: List[torch.Tensor], **cfg) -> NetHandle:
+    """One-layer network handle built from a stand-alone sub-module's own parameters (cached on the module)."""
+    _need_cuda(ps[0], "module parameters")
+    ver = _versions(ps)
+    h = mod.__dict__.get("_gb_handle")
+    if h is None or h.versions != ver:
+        tens = [_f32c(p) for p in ps]
+        arr = (_VP * len(tens))(*[t.data_ptr() for t in tens])
+        out = _VP(0)
+        L = _lib.lib()
+        if kind == "den":
+            _lib.check(L.gb_denoiser_create(C.byref(out), 0, cfg["hidden"], cfg.get("n_layers", 1), cfg["n_sub"],
+                                            int(cfg["attention"]), int(cfg["tanh"]), float(cfg["coords_range"]),
+                                            float(cfg["norm_constant"]), float(cfg["normf"]), arr, len(tens), _stream()))
+        else:
+            _lib.check(L.gb_predictor_create(C.byref(out), 0, 1, cfg["hidden"], 1, int(cfg["attention"]),
+                                             int(cfg["tanh"]), float(cfg["coords_range"]), arr, len(tens), _stream()))
+        h = NetHandle(out.value, tens, ver)
+        mod.__dict__["_gb_handle"] = h
+    return h
+
+
+def _flat_graph(h, edge_index, node_mask, edge_mask):
+    """Graph handle for flattened [B*N, .] inputs; N is recovered from the dense edge list length."""
+    _need_cuda(h, "h")
+    n_nodes = h.shape[0]
+    row = edge_index[0]
+    n = row.numel() // n_nodes
+    if n * n_nodes != row.numel():
+        raise ValueError("edge_index is not the dense per-graph edge list of get_adj_matrix")
+    B = n_nodes // n
+    if node_mask is None:
+        node_mask = torch.ones(n_nodes, 1, dtype=torch.float32, device=h.device)
+    if edge_mask is None:
+        edge_mask = torch.ones(row.numel(), 1, dtype=torch.float32, device=h.device)
+    g = graph_for(node_mask, edge_mask, B, n)
+    return g, B, n
+
+
+def _den_ws(net, g, device):
+    nbytes = _lib.lib().gb_denoiser_workspace_bytes(net.handle, g.handle)
+    return workspace("den", device).get(nbytes, device)
+
+
+def _edge_gather(t, g, width):
+    return _f32c(t.reshape(-1, width)[g.topo.dense_idx])
 
 
 def gcl_forward(mod, h, edge_index, edge_attr, node_mask, edge_mask):
-    _unsupported("GCL")
+    g, B, n = _flat_graph(h, edge_index, node_mask, edge_mask)
+    H = mod.node_mlp[2].out_features
+    ps = _dummy_linear(H, 1, h.device) + _dummy_linear(1, H, h.device) + _gcl_params(mod) + \
+        _dummy_linear(H, 2 * H + 2, h.device) + _dummy_linear(H, H, h.device) + _dummy_linear(1, H, h.device, bias=False)
+    net = _sub_handle(mod, "den", ps, hidden=H, n_sub=1, attention=mod.attention, tanh=False, coords_range=1.0,
+                      norm_constant=1.0, normf=mod.normalization_factor)
+    hin = _f32c(h)
+    out = torch.empty_like(hin)
+    ws = _den_ws(net, g, h.device)
+    ea = _edge_gather(edge_attr, g, 2)            # keep alive across the call
+    _lib.check(_lib.lib().gb_den_gcl_forward(net.handle, g.handle, 0, 0, _ptr(hin), _ptr(ea),
+                                             _ptr(out), _ptr(ws), ws.numel(), _stream()))
+    return out
 
 
 def equiv_update_forward(mod, h, coord, edge_index, coord_diff, edge_attr, node_mask, edge_mask):
-    _unsupported("EquivariantUpdate")
+    g, B, n = _flat_graph(h, edge_index, node_mask, edge_mask)
+    H = mod.coord_mlp[2].out_features
+    ps = _dummy_linear(H, 1, h.device) + _dummy_linear(1, H, h.device) + _dummy_linear(H, 2 * H + 2, h.device) + \
+        _dummy_linear(H, H, h.device) + _dummy_linear(H, 2 * H, h.device) + _dummy_linear(H, H, h.device) + _equiv_params(mod)
+    net = _sub_handle(mod, "den", ps, hidden=H, n_sub=1, attention=False, tanh=mod.tanh, coords_range=mod.coords_range,
+                      norm_constant=1.0, normf=mod.normalization_factor)
+    hin, xin = _f32c(h), _f32c(coord)
+    out = torch.empty_like(xin)
+    ws = _den_ws(net, g, h.device)
+    cd, ea = _edge_gather(coord_diff, g, 3), _edge_gather(edge_attr, g, 2)
+    _lib.check(_lib.lib().gb_den_equiv_forward(net.handle, g.handle, 0, _ptr(hin), _ptr(xin), _ptr(cd), _ptr(ea),
+                                               _ptr(out), _ptr(ws), ws.numel(), _stream()))
+    return out
+
+
+def _block_params(blk):
+    ps = []
+    for s in range(blk.n_layers):
+        ps += _gcl_params(getattr(blk, f"gcl_{s}"))
+    return ps + _equiv_params(blk.gcl_equiv)
 
 
 def equiv_block_forward(mod, h, x, edge_index, node_mask, edge_mask, edge_attr):
-    _unsupported("EquivariantBlock")
+    g, B, n = _flat_graph(h, edge_index, node_mask, edge_mask)
+    H = mod.hidden_nf
+    ps = _dummy_linear(H, 1, h.device) + _dummy_linear(1, H, h.device) + _block_params(mod)
+    net = _sub_handle(mod, "den", ps, hidden=H, n_sub=mod.n_layers, attention=mod.gcl_0.attention, tanh=mod.gcl_equiv.tanh,
+                      coords_range=mod.coords_range_layer, norm_constant=mod.norm_constant, normf=mod.normalization_factor)
+    hin, xin = _f32c(h), _f32c(x)
+    hout, xout = torch.empty_like(hin), torch.empty_like(xin)
+    ws = _den_ws(net, g, h.device)
+    d0 = _edge_gather(edge_attr, g, 1)
+    _lib.check(_lib.lib().gb_den_block_forward(net.handle, g.handle, 0, _ptr(hin), _ptr(xin), _ptr(d0), _ptr(hout),
+                                               _ptr(xout), _ptr(ws), ws.numel(), _stream()))
+    return hout, xout
 
 
 def egnn_forward(mod, h, x, edge_index, node_mask, edge_mask):
-    _unsupported("EGNN")
+    g, B, n = _flat_graph(h, edge_index, node_mask, edge_mask)
+    ps = _param_list_denoiser(mod)
+    _need_cuda(ps[0], "EGNN parameters")
+    ver = _versions(ps)
+    net = mod.__dict__.get("_gb_handle")
+    if net is None or net.versions != ver:
+        tens = [_f32c(p) for p in ps]
+        arr = (_VP * len(tens))(*[t.data_ptr() for t in tens])
+        out = _VP(0)
+        b0 = mod.e_block_0
+        _lib.check(_lib.lib().gb_denoiser_create(
+            C.byref(out), mod.embedding.in_features - 1, mod.hidden_nf, mod.n_layers, b0.n_layers, int(b0.gcl_0.attention),
+            int(b0.gcl_equiv.tanh), float(b0.coords_range_layer), float(b0.norm_constant), float(mod.normalization_factor),
+            arr, len(tens), _stream()))
+        net = NetHandle(out.value, tens, ver)
+        mod.__dict__["_gb_handle"] = net
+    hin, xin = _f32c(h), _f32c(x)
+    hout, xout = torch.empty(hin.shape[0], mod.embedding_out.out_features, dtype=torch.float32, device=h.device), torch.empty_like(xin)
+    ws = _den_ws(net, g, h.device)
+    _lib.check(_lib.lib().gb_den_egnn_forward(net.handle, g.handle, _ptr(hin), _ptr(xin), _ptr(hout), _ptr(xout), _ptr(ws),
+                                              ws.numel(), _stream()))
+    return hout, xout
+
+
+def _egcl_params(g):
+    ps = [g.edge_mlp[0].weight, g.edge_mlp[0].bias, g.edge_mlp[2].weight, g.edge_mlp[2].bias,
+          g.node_mlp[0].weight, g.node_mlp[0].bias, g.node_mlp[2].weight, g.node_mlp[2].bias,
+          g.coord_mlp[0].weight, g.coord_mlp[0].bias, g.coord_mlp[2].weight]
+    if g.attention:
+        ps += [g.att_mlp[0].weight, g.att_mlp[0].bias]
+    return ps
+
+
+def _pred_ws(net, g, device):
+    nbytes = _lib.lib().gb_predictor_workspace_bytes(net.handle, g.handle, 0)
+    return workspace("pred", device).get(nbytes, device)
 
 
 def e_gcl_forward(mod, h, edge_index, coord, edge_attr, node_mask, edge_mask):
-    _unsupported("E_GCL")
+    g, B, n = _flat_graph(h, edge_index, node_mask, edge_mask)
+    H = mod.node_mlp[2].out_features
+    ps = _dummy_linear(H, 1, h.device) + _dummy_linear(1, H, h.device) + _egcl_params(mod)
+    net = _sub_handle(mod, "pred", ps, hidden=H, attention=mod.attention, tanh=mod.tanh,
+                      coords_range=getattr(mod, "coords_range", 1.0))
+    hin, xin = _f32c(h), _f32c(coord)
+    hout, xout = torch.empty_like(hin), torch.empty_like(xin)
+    ws = _pred_ws(net, g, h.device)
+    ea = _edge_gather(edge_attr, g, 1)
+    _lib.check(_lib.lib().gb_pred_layer_forward(net.handle, g.handle, 0, _ptr(hin), _ptr(xin), _ptr(ea), _ptr(hout),
+                                                _ptr(xout), _ptr(ws), ws.numel(), _stream()))
+    return hout, xout
 
 
 def pred_egnn_forward(mod, h, x, edges, edge_attr, node_mask, edge_mask):
-    _unsupported("EGNN (predictor)")
+    g, B, n = _flat_graph(h, edges, node_mask, edge_mask)
+    ps = _param_list_predictor(mod)
+    _need_cuda(ps[0], "EGNN parameters")
+    ver = _versions(ps)
+    net = mod.__dict__.get("_gb_handle")
+    if net is None or net.versions != ver:
+        tens = [_f32c(p) for p in ps]
+        arr = (_VP * len(tens))(*[t.data_ptr() for t in tens])
+        out = _VP(0)
+        g0 = mod.gcl_0
+        _lib.check(_lib.lib().gb_predictor_create(
+            C.byref(out), mod.embedding.in_features - 1, mod.embedding_out.out_features, mod.hidden_nf, mod.n_layers,
+            int(g0.attention), int(g0.tanh), float(mod.coords_range_layer * mod.n_layers), arr, len(tens), _stream()))
+        net = NetHandle(out.value, tens, ver)
+        mod.__dict__["_gb_handle"] = net
+    hin, xin = _f32c(h), _f32c(x)
+    hout = torch.empty(hin.shape[0], mod.embedding_out.out_features, dtype=torch.float32, device=h.device)
+    xout = torch.empty_like(xin)
+    ws = _pred_ws(net, g, h.device)
+    ea = _edge_gather(edge_attr, g, 1)
+    _lib.check(_lib.lib().gb_pred_egnn_forward(net.handle, g.handle, _ptr(hin), _ptr(xin), _ptr(ea),
+                                               _ptr(hout), _ptr(xout), _ptr(ws), ws.numel(), _stream()))
+    return hout, xout

@@ -119,6 +119,32 @@ int gb_sample_loop(const gb_net* den, const gb_net* pred, const gb_graph* g, flo
                    void* stream);
 size_t gb_sample_loop_workspace_bytes(const gb_net* den, const gb_net* pred, const gb_graph* g);
 
+/* ---- hot path: sub-module forwards (inference; node tensors [n_nodes, hidden_nf], hidden_nf in {64,192,196,256}) -------
+ * Edge-level inputs are given per COMPACTED edge (the order of gb_graph's erow/ecol), i.e. the reference's dense
+ * edge_attr / coord_diff tensors gathered at the edges with edge_mask != 0.
+ * gb_den_gcl_forward     GCL.forward (edm/egnn/egnn_new.py:75-89): eattr [n_edges][2]
+ * gb_den_equiv_forward   EquivariantUpdate.forward (:142-155): cdiff [n_edges][3], eattr [n_edges][2]
+ * gb_den_block_forward   EquivariantBlock.forward (:214-235): d0_edge [n_edges] (the `edge_attr` argument)
+ * gb_den_egnn_forward    EGNN.forward (:299-321): h_in/h_out [n_nodes, in_node_nf+1]
+ * gb_pred_layer_forward  E_GCL.forward (edm/egnn_predictor/gcl.py:281-306): a_edge [n_edges]
+ * gb_pred_egnn_forward   EGNN.forward (edm/egnn_predictor/models.py:543-560): h_out [n_nodes, out_nf]
+ * workspace: gb_denoiser_workspace_bytes / gb_predictor_workspace_bytes(with_grad = 0). */
+int gb_den_gcl_forward(const gb_net* net, const gb_graph* g, int block, int sub, const float* h_in, const float* eattr,
+                       float* h_out, void* workspace, size_t workspace_bytes, void* stream);
+int gb_den_equiv_forward(const gb_net* net, const gb_graph* g, int block, const float* h_in, const float* x_in,
+                         const float* cdiff, const float* eattr, float* x_out, void* workspace, size_t workspace_bytes,
+                         void* stream);
+int gb_den_block_forward(const gb_net* net, const gb_graph* g, int block, const float* h_in, const float* x_in,
+                         const float* d0_edge, float* h_out, float* x_out, void* workspace, size_t workspace_bytes,
+                         void* stream);
+int gb_den_egnn_forward(const gb_net* net, const gb_graph* g, const float* h_in, const float* x_in, float* h_out,
+                        float* x_out, void* workspace, size_t workspace_bytes, void* stream);
+int gb_pred_layer_forward(const gb_net* net, const gb_graph* g, int layer, const float* h_in, const float* x_in,
+                          const float* a_edge, float* h_out, float* x_out, void* workspace, size_t workspace_bytes,
+                          void* stream);
+int gb_pred_egnn_forward(const gb_net* net, const gb_graph* g, const float* h_in, const float* x_in, const float* a_edge,
+                         float* h_out, float* x_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- measurement aid (bench.py roofline leg): re-launch ONE kernel `repeats` times on the workspace left by the
  * last forward / input-gradient call.  which: 0 denoiser GCL edge, 1 denoiser EquivariantUpdate edge (denoiser
  * workspace); 2 predictor edge forward, 3 predictor edge backward, 4 node-MLP Linear (predictor grad workspace). */

@@ -403,3 +403,57 @@ def make_target_opv(mean: Tensor, std: Tensor) -> Callable[[Tensor], Tensor]:
         p = pred * std + mean                                  # models_edm.py:186-188
         return p[:, 3] + p[:, 2] + 3 * p[:, 0]
     return f
+
+
+# --------------------------------------------------------------------------
+# sub-module restatements (used to test the stand-alone module forwards of the product)
+# --------------------------------------------------------------------------
+def gcl_layer(w: Weights, key: str, h: Tensor, row: Tensor, col: Tensor, edge_attr: Tensor, nm: Tensor, em: Tensor,
+              normalization_factor: float = 1.0, attention: bool = True) -> Tensor:
+    """GCL.forward (egnn_new.py:75-89) for parameters stored under ``key`` (e.g. '...gcl_0.')."""
+    m = torch.cat([h[row], h[col], edge_attr], dim=1)
+    m = F.silu(_lin(w, key + "edge_mlp.0", m))
+    m = F.silu(_lin(w, key + "edge_mlp.2", m))
+    ef = (m * torch.sigmoid(_lin(w, key + "att_mlp.0", m)) if attention else m) * em
+    agg = _segment_sum(ef, row, h.size(0)) / normalization_factor
+    upd = _lin(w, key + "node_mlp.2", F.silu(_lin(w, key + "node_mlp.0", torch.cat([h, agg], dim=1))))
+    return (h + upd) * nm
+
+
+def equiv_update_layer(w: Weights, key: str, h: Tensor, x: Tensor, row: Tensor, col: Tensor, coord_diff: Tensor,
+                       edge_attr: Tensor, nm: Tensor, em: Tensor, coords_range: float, tanh: bool = True,
+                       normalization_factor: float = 1.0) -> Tensor:
+    """EquivariantUpdate.forward (egnn_new.py:119-155)."""
+    c = torch.cat([h[row], h[col], edge_attr], dim=1)
+    c = F.silu(_lin(w, key + "coord_mlp.0", c))
+    c = F.silu(_lin(w, key + "coord_mlp.2", c))
+    phi = _lin(w, key + "coord_mlp.4", c, bias=False)
+    trans = (coord_diff * torch.tanh(phi) * coords_range if tanh else coord_diff * phi) * em
+    return (x + _segment_sum(trans, row, x.size(0)) / normalization_factor) * nm
+
+
+def equiv_block(w: Weights, key: str, h: Tensor, x: Tensor, row: Tensor, col: Tensor, d0: Tensor, nm: Tensor, em: Tensor,
+                coords_range: float, norm_constant: float = 1.0, n_sub: int = 1) -> Tuple[Tensor, Tensor]:
+    """EquivariantBlock.forward (egnn_new.py:214-235)."""
+    r, u = _radial(x, row, col, norm_constant)
+    e_attr = torch.cat([r, d0], dim=1)
+    for s in range(n_sub):
+        h = gcl_layer(w, f"{key}gcl_{s}.", h, row, col, e_attr, nm, em)
+    x = equiv_update_layer(w, key + "gcl_equiv.", h, x, row, col, u, e_attr, nm, em, coords_range)
+    return h * nm, x
+
+
+def e_gcl_layer(w: Weights, key: str, h: Tensor, x: Tensor, row: Tensor, col: Tensor, edge_attr: Tensor, nm: Tensor,
+                em: Tensor, coords_range: float) -> Tuple[Tensor, Tensor]:
+    """E_GCL.forward (gcl.py:281-306) with attention and tanh."""
+    r, u = _radial(x, row, col, 1.0)
+    e = torch.cat([h[row], h[col], r, edge_attr], dim=1)
+    e = F.silu(_lin(w, key + "edge_mlp.0", e))
+    e = F.silu(_lin(w, key + "edge_mlp.2", e))
+    ef = e * torch.sigmoid(_lin(w, key + "att_mlp.0", e)) * em
+    c = F.silu(_lin(w, key + "coord_mlp.0", ef))
+    trans = u * torch.tanh(_lin(w, key + "coord_mlp.2", c, bias=False)) * coords_range * em
+    x_new = x + _segment_sum(trans, row, x.size(0))
+    agg = _segment_sum(ef, row, h.size(0))
+    upd = _lin(w, key + "node_mlp.2", F.silu(_lin(w, key + "node_mlp.0", torch.cat([h, agg], dim=1))))
+    return (h + upd) * nm, x_new * nm
