@@ -324,7 +324,12 @@ class EnVariationalDiffusion(torch.nn.Module):
 
     def _fused_loop(self, z, node_mask, edge_mask, predictor, target_w, noise, stats):
         sched, tvals, _ = self._tables(z.device)
-        seed = self.seed if self.seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+        if self.seed is not None:      # fixed base seed (e.g. seed + rank): every loop call / batch chunk gets its own stream
+            calls = self.__dict__.get("_loop_calls", 0)
+            self.__dict__["_loop_calls"] = calls + 1
+            seed = (int(self.seed) * 0x9E3779B1 + calls) & ((1 << 62) - 1)
+        else:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         nz = None if noise is None else noise.to(torch.float32).contiguous()
         runtime.sample_loop(self.dynamics, predictor, node_mask, edge_mask, z, self.T, self.T, 0, sched, tvals,
                             target_w, nz, seed, stats, self.use_cuda_graph)
@@ -336,6 +341,11 @@ class EnVariationalDiffusion(torch.nn.Module):
         """Unconditional sampling (en_diffusion.py:958-1008).  ``noise``: optional injected [T+2,B,N,D] draws."""
         if context is not None:
             raise NotImplementedError("context conditioning is unused by GaUDI's sampling path")
+        if not fix_noise:
+            out = self._chunked(lambda n, nm, em, nz: self.sample(n, n_nodes, nm, em, None, False, std, nz),
+                                n_samples, node_mask, edge_mask, noise, None)
+            if out is not None:
+                return out
         z = self._initial_z(n_samples, n_nodes, node_mask, fix_noise, std, noise)
         stats = torch.zeros(self.T, 8, dtype=torch.float32, device=z.device)
         if fix_noise:
@@ -352,10 +362,53 @@ class EnVariationalDiffusion(torch.nn.Module):
         self._check_stats(stats)
         return self._finish(z, node_mask, edge_mask, fix_noise, last)
 
+    # ---- batch chunking: the input-gradient pass keeps 3 x hidden floats per edge and layer (25 GB per 10k cc-PBH
+    #      molecules); batches whose workspace would not fit the free HBM are sampled in sequential chunks ----
+    memory_fraction = 0.7
+
+    def _max_chunk(self, node_mask, edge_mask, predictor, guided=False) -> int:
+        B = node_mask.size(0)
+        if not node_mask.is_cuda:
+            return B
+        edges_per_mol = float(edge_mask.sum().item()) / max(B, 1)
+        n = node_mask.size(1)
+        hd = self.dynamics.hyper["hidden_nf"]
+        per_mol = 4.0 * n * (8 * hd + 64)                                   # denoiser node buffers
+        if predictor is not None or guided:
+            hyper = getattr(getattr(predictor, "module", predictor), "hyper", None) or {"hidden_nf": 256, "n_layers": 12}
+            hp, lp = hyper["hidden_nf"], hyper["n_layers"]
+            per_mol += 4.0 * (3 * lp * hp * edges_per_mol * 1.1 + n * hp * (lp + 12))
+        free, _ = torch.cuda.mem_get_info(node_mask.device)
+        reusable = sum(w.buf.numel() for w in runtime._ws.values() if w.buf is not None)
+        return max(1, int(self.memory_fraction * (free + reusable) / per_mol))
+
+    def _chunked(self, fn, n_samples, node_mask, edge_mask, noise, predictor, guided=False):
+        """Run ``fn(n, node_mask, edge_mask, noise)`` on batch slices that fit in memory and concatenate (x, h)."""
+        chunk = self._max_chunk(node_mask, edge_mask, predictor, guided)
+        if chunk >= n_samples:
+            return None
+        n = node_mask.size(1)
+        em = edge_mask.reshape(n_samples, n * n)
+        xs, cats = [], []
+        for lo in range(0, n_samples, chunk):
+            hi = min(n_samples, lo + chunk)
+            nz = None if noise is None else noise[:, lo:hi].contiguous()
+            x, h = fn(hi - lo, node_mask[lo:hi].contiguous(), em[lo:hi].reshape(-1, 1).contiguous(), nz)
+            xs.append(x); cats.append(h["categorical"])
+        x = torch.cat(xs, dim=0)
+        return x, {"integer": torch.zeros(n_samples, n, 0, dtype=torch.float32, device=x.device),
+                   "categorical": torch.cat(cats, dim=0)}
+
     @torch.no_grad()
     def sample_guidance(self, n_samples, target_function: Callable, node_mask, edge_mask, scale=1, fix_noise=False,
                         std=1.0, noise=None):
         """Guided sampling (en_diffusion.py:1010-1067)."""
+        predictor = getattr(target_function, "predictor", None)
+        if not fix_noise:
+            out = self._chunked(lambda n, nm, em, nz: self.sample_guidance(n, target_function, nm, em, scale, False, std, nz),
+                                n_samples, node_mask, edge_mask, noise, predictor, guided=True)
+            if out is not None:
+                return out
         n_nodes = node_mask.size(1)
         z = self._initial_z(n_samples, n_nodes, node_mask, fix_noise, std, noise)
         stats = torch.zeros(self.T, 8, dtype=torch.float32, device=z.device)

@@ -169,3 +169,25 @@ def test_small_batch_edge_cases():
         assert maxabs(eps, ref) <= TOL
         p = pred(z.to(dev), nm, em, t.to(dev))
         assert maxabs(p, O.predictor_forward(wp, pcfg, z, nm.cpu(), em.cpu(), t)) <= TOL
+
+
+def test_large_batches_are_chunked_to_fit_memory():
+    """memory_fraction forces tiny chunks; the chunked run must equal the un-chunked one (injected noise)."""
+    dev = _dev()
+    args, model, pred, prop = build_models("cata", dev, hidden=(64, 64), layers=(2, 2), timesteps=20)
+    nx = torch.tensor([10, 9, 11, 4, 7, 10, 11])
+    nm, em = gb.build_masks(nx, 11, False, device=dev)
+    gen = torch.Generator().manual_seed(9)
+    noise = torch.stack([O.draw_noise(7, 11, 4, nm.cpu(), generator=gen) for _ in range(model.T + 2)]).to(dev)
+    tf = gb.AffineTarget.max_gap(pred)
+    x_ref, h_ref = model.sample_guidance(7, tf, nm, em, scale=0.6, noise=noise)
+    calls = []
+    orig = model._max_chunk
+    model._max_chunk = lambda *a, **k: (calls.append(1) or 3)
+    try:
+        x, h = model.sample_guidance(7, tf, nm, em, scale=0.6, noise=noise)
+    finally:
+        model._max_chunk = orig
+    assert calls and x.shape == x_ref.shape
+    assert maxabs(x, x_ref) <= 1e-4 * max(1.0, float(x_ref.abs().max()))
+    assert torch.equal(h["categorical"], h_ref["categorical"])
