@@ -8,6 +8,10 @@
 #include "tc_common.cuh"
 #include "kernels.h"
 
+#ifndef GB_PRED_NPARTS
+#define GB_PRED_NPARTS 4
+#endif
+
 namespace gb {
 using namespace tc;
 
@@ -17,7 +21,7 @@ struct TcPredCfg {
     static constexpr int A_BYTES = 128 * ATOM_ROW_BYTES;
     static constexpr int W_BYTES = NP * ATOM_ROW_BYTES;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-    static constexpr int NPARTS = 4;                          // worker parts of 4 warps; part p owns 16-column chunks ch == p (mod 4)
+    static constexpr int NPARTS = GB_PRED_NPARTS;                          // worker parts of 4 warps; part p owns 16-column chunks ch == p (mod 4)
     static constexpr int NWORK = 128 * NPARTS;
     static constexpr int THREADS = 64 + NWORK;
     static constexpr int MAXCH = (NP + 15) / 16;
@@ -27,6 +31,14 @@ struct TcPredCfg {
     static constexpr int SMEM = S * STAGE_BYTES + 1024 + 256 + SCRATCH;
     static constexpr int D2_COL = 256;
 };
+
+template <int NPARTS>
+__device__ __forceinline__ float psum_parts(const float* red, int r) {
+    float s = 0.f;
+#pragma unroll
+    for (int p = 0; p < NPARTS; ++p) s += red[p * 128 + r];
+    return s;
+}
 
 __device__ __forceinline__ void nbar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -167,7 +179,7 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
             // ---- GEMM 1 operand: s1 = SiLU(pre1); SiLU'(pre1) is saved ----
             const float* pa_row = a.P + (size_t)rown * (2 * H);
             const float* pb_row = a.P + (size_t)coln * (2 * H) + H;
-            for (int j = part >> 1; j < na; j += 2) {
+            for (int j = part >> 1; j < na; j += CF::NPARTS / 2) {
                 float4 x[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -216,7 +228,7 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
             }
             red_s[part * 128 + r] = psum;
             nbar(1, CF::NWORK);
-            const float gate = a.attention ? sigmoid_f(red_s[r] + red_s[128 + r] + red_s[256 + r] + red_s[384 + r] + a.att_b) : 1.f;
+            const float gate = a.attention ? sigmoid_f(psum_parts<CF::NPARTS>(red_s, r) + a.att_b) : 1.f;
             // ---- gated edge feature: segment sums -> agg, and operand atoms of GEMM 2 ----
 #pragma unroll
             for (int ci = 0; ci < CF::MYCH; ++ci) {
@@ -269,10 +281,10 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
             }
             fence_before_sync();
             mbar_arrive(d_empty);
-            red_s[512 + part * 128 + r] = phi_part;
+            red_s[CF::NPARTS * 128 + part * 128 + r] = phi_part;
             nbar(1, CF::NWORK);
             if (part == 0) {
-                const float phi = red_s[512 + r] + red_s[640 + r] + red_s[768 + r] + red_s[896 + r];
+                const float phi = psum_parts<CF::NPARTS>(red_s + CF::NPARTS * 128, r);
                 const float tau = a.use_tanh ? tanhf(phi) : phi;
                 if (SAVE && valid) a.sv_tau[e_lo + r] = tau;
                 if (a.use_tanh) { tr_s[3 * r] = ux * tau * a.coords_range; tr_s[3 * r + 1] = uy * tau * a.coords_range; tr_s[3 * r + 2] = uz * tau * a.coords_range; }
@@ -388,7 +400,7 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
             }
             const uint32_t it0 = tcnt * 2 * na;
             // ---- GEMM 1 operand: g_pre3 = g_phi * w_c * SiLU'(pre3) ----
-            for (int j = part >> 1; j < na; j += 2) {
+            for (int j = part >> 1; j < na; j += CF::NPARTS / 2) {
                 float4 x[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -435,12 +447,12 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
                 }
             }
             red_s[part * 128 + r] = plog;
-            red_s[512 + part * 128 + r] = pdot;
+            red_s[CF::NPARTS * 128 + part * 128 + r] = pdot;
             nbar(1, CF::NWORK);
             float gate = 1.f, kap = 0.f;
             if (a.attention) {
-                gate = sigmoid_f(red_s[r] + red_s[128 + r] + red_s[256 + r] + red_s[384 + r] + a.att_b);
-                kap = (red_s[512 + r] + red_s[640 + r] + red_s[768 + r] + red_s[896 + r]) * gate * (1.f - gate);
+                gate = sigmoid_f(psum_parts<CF::NPARTS>(red_s, r) + a.att_b);
+                kap = (psum_parts<CF::NPARTS>(red_s + CF::NPARTS * 128, r)) * gate * (1.f - gate);
             }
             // ---- GEMM 2 operand: g_pre2 = (g_ef gate + kappa w_att) SiLU'(pre2) ----
 #pragma unroll
@@ -500,12 +512,12 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
             }
             fence_before_sync();
             mbar_arrive(d_empty);
-            red_s[1024 + part * 128 + r] = pr;
-            red_s[1536 + part * 128 + r] = pa;
+            red_s[2 * CF::NPARTS * 128 + part * 128 + r] = pr;
+            red_s[3 * CF::NPARTS * 128 + part * 128 + r] = pa;
             nbar(1, CF::NWORK);
             if (part == 0) {
-                const float g_r = red_s[1024 + r] + red_s[1152 + r] + red_s[1280 + r] + red_s[1408 + r];
-                const float g_a = red_s[1536 + r] + red_s[1664 + r] + red_s[1792 + r] + red_s[1920 + r];
+                const float g_r = psum_parts<CF::NPARTS>(red_s + 2 * CF::NPARTS * 128, r);
+                const float g_a = psum_parts<CF::NPARTS>(red_s + 3 * CF::NPARTS * 128, r);
                 float gdx = 0.f, gdy = 0.f, gdz = 0.f;
                 if (valid) {
                     a.g_attr[e_lo + r] += g_a;
