@@ -80,7 +80,7 @@ struct DenEdgeArgs {
     const float* b2;           // [HP]
     const float* vecw;         // att_mlp weight (mode 0) / last coord Linear (mode 1), [HP]
     float att_b; int attention; int use_tanh;
-    float norm_constant, inv_normf_unused, normf, coords_range;
+    float norm_constant, normf, coords_range;
     const float* x;            // current coords [n_nodes,3]
     const float* x0;           // coords at network input (second edge attribute)
     const float* eattr;        // optional explicit [n_edges][2] edge attributes (module-level API); else null

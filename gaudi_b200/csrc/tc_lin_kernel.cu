@@ -1,11 +1,11 @@
 // Tensor-core (tcgen05, 3xTF32) version of the node-level fused Linear kernel -- same contract as lin_kernel.cu.
 //
-// Warp roles (one persistent CTA per SM, 320 threads):
+// Warp roles (one persistent CTA per SM, 576 threads):
 //   warp 0      TMA producer: streams the pre-swizzled hi/lo weight K-atoms (one 1-D bulk copy per atom)
 //   warp 1      MMA issuer: 3 tcgen05.mma (lo*hi, hi*lo, hi*hi) per 8-wide K step, accumulator [128 x NP] fp32 in TMEM
-//   warps 2-9   workers, thread = tile row (two halves of 4 warps, each half covers all 128 TMEM lanes):
-//               build the A K-atoms (global row -> hi/lo split -> 128B-swizzled smem), then run the epilogue on
-//               alternating 16-column chunks read back with tcgen05.ld.
+//   warps 2-17  workers, thread = tile row (four parts of 4 warps, each part covers all 128 TMEM lanes; part p owns the
+//               16-column chunks ch == p mod 4): build the A K-atoms (global row -> hi/lo split -> 128B-swizzled smem),
+//               then run the epilogue on their chunks read back with tcgen05.ld.
 #include "tc_common.cuh"
 #include "kernels.h"
 

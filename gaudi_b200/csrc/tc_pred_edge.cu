@@ -1,9 +1,9 @@
 // Tensor-core (tcgen05, 3xTF32) versions of the predictor E_GCL edge kernels -- same contract and same saved-activation
 // layouts as pred_edge.cu (forward: gcl.py:225-279; backward: the hand-written reverse pass replacing autograd).
 //
-// thread = edge row; 8 worker warps in two halves, half h owns the 16-column chunks ch == h (mod 2) both when building
-// A K-atoms (chunk ch = 16-byte chunks 4h..4h+3 of atom ch/2) and in the epilogues, so every atom is built by all 256
-// workers.  Two accumulators live in TMEM (columns [0,NP) and [256,256+NP)): the epilogue of GEMM 1 produces the A
+// thread = edge row; 16 worker warps in four parts, part p owns the 16-column chunks ch == p (mod 4) both when building
+// A K-atoms (chunk ch = 16-byte chunks 4(ch&1)..+3 of atom ch/2) and in the epilogues, so every atom is built by two
+// parts (256 threads).  Two accumulators live in TMEM (columns [0,NP) and [256,256+NP)): the epilogue of GEMM 1 produces the A
 // atoms of GEMM 2 on the fly, chunk by chunk, while the MMA warp consumes them.
 #include "tc_common.cuh"
 #include "kernels.h"

@@ -191,3 +191,30 @@ def test_large_batches_are_chunked_to_fit_memory():
     assert calls and x.shape == x_ref.shape
     assert maxabs(x, x_ref) <= 1e-4 * max(1.0, float(x_ref.abs().max()))
     assert torch.equal(h["categorical"], h_ref["categorical"])
+
+
+def test_less_travelled_paths_fix_noise_hetro_unconditional_and_per_molecule_time():
+    dev = _dev()
+    # hetro unconditional sampling through sample_pos_edm (pads to args.max_nodes, orientation nodes)
+    args, model, pred, prop = build_models("hetro", dev, hidden=(64, 64), layers=(2, 2), timesteps=12)
+    nx = torch.tensor([10, 3, 7])
+    x, oh, nm, em = gb.sample_pos_edm(args, model, nx)
+    assert x.shape == (3, 20, 3) and oh.shape == (3, 20, 12)
+    assert float((x * (1 - nm)).abs().max()) == 0.0 and float(x.sum(1).abs().max()) < 1e-3 * max(1.0, float(x.abs().max()))
+    assert torch.all((oh.sum(-1) == nm.squeeze(-1)))                      # exactly one class per real node
+    # fix_noise=True: one noise sample broadcast over the batch (python-loop path of sample / sample_guidance)
+    nm2, em2 = gb.build_masks(torch.tensor([5, 5]), 5, True, device=dev)
+    torch.manual_seed(3)
+    xf, hf = model.sample(2, 10, nm2, em2, fix_noise=True)
+    assert maxabs(xf[0], xf[1]) <= 1e-4 * max(1.0, float(xf.abs().max()))  # identical molecules from identical noise
+    tf = gb.AffineTarget.opv(pred, prop)
+    xg, hg = model.sample_guidance(2, tf, nm2, em2, scale=0.5, fix_noise=True)
+    assert torch.isfinite(xg).all()
+    # per-molecule time values (t.numel() == B branch of EGNN_dynamics._forward / EGNN_predictor.forward)
+    wd, wp = cpu_weights(model, pred)
+    dcfg, pcfg = oracle_cfgs("hetro", hidden=(64, 64), layers=(2, 2))
+    gen = torch.Generator().manual_seed(4)
+    z = O.draw_noise(3, 20, 15, nm.cpu(), generator=gen)
+    t = torch.tensor([[0.1], [0.5], [0.9]])
+    assert maxabs(model.phi(z.to(dev), t.to(dev), nm, em, None), O.denoiser_forward(wd, dcfg, z, t, nm.cpu(), em.cpu())) <= TOL
+    assert maxabs(pred(z.to(dev), nm, em, t.to(dev)), O.predictor_forward(wp, pcfg, z, nm.cpu(), em.cpu(), t)) <= TOL
