@@ -30,7 +30,7 @@ SIGNATURES = {
     "gb_net_destroy": (_I, [_P]),
     "gb_net_hidden_padded": (_I, [_P]),
     "gb_tile_pack": (_I, [_P, _I, _P, C.POINTER(_I)]),
-    "gb_graph_create": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gb_graph_create": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gb_graph_destroy": (_I, [_P]),
     "gb_denoiser_workspace_bytes": (_SZ, [_P, _P]),
     "gb_predictor_workspace_bytes": (_SZ, [_P, _P, _I]),

@@ -320,11 +320,11 @@ extern "C" int gb_tile_pack(const int32_t* rowptr, int n_nodes, int32_t* tile_pt
 extern "C" int gb_graph_create(gb_graph** out, int B, int N, int n_edges, int n_tiles, int n_tc, const int32_t* rowptr,
                                const int32_t* erow, const int32_t* ecol, const int32_t* tile_ptr, const int32_t* tc_ptr,
                                const int32_t* tc_node, const int32_t* tc_start, const int32_t* cperm,
-                               const float* node_mask) {
+                               const int32_t* colptr, const int32_t* cedge, const float* node_mask) {
     (void)n_tc;
     if (!out) return fail("null argument");
     gb_graph* g = new gb_graph();
-    g->g = Graph{B * N, n_edges, n_tiles, B, N, rowptr, erow, ecol, tile_ptr, tc_ptr, tc_node, tc_start, cperm, node_mask};
+    g->g = Graph{B * N, n_edges, n_tiles, B, N, rowptr, erow, ecol, tile_ptr, tc_ptr, tc_node, tc_start, cperm, colptr, cedge, node_mask};
     *out = g;
     return 0;
 }
@@ -360,7 +360,7 @@ struct PredWs {
     float* pre4;     // [L][nn][HP]
     float *sv_d1, *sv_pre2, *sv_d3, *sv_tau;   // per layer strides below
     size_t sv_stride, tau_stride;
-    float *gh, *gh2, *gcat, *gpre4, *gPa, *gPb, *gx, *gx2, *gattr;
+    float *gh, *gh2, *gcat, *gpre4, *gPa, *gPb, *gx, *gx2, *gattr, *gpre1, *gd;
 };
 void carve_pred(Bump& b, const gb_net* n, const Graph& g, bool grad, PredWs& w) {
     const size_t nn = g.n_nodes, HP = n->HP, L = n->L;
@@ -376,9 +376,11 @@ void carve_pred(Bump& b, const gb_net* n, const Graph& g, bool grad, PredWs& w) 
         w.gh = b.get<float>(nn * HP); w.gh2 = b.get<float>(nn * HP); w.gcat = b.get<float>(nn * 2 * HP);
         w.gpre4 = b.get<float>(nn * HP); w.gPa = b.get<float>(nn * HP); w.gPb = b.get<float>(nn * HP);
         w.gx = b.get<float>(nn * 3); w.gx2 = b.get<float>(nn * 3); w.gattr = b.get<float>(g.n_edges + 1);
+        w.gpre1 = n->tc_pred ? b.get<float>((size_t)g.n_edges * HP + 4) : nullptr;
+        w.gd = n->tc_pred ? b.get<float>((size_t)g.n_edges * 3 + 4) : nullptr;
     } else {
         w.pre4 = w.sv_d1 = w.sv_pre2 = w.sv_d3 = w.sv_tau = nullptr;
-        w.gh = w.gh2 = w.gcat = w.gpre4 = w.gPa = w.gPb = w.gx = w.gx2 = w.gattr = nullptr;
+        w.gh = w.gh2 = w.gcat = w.gpre4 = w.gPa = w.gPb = w.gx = w.gx2 = w.gattr = w.gpre1 = w.gd = nullptr;
     }
 }
 }  // namespace
@@ -553,7 +555,7 @@ static int predictor_grad_impl(const gb_net* n, const Graph& g, const float* g_p
     HeadBwdArgs hb{gp, n->p(n->out_w), n->out_nf, n->H, HP, g.node_mask, g.B, g.N, w.gh};
     launch_head_bwd(hb, s); GB_LAUNCHED(1);
     float *gh = w.gh, *gh2 = w.gh2, *gx = w.gx, *gx2 = w.gx2;
-    cudaMemsetAsync(gx, 0, nn * 3 * sizeof(float), s);
+    cudaMemsetAsync(gx, 0, nn * 3 * sizeof(float), s);      // dL/dx_L = 0: the head only reads h
     cudaMemsetAsync(w.gattr, 0, (size_t)g.n_edges * sizeof(float), s);
     for (int l = n->L - 1; l >= 0; --l) {
         const PredLayer& Lr = n->pl[l];
@@ -567,13 +569,19 @@ static int predictor_grad_impl(const gb_net* n, const Graph& g, const float* g_p
         c.A1 = w.gpre4; c.lda1 = HP; c.K1 = HP; c.wt = n->p(Lr.n.l1_nt); c.wt_tc = n->p(Lr.n.l1_nt_tc); c.ncb = 2; c.out = w.gcat; c.ldo = 2 * HP;
         c.epi = EPI_ADD_RES; c.res = gh; c.ldr = HP; c.mask = g.node_mask; c.res_cb = 0;
         run_lin(n, c, s);
-        cudaMemsetAsync(w.gPb, 0, nn * HP * sizeof(float), s);
-        cudaMemsetAsync(gx2, 0, nn * 3 * sizeof(float), s);
         PredEdgeArgs e = pred_edge_args(n, Lr, g, w, l, true);
         e.w2_nt = n->p(Lr.e.l2_nt); e.wc_nt = n->p(Lr.c_nt);
         e.g_agg = w.gcat + HP; e.ld_gagg = 2 * HP; e.g_xout = gx; e.g_Pa = w.gPa; e.g_Pb = w.gPb; e.g_x = gx2; e.g_attr = w.gattr;
-        if (n->tc_pred) launch_pred_edge_bwd_tc(HP, e, n->p(Lr.c_nt_tc), n->p(Lr.e.l2_nt_tc), s);
-        else launch_pred_edge_bwd(HP, e, s);
+        e.g_pre1 = w.gpre1; e.g_d = w.gd;
+        if (n->tc_pred) {                   // tile kernel writes dL/dpre1 and dL/dd per edge; node-parallel kernel reduces them
+            launch_pred_edge_bwd_tc(HP, e, n->p(Lr.c_nt_tc), n->p(Lr.e.l2_nt_tc), s);
+            launch_pred_bwd_reduce(HP, e, s);
+            GB_LAUNCHED(1);
+        } else {
+            cudaMemsetAsync(w.gPb, 0, nn * HP * sizeof(float), s);
+            cudaMemsetAsync(gx2, 0, nn * 3 * sizeof(float), s);
+            launch_pred_edge_bwd(HP, e, s);
+        }
         // gh_l = gcat[:, :HP] + gPa W1a + gPb W1b
         LinArgs d = lin_base(g.n_nodes);
         d.A1 = w.gPa; d.lda1 = HP; d.K1 = HP; d.A2 = w.gPb; d.lda2 = HP; d.K2 = HP; d.wt = n->p(Lr.e.l1_nt); d.wt_tc = n->p(Lr.e.l1_nt_tc);
@@ -584,7 +592,7 @@ static int predictor_grad_impl(const gb_net* n, const Graph& g, const float* g_p
         tmp = gx; gx = gx2; gx2 = tmp;
     }
     InBwdArgs ib{g, gh, HP, n->H, n->p(n->emb_w), n->F, gx, w.gattr, w.x, 3 + n->F, g_z};
-    launch_in_bwd(ib, s); GB_LAUNCHED(2);
+    launch_in_bwd(ib, s); GB_LAUNCHED(1);
     return check_launch("predictor_input_grad");
 }
 
@@ -922,6 +930,7 @@ extern "C" int gb_profile_kernel(const gb_net* n, const gb_graph* gg, int which,
             PredEdgeArgs e = pred_edge_args(n, Lr, g, w, layer, true);
             e.w2_nt = n->p(Lr.e.l2_nt); e.wc_nt = n->p(Lr.c_nt);
             e.g_agg = w.gcat + n->HP; e.ld_gagg = 2 * n->HP; e.g_xout = w.gx; e.g_Pa = w.gPa; e.g_Pb = w.gPb; e.g_x = w.gx2; e.g_attr = w.gattr;
+            e.g_pre1 = w.gpre1; e.g_d = w.gd;
             if (n->tc_pred) launch_pred_edge_bwd_tc(n->HP, e, n->p(Lr.c_nt_tc), n->p(Lr.e.l2_nt_tc), s);
             else launch_pred_edge_bwd(n->HP, e, s);
         } else {

@@ -25,6 +25,8 @@ struct Graph {
     const int* tc_node;   // [n_tc] distinct column nodes per tile
     const int* tc_start;  // [n_tc+1] start in cperm (absolute edge slot), sentinel = n_edges
     const int* cperm;     // [n_edges] tile-local row index, grouped by column node
+    const int* colptr;    // [n_nodes+1] CSC pointer
+    const int* cedge;     // [n_edges] edge ids grouped by column node
     const float* node_mask;  // [n_nodes]
 };
 
@@ -115,11 +117,15 @@ struct PredEdgeArgs {
     float* g_Pb;               // [n_nodes, HP]  (zero-initialised, RED column scatter)
     float* g_x;                // [n_nodes, 3]   (zero-initialised, atomics)
     float* g_attr;             // [n_edges] running dL/d edge_attr (+=)
+    float* g_pre1;             // tensor-core path: [n_edges, H] dL/d pre1 handed to the node-parallel reduction kernel
+    float* g_d;                // tensor-core path: [n_edges, 3] dL/d (x_row - x_col)
 };
 void launch_pred_edge_fwd(int HP, bool save, const PredEdgeArgs& a, cudaStream_t s);
 void launch_pred_edge_bwd(int HP, const PredEdgeArgs& a, cudaStream_t s);
 void launch_pred_edge_fwd_tc(int H, bool save, const PredEdgeArgs& a, const float* w2img, const float* wcimg, cudaStream_t s);
 void launch_pred_edge_bwd_tc(int H, const PredEdgeArgs& a, const float* wcimg_nt, const float* w2img_nt, cudaStream_t s);
+// node-parallel, deterministic reductions of the backward: g_Pa (row sums), g_Pb (column sums), g_x
+void launch_pred_bwd_reduce(int H, const PredEdgeArgs& a, cudaStream_t s);
 
 size_t tile_kernel_smem_bytes(int HP);
 

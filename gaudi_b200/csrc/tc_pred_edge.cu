@@ -392,12 +392,6 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
                 else { gphi = gdotu; gux = gx * tau; guy = gy * tau; guz = gz * tau; }
             }
             if (part == 0) for (int i = r; i <= nn; i += 128) seg_s[i] = g.rowptr[node_lo + i] - e_lo;
-            const int t0 = g.tc_ptr[tile], t1 = g.tc_ptr[tile + 1], ntc = t1 - t0;
-            if (part == 1) {
-                if (r < ne) cperm_s[r] = g.cperm[e_lo + r];
-                for (int i = r; i <= ntc; i += 128) tcs_s[i] = g.tc_start[t0 + i] - e_lo;
-                for (int i = r; i < ntc; i += 128) tcn_s[i] = g.tc_node[t0 + i];
-            }
             const uint32_t it0 = tcnt * 2 * na;
             // ---- GEMM 1 operand: g_pre3 = g_phi * w_c * SiLU'(pre3) ----
             for (int j = part >> 1; j < na; j += CF::NPARTS / 2) {
@@ -476,10 +470,13 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
                     put_chunk<NP>(p, it0 + na + (ch >> 1), r, half, x);
                 }
             }
-            // ---- epilogue 2: g_pre1 = g_s1 * SiLU'(pre1); row / column sums; geometry gradients ----
+            // ---- epilogue 2: g_pre1 = g_s1 * SiLU'(pre1) -> HBM (row-major per edge); radial / attr dots ----
+            //      the row sums (g_Pa), column sums (g_Pb) and the coordinate gradient are reduced afterwards by the
+            //      node-parallel pred_bwd_reduce_kernel: fixed summation order, no atomics, no per-chunk barriers here
             mbar_wait(d2_full, tcnt & 1);
             fence_after_sync();
             float pr = 0.f, pa = 0.f;
+            float* gp_row = a.g_pre1 + (size_t)(e_lo + r) * H;
 #pragma unroll 1
             for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
                 float v[16];
@@ -487,58 +484,34 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
                     const int c0 = ch * 16 + 4 * c4;
-                    float4 d1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (c0 < H) d1 = __ldg(reinterpret_cast<const float4*>(a.sv_d1 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4));
-                    const float gp[4] = {v[4 * c4] * d1.x, v[4 * c4 + 1] * d1.y, v[4 * c4 + 2] * d1.z, v[4 * c4 + 3] * d1.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        my_ef[r * CF::EF_STRIDE + 4 * c4 + e] = valid ? gp[e] : 0.f;
-                        if (c0 < H) { pr = fmaf(vec_s[c0 + e], gp[e], pr); pa = fmaf(vec_s[NP + c0 + e], gp[e], pa); }
+                    if (c0 < H) {
+                        const float4 d1 = __ldg(reinterpret_cast<const float4*>(a.sv_d1 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4));
+                        const float4 gp = make_float4(v[4 * c4] * d1.x, v[4 * c4 + 1] * d1.y, v[4 * c4 + 2] * d1.z, v[4 * c4 + 3] * d1.w);
+                        const float4 wr = *reinterpret_cast<const float4*>(vec_s + c0);
+                        const float4 wa = *reinterpret_cast<const float4*>(vec_s + NP + c0);
+                        pr += wr.x * gp.x + wr.y * gp.y + wr.z * gp.z + wr.w * gp.w;
+                        pa += wa.x * gp.x + wa.y * gp.y + wa.z * gp.z + wa.w * gp.w;
+                        if (valid) *reinterpret_cast<float4*>(gp_row + c0) = gp;
                     }
                 }
-                nbar(2 + part, 128);
-                const int col = r & 15, c = ch * 16 + col;
-                for (int nl = r >> 4; nl < nn; nl += 8) {
-                    float sum = 0.f;
-                    for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += my_ef[mm * CF::EF_STRIDE + col];
-                    if (c < H) a.g_Pa[(size_t)(node_lo + nl) * H + c] = sum;
-                }
-                for (int ti = r >> 4; ti < ntc; ti += 8) {
-                    float sum = 0.f;
-                    for (int q = tcs_s[ti]; q < tcs_s[ti + 1]; ++q) sum += my_ef[cperm_s[q] * CF::EF_STRIDE + col];
-                    if (c < H) atomicAdd(a.g_Pb + (size_t)tcn_s[ti] * H + c, sum);
-                }
-                nbar(2 + part, 128);
             }
             fence_before_sync();
             mbar_arrive(d_empty);
             red_s[2 * CF::NPARTS * 128 + part * 128 + r] = pr;
             red_s[3 * CF::NPARTS * 128 + part * 128 + r] = pa;
             nbar(1, CF::NWORK);
-            if (part == 0) {
+            if (part == 0 && valid) {
                 const float g_r = psum_parts<CF::NPARTS>(red_s + 2 * CF::NPARTS * 128, r);
                 const float g_a = psum_parts<CF::NPARTS>(red_s + 3 * CF::NPARTS * 128, r);
-                float gdx = 0.f, gdy = 0.f, gdz = 0.f;
-                if (valid) {
-                    a.g_attr[e_lo + r] += g_a;
-                    const float inv = 1.f / (nrm + 1.f);
-                    const float k2 = (gux * dx + guy * dy + guz * dz) * inv * inv / nrm;
-                    gdx = 2.f * g_r * dx + gux * inv - k2 * dx;
-                    gdy = 2.f * g_r * dy + guy * inv - k2 * dy;
-                    gdz = 2.f * g_r * dz + guz * inv - k2 * dz;
-                    atomicAdd(a.g_x + 3 * coln, -gdx); atomicAdd(a.g_x + 3 * coln + 1, -gdy); atomicAdd(a.g_x + 3 * coln + 2, -gdz);
-                }
-                gd_s[3 * r] = gdx; gd_s[3 * r + 1] = gdy; gd_s[3 * r + 2] = gdz;
+                a.g_attr[e_lo + r] += g_a;
+                const float inv = 1.f / (nrm + 1.f);
+                const float k2 = (gux * dx + guy * dy + guz * dz) * inv * inv / nrm;
+                float* gd = a.g_d + (size_t)(e_lo + r) * 3;
+                gd[0] = 2.f * g_r * dx + gux * inv - k2 * dx;
+                gd[1] = 2.f * g_r * dy + guy * inv - k2 * dy;
+                gd[2] = 2.f * g_r * dz + guz * inv - k2 * dz;
             }
-            nbar(1, CF::NWORK);
-            for (int idx = part * 128 + r; idx < nn * 3; idx += CF::NWORK) {
-                const int nl = idx / 3, d = idx - 3 * nl;
-                const int node = node_lo + nl;
-                float sum = a.g_xout[3 * node + d] * g.node_mask[node];
-                for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += gd_s[3 * mm + d];
-                atomicAdd(a.g_x + 3 * node + d, sum);
-            }
-            nbar(1, CF::NWORK);
+            nbar(1, CF::NWORK);                                  // red_s / seg_s free for the next tile
         }
     }
     fence_before_sync();
@@ -569,6 +542,45 @@ void launch_pred_edge_bwd_tc(int H, const PredEdgeArgs& a, const float* wcimg_nt
         case 208: launch_bwd_t<208>(a, wcimg_nt, w2img_nt, H, s); break;
         default: launch_bwd_t<256>(a, wcimg_nt, w2img_nt, H, s); break;
     }
+}
+
+// Node-parallel reductions of the backward (one warp per node, lanes along the feature dimension):
+//   g_Pa[i] = sum over the row segment of i,  g_Pb[i] = sum over the edges whose column is i (CSC order),
+//   g_x[i]  = g_xout[i]*mask_i + sum_row g_d - sum_col g_d.          Fixed order -> bit-reproducible.
+__global__ void pred_bwd_reduce_kernel(PredEdgeArgs a, int H) {
+    const Graph& g = a.g;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int nq = H >> 2;                                       // float4 columns
+    for (int node = warp; node < g.n_nodes; node += nwarps) {
+        const int r0 = g.rowptr[node], r1 = g.rowptr[node + 1];
+        const int c0 = g.colptr[node], c1 = g.colptr[node + 1];
+        for (int q = lane; q < nq; q += 32) {
+            float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+            for (int e = r0; e < r1; ++e) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(a.g_pre1 + (size_t)e * H) + q);
+                sa.x += v.x; sa.y += v.y; sa.z += v.z; sa.w += v.w;
+            }
+            for (int p = c0; p < c1; ++p) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(a.g_pre1 + (size_t)__ldg(g.cedge + p) * H) + q);
+                sb.x += v.x; sb.y += v.y; sb.z += v.z; sb.w += v.w;
+            }
+            reinterpret_cast<float4*>(a.g_Pa + (size_t)node * H)[q] = sa;
+            reinterpret_cast<float4*>(a.g_Pb + (size_t)node * H)[q] = sb;
+        }
+        if (lane < 3) {
+            float sum = a.g_xout[3 * node + lane] * g.node_mask[node];
+            for (int e = r0; e < r1; ++e) sum += a.g_d[(size_t)e * 3 + lane];
+            for (int p = c0; p < c1; ++p) sum -= a.g_d[(size_t)g.cedge[p] * 3 + lane];
+            a.g_x[3 * node + lane] = sum;
+        }
+    }
+}
+
+void launch_pred_bwd_reduce(int H, const PredEdgeArgs& a, cudaStream_t s) {
+    if (a.g.n_nodes <= 0) return;
+    const int blocks = min(148 * 8, (a.g.n_nodes + 7) / 8);
+    pred_bwd_reduce_kernel<<<blocks, 256, 0, s>>>(a, H);
 }
 
 template <int NP>

@@ -66,6 +66,8 @@ class Topology:
     cperm: torch.Tensor
     node_mask: torch.Tensor     # flat fp32 [B*N]
     dense_idx: torch.Tensor = None   # int64 [n_edges]: position of every kept edge in the dense B*N*N list
+    colptr: torch.Tensor = None      # int32 [n_nodes+1] CSC pointer (edges grouped by column node)
+    cedge: torch.Tensor = None       # int32 [n_edges] edge ids in CSC order
 
 
 def tile_pack(rowptr_host: np.ndarray) -> np.ndarray:
@@ -111,6 +113,9 @@ def build_topology(node_mask: torch.Tensor, edge_mask: torch.Tensor, B: int, N: 
     tc_start[1:] = torch.cumsum(cnt, 0)
     tc_tile = torch.div(uniq, B * N, rounding_mode="floor")
     tc_ptr = torch.searchsorted(tc_tile.contiguous(), torch.arange(n_tiles + 1, device=dev), right=False)
+    cedge = torch.argsort(ecol, stable=True)
+    colptr = torch.zeros(B * N + 1, dtype=torch.int64, device=dev)
+    colptr[1:] = torch.cumsum(torch.bincount(ecol, minlength=B * N), 0)
     i32 = lambda t: t.to(torch.int32).contiguous()
     return Topology(B, N, n_edges, n_tiles, n_tc, i32(rowptr), i32(erow), i32(ecol), i32(tile_ptr), i32(tc_ptr),
-                    i32(tc_node), i32(tc_start), i32(cperm), nm, flat)
+                    i32(tc_node), i32(tc_start), i32(cperm), nm, flat, i32(colptr), i32(cedge))

@@ -132,7 +132,7 @@ class GraphHandle:
         _lib.check(_lib.lib().gb_graph_create(
             C.byref(out), topo.B, topo.N, topo.n_edges, topo.n_tiles, topo.n_tc, _ptr(topo.rowptr), _ptr(topo.erow),
             _ptr(topo.ecol), _ptr(topo.tile_ptr), _ptr(topo.tc_ptr), _ptr(topo.tc_node), _ptr(topo.tc_start),
-            _ptr(topo.cperm), _ptr(topo.node_mask)))
+            _ptr(topo.cperm), _ptr(topo.colptr), _ptr(topo.cedge), _ptr(topo.node_mask)))
         self.handle = out
 
     def __del__(self):

@@ -53,11 +53,13 @@ int gb_net_hidden_padded(const gb_net* net);
  * h[row]/h[col] index tensors).  All arrays are DEVICE int32, borrowed for the lifetime of the handle.
  *   rowptr[n_nodes+1], erow/ecol[n_edges]: CSR of the edges with edge_mask != 0 in dense row-major order
  *   tile_ptr[n_tiles+1]: node boundaries of GEMM tiles (<=128 edges and <=128 nodes each, see gb_tile_pack)
- *   tc_ptr[n_tiles+1], tc_node[n_tc], tc_start[n_tc+1], cperm[n_edges]: each tile's edges grouped by column node */
+ *   tc_ptr[n_tiles+1], tc_node[n_tc], tc_start[n_tc+1], cperm[n_edges]: each tile's edges grouped by column node
+ *   colptr[n_nodes+1], cedge[n_edges]: CSC view (edge ids grouped by column node, ascending edge id inside a group) */
 int gb_tile_pack(const int32_t* rowptr_host, int n_nodes, int32_t* tile_ptr_host_out, int* n_tiles_out);
 int gb_graph_create(gb_graph** out, int B, int N, int n_edges, int n_tiles, int n_tc, const int32_t* rowptr,
                     const int32_t* erow, const int32_t* ecol, const int32_t* tile_ptr, const int32_t* tc_ptr,
-                    const int32_t* tc_node, const int32_t* tc_start, const int32_t* cperm, const float* node_mask);
+                    const int32_t* tc_node, const int32_t* tc_start, const int32_t* cperm, const int32_t* colptr,
+                    const int32_t* cedge, const float* node_mask);
 int gb_graph_destroy(gb_graph* g);
 
 /* ---- workspace sizes (bytes of device scratch the hot-path calls need) */

@@ -132,9 +132,10 @@ def test_graph_and_eager_loop_agree_and_philox_noise_is_valid():
         model.use_cuda_graph = use_graph
         x, h = model.sample_guidance(B, tf, nm, em, scale=0.6, noise=noise)
         outs.append((x.clone(), h["categorical"].clone()))
-    # same kernels, same inputs: only the order of a few float atomics in the backward scatter may differ
-    assert maxabs(outs[0][0], outs[1][0]) <= 1e-4 * max(1.0, float(outs[0][0].abs().max()))
-    assert torch.equal(outs[0][1], outs[1][1])
+    # same kernels, same inputs, fixed reduction orders everywhere (no float atomics on the tensor-core path): bit-identical
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    x_again, _ = model.sample_guidance(B, tf, nm, em, scale=0.6, noise=noise)
+    assert torch.equal(outs[1][0], x_again), "guided sampling must be reproducible run to run" 
     # generic (autograd) path == fused loop
     model.use_cuda_graph = False
     x2, h2 = model.sample_guidance(B, lambda z, a, b, t: -pred(z, a, b, t)[:, 1], nm, em, scale=0.6, noise=noise)
