@@ -9,24 +9,30 @@
 #include "tc_common.cuh"
 #include "kernels.h"
 
+#ifndef GB_LIN_NPARTS
+#define GB_LIN_NPARTS 4     // worker parts of 4 warps
+#define GB_LIN_S 2          // operand ring stages
+#define GB_LIN_CTAS 1       // CTAs per SM
+#endif
+
 namespace gb {
 using namespace tc;
 
 template <int NP>
 struct TcLinCfg {
-    static constexpr int S = 2;
+    static constexpr int S = GB_LIN_S;
     static constexpr int A_BYTES = 128 * ATOM_ROW_BYTES;
     static constexpr int W_BYTES = NP * ATOM_ROW_BYTES;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
     static constexpr int SMEM = S * STAGE_BYTES + 1024 + 256;
     static constexpr int TMEM_COLS = 256;
-    static constexpr int NPARTS = 4;                          // worker parts of 4 warps; part p owns 16-column chunks ch == p (mod 4)
+    static constexpr int NPARTS = GB_LIN_NPARTS;                          // worker parts of 4 warps; part p owns 16-column chunks ch == p (mod 4)
     static constexpr int NWORK = 128 * NPARTS;
     static constexpr int THREADS = 64 + NWORK;
 };
 
 template <int NP>
-__global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, 1) tc_lin_kernel(LinArgs a, const float* __restrict__ wimg, int H) {
+__global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, GB_LIN_CTAS) tc_lin_kernel(LinArgs a, const float* __restrict__ wimg, int H) {
     using CF = TcLinCfg<NP>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -102,7 +108,7 @@ __global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, 1) tc_lin_kernel(LinArg
             const bool rvalid = row < a.M;
             const float rs = (rvalid && a.rowscale) ? __ldg(a.rowscale + row) : 1.f;
             // ---- build the A atoms owned by this half ----
-            for (int j = part >> 1; j < na; j += 2) {
+            for (int j = part >> 1; j < na; j += CF::NPARTS / 2) {
                 const uint32_t it = tcnt * na + j;
                 const uint32_t s = it % CF::S, rr = it / CF::S;
                 const bool first = j < na1;
@@ -182,7 +188,7 @@ static void launch_t(const LinArgs& a, const float* wimg, int H, cudaStream_t s)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_tiles = (a.M + 127) / 128;
     int gx = n_tiles;
-    const int cap = max(1, sms / a.ncb);
+    const int cap = max(1, sms * GB_LIN_CTAS / a.ncb);
     if (gx > cap) gx = cap;
     tc_lin_kernel<NP><<<dim3(gx, a.ncb), CF::THREADS, CF::SMEM, s>>>(a, wimg, H);
 }
