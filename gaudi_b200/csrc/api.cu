@@ -34,6 +34,9 @@ static int fail(const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail("%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
     } while (0)
 #define GB_LAUNCHED(n) (g_launches += (n))
+// train_ops.cu reports launch failures through the same thread-local error string and counts its launches here
+int gb_train_fail(const char* what) { return fail("%s: launch failed", what); }
+void gb_train_launched(int n) { g_launches += n; }
 static int check_launch(const char* what) {
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) { cudaGetLastError(); return fail("%s: %s", what, cudaGetErrorString(e)); }

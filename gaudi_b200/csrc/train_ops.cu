@@ -1,0 +1,461 @@
+// Training-step ops (SURVEY.md 8a row a19 / BASELINE config 5): the EDM denoising loss forward + backward with weight
+// gradients.  The batch is small there (512 molecules, 56k edges), so this path is UNFUSED: every op of an
+// EquivariantBlock (egnn_new.py:42-155) is one hand-written kernel with an explicit backward, activations live in HBM and
+// torch.autograd only chains the ops (gaudi_b200/training.py).  No cuBLAS: the three GEMM flavours (forward y = x W^T,
+// dgrad gx = gy W, wgrad gW = gy^T x) are one shared-memory tiled FP32 kernel.
+#include "../../include/gaudi_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+#include <float.h>
+
+namespace gb {
+
+// ------------------------------------------------------------------------------------------------------------------
+// GEMM: C[M,N] (+)= op(A) op(B) (+ bias[N])
+//   mode 0 (NT): A[M,K] row-major, B[N,K] row-major      C = A B^T      (Linear forward)
+//   mode 1 (NN): A[M,K],           B[K,N]                C = A B        (dgrad)
+//   mode 2 (TN): A[K,M],           B[K,N]                C = A^T B      (wgrad; K = rows of the batch, split over gridDim.z)
+// 64x64 tile, BK = 16, 256 threads x (4x4) outputs.
+// ------------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                   const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                                                   const float* __restrict__ bias, int accumulate, int k_per_split) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64 + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int k_lo = blockIdx.z * k_per_split, k_hi = min(K, k_lo + k_per_split);
+    float acc[4][4] = {};
+    for (int k0 = k_lo; k0 < k_hi; k0 += 16) {
+        // ---- stage A tile as As[k][m] and B tile as Bs[k][n] ----
+        for (int i = tid; i < 16 * 64; i += 256) {
+            int kk, mm;
+            float v = 0.f;
+            if (MODE == 2) { mm = i & 63; kk = i >> 6; if (k0 + kk < k_hi && m0 + mm < M) v = A[(size_t)(k0 + kk) * lda + m0 + mm]; }
+            else { kk = i & 15; mm = i >> 4; if (k0 + kk < k_hi && m0 + mm < M) v = A[(size_t)(m0 + mm) * lda + k0 + kk]; }
+            As[kk][mm] = v;
+        }
+        for (int i = tid; i < 16 * 64; i += 256) {
+            int kk, nn;
+            float v = 0.f;
+            if (MODE == 0) { kk = i & 15; nn = i >> 4; if (k0 + kk < k_hi && n0 + nn < N) v = B[(size_t)(n0 + nn) * ldb + k0 + kk]; }
+            else { nn = i & 63; kk = i >> 6; if (k0 + kk < k_hi && n0 + nn < N) v = B[(size_t)(k0 + kk) * ldb + n0 + nn]; }
+            Bs[kk][nn] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[kk][4 * ty]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][4 * tx]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + 4 * ty + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + 4 * tx + j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (bias && blockIdx.z == 0) v += bias[n];
+            float* c = C + (size_t)m * ldc + n;
+            if (gridDim.z > 1) atomicAdd(c, v);          // split-K partials (C pre-zeroed by the launcher unless accumulating)
+            else *c = accumulate ? *c + v : v;
+        }
+    }
+}
+
+// out[k] (+)= sum_m w[m] * X[m][k]   (w == null: plain column sum).  One block per 32 columns, rows strided over the block.
+__global__ void colsum_kernel(const float* __restrict__ X, int ld, int M, int N, const float* __restrict__ w,
+                              float* __restrict__ out, int accumulate) {
+    __shared__ float red[8][33];
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
+    float s = 0.f;
+    if (col < N)
+        for (int m = slice + 8 * blockIdx.y; m < M; m += 8 * gridDim.y) s += (w ? w[m] : 1.f) * X[(size_t)m * ld + col];
+    red[slice][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (slice == 0 && col < N) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
+        if (gridDim.y > 1) atomicAdd(out + col, t);
+        else out[col] = accumulate ? out[col] + t : t;
+    }
+}
+
+// out[m] = bias + sum_k X[m][k] v[k]     (one warp per row)
+__global__ void rowdot_kernel(const float* __restrict__ X, int ld, int M, int N, const float* __restrict__ v, float bias,
+                              float* __restrict__ out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    for (int m = warp; m < M; m += nw) {
+        float s = 0.f;
+        for (int k = lane; k < N; k += 32) s = fmaf(X[(size_t)m * ld + k], v[k], s);
+#pragma unroll
+        for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) out[m] = s + bias;
+    }
+}
+
+__global__ void silu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = silu_f(x[i]);
+}
+// gx = gy * SiLU'(x) * (scale_row ? scale_row[row] * v[col] : 1): also serves the "outer product times SiLU'" of the heads
+__global__ void silu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) gx[i] = gy[i] * dsilu_f(x[i]);
+}
+// G[e][k] = s[e] * v[k] * SiLU'(pre[e][k])   (backward of  phi = v . SiLU(pre))
+__global__ void outer_dsilu_kernel(const float* __restrict__ s, const float* __restrict__ v, const float* __restrict__ pre,
+                                   float* __restrict__ G, int M, int N) {
+    const size_t n = (size_t)M * N;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int e = (int)(i / N), k = (int)(i % N);
+        G[i] = s[e] * v[k] * dsilu_f(pre[i]);
+    }
+}
+
+// pre[e][k] = Pa[row_e][k] + Pb[col_e][k] + wr[k] r_e + wd[k] d0_e      (GCL.edge_model / coord_model input, factorised)
+__global__ void edge_pre_kernel(Graph g, const float* __restrict__ Pa, const float* __restrict__ Pb, const float* __restrict__ r,
+                                const float* __restrict__ d0, const float* __restrict__ wr, const float* __restrict__ wd,
+                                int H, float* __restrict__ pre) {
+    const size_t n = (size_t)g.n_edges * H;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int e = (int)(i / H), k = (int)(i % H);
+        pre[i] = Pa[(size_t)g.erow[e] * H + k] + Pb[(size_t)g.ecol[e] * H + k] + wr[k] * r[e] + wd[k] * d0[e];
+    }
+}
+
+// row[i] = sum over the row segment of node i of G[e];  col[j] = sum over the edges whose column is j (CSC order)
+__global__ void rowcol_reduce_kernel(Graph g, const float* __restrict__ G, int H, float scale, float* __restrict__ out_row,
+                                     float* __restrict__ out_col) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    for (int node = warp; node < g.n_nodes; node += nw) {
+        for (int k = lane; k < H; k += 32) {
+            if (out_row) {
+                float s = 0.f;
+                for (int e = g.rowptr[node]; e < g.rowptr[node + 1]; ++e) s += G[(size_t)e * H + k];
+                out_row[(size_t)node * H + k] = s * scale;
+            }
+            if (out_col) {
+                float s = 0.f;
+                for (int p = g.colptr[node]; p < g.colptr[node + 1]; ++p) s += G[(size_t)g.cedge[p] * H + k];
+                out_col[(size_t)node * H + k] = s * scale;
+            }
+        }
+    }
+}
+
+// out[e][k] = X[row_e][k]      (backward of the row segment sum)
+__global__ void gather_rows_kernel(Graph g, const float* __restrict__ X, int H, float scale, float* __restrict__ out) {
+    const size_t n = (size_t)g.n_edges * H;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int e = (int)(i / H), k = (int)(i % H);
+        out[i] = X[(size_t)g.erow[e] * H + k] * scale;
+    }
+}
+
+// attention gate (egnn_new.py:49-56):  ef = m * sigmoid(logit)      backward: g_m = g_ef*gate + coef*wa, coef = (g_ef.m) gate (1-gate)
+__global__ void gate_fwd_kernel(const float* __restrict__ m, const float* __restrict__ logit, int E, int H, float* __restrict__ ef,
+                                float* __restrict__ gate) {
+    const size_t n = (size_t)E * H;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int e = (int)(i / H);
+        const float gt = sigmoid_f(logit[e]);
+        ef[i] = m[i] * gt;
+        if (i % H == 0) gate[e] = gt;
+    }
+}
+__global__ void gate_bwd_kernel(const float* __restrict__ m, const float* __restrict__ gate, const float* __restrict__ wa,
+                                const float* __restrict__ g_ef, int E, int H, float* __restrict__ g_m, float* __restrict__ coef) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    for (int e = warp; e < E; e += nw) {
+        float dot = 0.f;
+        for (int k = lane; k < H; k += 32) dot = fmaf(g_ef[(size_t)e * H + k], m[(size_t)e * H + k], dot);
+#pragma unroll
+        for (int off = 16; off; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+        const float gt = gate[e], c = dot * gt * (1.f - gt);
+        for (int k = lane; k < H; k += 32) g_m[(size_t)e * H + k] = g_ef[(size_t)e * H + k] * gt + c * wa[k];
+        if (lane == 0) coef[e] = c;
+    }
+}
+
+// coord2diff (egnn_new.py:394-400): r = |x_i-x_j|^2, u = (x_i-x_j)/(sqrt(r+1e-8)+c)
+__global__ void geom_fwd_kernel(Graph g, const float* __restrict__ x, float c, float* __restrict__ r, float* __restrict__ u) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < g.n_edges; e += gridDim.x * blockDim.x) {
+        const int i = g.erow[e], j = g.ecol[e];
+        const float dx = x[3 * i] - x[3 * j], dy = x[3 * i + 1] - x[3 * j + 1], dz = x[3 * i + 2] - x[3 * j + 2];
+        const float rr = dx * dx + dy * dy + dz * dz;
+        const float inv = 1.f / (sqrtf(rr + 1e-8f) + c);
+        r[e] = rr;
+        if (u) { u[3 * e] = dx * inv; u[3 * e + 1] = dy * inv; u[3 * e + 2] = dz * inv; }
+    }
+}
+// per-edge dL/d(x_i - x_j) from dL/dr and dL/du, then node-parallel: g_x[i] = sum_row g_d - sum_col g_d
+__global__ void geom_bwd_edge_kernel(Graph g, const float* __restrict__ x, float c, const float* __restrict__ g_r,
+                                     const float* __restrict__ g_u, float* __restrict__ g_d) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < g.n_edges; e += gridDim.x * blockDim.x) {
+        const int i = g.erow[e], j = g.ecol[e];
+        const float dx = x[3 * i] - x[3 * j], dy = x[3 * i + 1] - x[3 * j + 1], dz = x[3 * i + 2] - x[3 * j + 2];
+        const float nrm = sqrtf(dx * dx + dy * dy + dz * dz + 1e-8f), inv = 1.f / (nrm + c);
+        const float gr = g_r ? g_r[e] : 0.f;
+        float gx = 2.f * gr * dx, gy = 2.f * gr * dy, gz = 2.f * gr * dz;
+        if (g_u) {
+            const float ux = g_u[3 * e], uy = g_u[3 * e + 1], uz = g_u[3 * e + 2];
+            const float k2 = (ux * dx + uy * dy + uz * dz) * inv * inv / nrm;
+            gx += ux * inv - k2 * dx; gy += uy * inv - k2 * dy; gz += uz * inv - k2 * dz;
+        }
+        g_d[3 * e] = gx; g_d[3 * e + 1] = gy; g_d[3 * e + 2] = gz;
+    }
+}
+__global__ void node_diff_reduce_kernel(Graph g, const float* __restrict__ g_d, float* __restrict__ g_x) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < g.n_nodes * 3; idx += gridDim.x * blockDim.x) {
+        const int node = idx / 3, d = idx - 3 * node;
+        float s = 0.f;
+        for (int e = g.rowptr[node]; e < g.rowptr[node + 1]; ++e) s += g_d[3 * e + d];
+        for (int p = g.colptr[node]; p < g.colptr[node + 1]; ++p) s -= g_d[3 * g.cedge[p] + d];
+        g_x[idx] = s;
+    }
+}
+
+// EquivariantUpdate tail (egnn_new.py:122-155): x' = (x + sum_row u*tanh(phi)*range) * mask
+__global__ void coord_fwd_kernel(Graph g, const float* __restrict__ x, const float* __restrict__ u, const float* __restrict__ phi,
+                                 float range, int use_tanh, float normf, float* __restrict__ x_out, float* __restrict__ tau) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < g.n_edges; e += gridDim.x * blockDim.x) tau[e] = use_tanh ? tanhf(phi[e]) : phi[e];
+    // the node phase recomputes tanh instead of reading tau, so no grid-wide ordering is needed
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < g.n_nodes * 3; idx += gridDim.x * blockDim.x) {
+        const int node = idx / 3, d = idx - 3 * node;
+        float s = 0.f;
+        for (int e = g.rowptr[node]; e < g.rowptr[node + 1]; ++e)
+            s += u[3 * e + d] * (use_tanh ? tanhf(phi[e]) * range : phi[e]);
+        x_out[idx] = (x[idx] + s / normf) * g.node_mask[node];
+    }
+}
+__global__ void coord_bwd_kernel(Graph g, const float* __restrict__ u, const float* __restrict__ tau, const float* __restrict__ g_xout,
+                                 float range, int use_tanh, float normf, float* __restrict__ g_phi, float* __restrict__ g_u,
+                                 float* __restrict__ g_x) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < g.n_edges; e += gridDim.x * blockDim.x) {
+        const int i = g.erow[e];
+        const float mk = g.node_mask[i] / normf;
+        const float gx = g_xout[3 * i] * mk, gy = g_xout[3 * i + 1] * mk, gz = g_xout[3 * i + 2] * mk;
+        const float t = tau[e];
+        const float dotu = gx * u[3 * e] + gy * u[3 * e + 1] + gz * u[3 * e + 2];
+        const float sc = use_tanh ? t * range : t;
+        g_phi[e] = use_tanh ? dotu * range * (1.f - t * t) : dotu;
+        g_u[3 * e] = gx * sc; g_u[3 * e + 1] = gy * sc; g_u[3 * e + 2] = gz * sc;
+    }
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < g.n_nodes * 3; idx += gridDim.x * blockDim.x)
+        g_x[idx] = g_xout[idx] * g.node_mask[idx / 3];
+}
+
+// out = (a + b) * mask[row]   /   out = a * mask[row]
+__global__ void resmask_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mask, int M, int N,
+                               float* __restrict__ out) {
+    const size_t n = (size_t)M * N;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = ((b ? b[i] : 0.f) + a[i]) * mask[i / N];
+}
+
+// EGNN_dynamics tail backward (edm/egnn/models.py:116-152): eps = [remove_mean((x_fin - x_in) mask), h3[:, :F]]
+__global__ void den_finish_bwd_kernel(const float* __restrict__ g_eps, const float* __restrict__ mask, int B, int N, int F,
+                                      float* __restrict__ g_xfin, float* __restrict__ g_h3) {
+    const int D = 3 + F;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    float s[3] = {0.f, 0.f, 0.f}, cnt = 0.f;
+    for (int i = lane; i < N; i += 32) {
+        const float mk = mask[b * N + i];
+        cnt += mk;
+        for (int d = 0; d < 3; ++d) s[d] += mk * g_eps[((size_t)(b * N + i)) * D + d];
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        for (int d = 0; d < 3; ++d) s[d] += __shfl_xor_sync(0xffffffffu, s[d], off);
+    }
+    cnt = fmaxf(cnt, 1.f);
+    for (int i = lane; i < N; i += 32) {
+        const int node = b * N + i;
+        const float mk = mask[node];
+        for (int d = 0; d < 3; ++d) g_xfin[3 * node + d] = (g_eps[(size_t)node * D + d] - s[d] / cnt) * mk;
+        for (int k = 0; k < F; ++k) g_h3[(size_t)node * (F + 1) + k] = g_eps[(size_t)node * D + 3 + k];
+        g_h3[(size_t)node * (F + 1) + F] = 0.f;          // the time column of embedding_out is discarded (models.py:132-134)
+    }
+}
+
+// Training loss of EnVariationalDiffusion.compute_loss(t0_always=False) in train mode with loss_type 'l2'
+// (en_diffusion.py:644-775, 459-491, 568-642; include_charges = False) and its gradient w.r.t. the network output.
+//   loss_b = kl_prior_b + [t_b == 0] (0.5 err_x - log p(h | z_t)) + [t_b != 0] 0.5 err
+__global__ void train_loss_kernel(const float* __restrict__ net, const float* __restrict__ eps, const float* __restrict__ zt,
+                                  const float* __restrict__ xh, const float* __restrict__ mask, const float* __restrict__ t_int,
+                                  const float* __restrict__ gamma_t, float gamma_T, float norm_h, float bias_h, int B, int N, int F,
+                                  float* __restrict__ loss, float* __restrict__ g_net) {
+    const int D = 3 + F;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const bool t0 = t_int[b] == 0.f;
+    const float denom = (float)((3 + F) * N);
+    const float sigma0_cat = sqrtf(sigmoid_f(gamma_t[b])) * norm_h;     // uses gamma_t of the sample (selected by t == 0)
+    const float alpha_T = sqrtf(1.f / (1.f + expf(gamma_T))), sigma_T = sqrtf(1.f / (1.f + expf(-gamma_T)));
+    float err = 0.f, err_x = 0.f, logph = 0.f, mu2_x = 0.f, kl_h = 0.f, n_nodes = 0.f;
+    for (int i = lane; i < N; i += 32) {
+        const size_t o = (size_t)(b * N + i) * D;
+        const float mk = mask[b * N + i];
+        n_nodes += mk;
+        for (int d = 0; d < D; ++d) {
+            const float df = eps[o + d] - net[o + d];
+            err += df * df;
+            if (d < 3) err_x += df * df;
+            g_net[o + d] = (t0 && d >= 3) ? 0.f : -df / denom;
+            const float mu = alpha_T * xh[o + d];
+            if (d < 3) mu2_x += mu * mu;
+            else kl_h += (logf(1.f / sigma_T) + 0.5f * (sigma_T * sigma_T + mu * mu) - 0.5f) * mk;
+        }
+        // categorical likelihood of the one-hot ring type given z_t (only counted when t == 0)
+        float lp[16], mx = -INFINITY;
+        for (int k = 0; k < F; ++k) {
+            const float c = zt[o + 3 + k] * norm_h + bias_h - 1.f;
+            const float hi = 0.5f * (1.f + erff((c + 0.5f) / sigma0_cat * 0.70710678118654752f));
+            const float lo = 0.5f * (1.f + erff((c - 0.5f) / sigma0_cat * 0.70710678118654752f));
+            lp[k] = logf(hi - lo + 1e-10f);
+            mx = fmaxf(mx, lp[k]);
+        }
+        float se = 0.f;
+        for (int k = 0; k < F; ++k) se += expf(lp[k] - mx);
+        const float logZ = mx + logf(se);
+        for (int k = 0; k < F; ++k) logph += (lp[k] - logZ) * (xh[o + 3 + k] * norm_h + bias_h) * mk;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        err += __shfl_xor_sync(0xffffffffu, err, off); err_x += __shfl_xor_sync(0xffffffffu, err_x, off);
+        logph += __shfl_xor_sync(0xffffffffu, logph, off); mu2_x += __shfl_xor_sync(0xffffffffu, mu2_x, off);
+        kl_h += __shfl_xor_sync(0xffffffffu, kl_h, off); n_nodes += __shfl_xor_sync(0xffffffffu, n_nodes, off);
+    }
+    if (lane == 0) {
+        const float dsub = (n_nodes - 1.f) * 3.f;
+        const float kl_x = dsub * logf(1.f / sigma_T) + 0.5f * (dsub * sigma_T * sigma_T + mu2_x) - 0.5f * dsub;
+        const float l = t0 ? (0.5f * err_x / denom - logph) : 0.5f * err / denom;
+        loss[b] = kl_x + kl_h + l;
+    }
+}
+
+static inline int ew_blocks(size_t n) { size_t b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
+
+}  // namespace gb
+
+using namespace gb;
+struct gb_graph { Graph g; };
+extern int gb_train_fail(const char* what);
+extern void gb_train_launched(int n);
+#define TR_CHECK(what)                                                     \
+    do {                                                                   \
+        cudaError_t e_ = cudaPeekAtLastError();                            \
+        if (e_ != cudaSuccess) { cudaGetLastError(); return gb_train_fail(what); } \
+        gb_train_launched(1);                                              \
+        return 0;                                                          \
+    } while (0)
+
+extern "C" int gb_gemm(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                       const float* bias, int accumulate, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (M <= 0 || N <= 0) return 0;
+    int splits = 1;
+    if (mode == 2 && K > 4096) { splits = (K + 4095) / 4096; if (splits > 32) splits = 32; }
+    const int kps = ((K + splits - 1) / splits + 15) / 16 * 16;
+    if (splits > 1 && !accumulate) cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, s);
+    dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
+    if (mode == 0) gemm_kernel<0><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, kps);
+    else if (mode == 1) gemm_kernel<1><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, kps);
+    else gemm_kernel<2><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, kps);
+    TR_CHECK("gemm");
+}
+extern "C" int gb_colsum(const float* X, int ld, int M, int N, const float* w, float* out, int accumulate, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int gy = M > 8192 ? 16 : 1;
+    if (gy > 1 && !accumulate) cudaMemsetAsync(out, 0, (size_t)N * 4, s);
+    colsum_kernel<<<dim3((N + 31) / 32, gy), 256, 0, s>>>(X, ld, M, N, w, out, accumulate);
+    TR_CHECK("colsum");
+}
+extern "C" int gb_rowdot(const float* X, int ld, int M, int N, const float* v, float bias, float* out, void* stream) {
+    rowdot_kernel<<<ew_blocks((size_t)M * 32), 256, 0, (cudaStream_t)stream>>>(X, ld, M, N, v, bias, out);
+    TR_CHECK("rowdot");
+}
+extern "C" int gb_silu_fwd(const float* x, float* y, size_t n, void* stream) {
+    silu_fwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+    TR_CHECK("silu_fwd");
+}
+extern "C" int gb_silu_bwd(const float* x, const float* gy, float* gx, size_t n, void* stream) {
+    silu_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, gy, gx, n);
+    TR_CHECK("silu_bwd");
+}
+extern "C" int gb_outer_dsilu(const float* s_row, const float* v, const float* pre, float* G, int M, int N, void* stream) {
+    outer_dsilu_kernel<<<ew_blocks((size_t)M * N), 256, 0, (cudaStream_t)stream>>>(s_row, v, pre, G, M, N);
+    TR_CHECK("outer_dsilu");
+}
+extern "C" int gb_edge_pre(const gb_graph* g, const float* Pa, const float* Pb, const float* r, const float* d0, const float* wr,
+                           const float* wd, int H, float* pre, void* stream) {
+    edge_pre_kernel<<<ew_blocks((size_t)g->g.n_edges * H), 256, 0, (cudaStream_t)stream>>>(g->g, Pa, Pb, r, d0, wr, wd, H, pre);
+    TR_CHECK("edge_pre");
+}
+extern "C" int gb_rowcol_reduce(const gb_graph* g, const float* G, int H, float scale, float* out_row, float* out_col, void* stream) {
+    rowcol_reduce_kernel<<<ew_blocks((size_t)g->g.n_nodes * 32), 256, 0, (cudaStream_t)stream>>>(g->g, G, H, scale, out_row, out_col);
+    TR_CHECK("rowcol_reduce");
+}
+extern "C" int gb_gather_rows(const gb_graph* g, const float* X, int H, float scale, float* out, void* stream) {
+    gather_rows_kernel<<<ew_blocks((size_t)g->g.n_edges * H), 256, 0, (cudaStream_t)stream>>>(g->g, X, H, scale, out);
+    TR_CHECK("gather_rows");
+}
+extern "C" int gb_gate_fwd(const float* m, const float* logit, int E, int H, float* ef, float* gate, void* stream) {
+    gate_fwd_kernel<<<ew_blocks((size_t)E * H), 256, 0, (cudaStream_t)stream>>>(m, logit, E, H, ef, gate);
+    TR_CHECK("gate_fwd");
+}
+extern "C" int gb_gate_bwd(const float* m, const float* gate, const float* wa, const float* g_ef, int E, int H, float* g_m,
+                           float* coef, void* stream) {
+    gate_bwd_kernel<<<ew_blocks((size_t)E * 32), 256, 0, (cudaStream_t)stream>>>(m, gate, wa, g_ef, E, H, g_m, coef);
+    TR_CHECK("gate_bwd");
+}
+extern "C" int gb_geom_fwd(const gb_graph* g, const float* x, float norm_constant, float* r, float* u, void* stream) {
+    geom_fwd_kernel<<<ew_blocks(g->g.n_edges), 256, 0, (cudaStream_t)stream>>>(g->g, x, norm_constant, r, u);
+    TR_CHECK("geom_fwd");
+}
+extern "C" int gb_geom_bwd(const gb_graph* g, const float* x, float norm_constant, const float* g_r, const float* g_u, float* g_d_scratch,
+                           float* g_x, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    geom_bwd_edge_kernel<<<ew_blocks(g->g.n_edges), 256, 0, s>>>(g->g, x, norm_constant, g_r, g_u, g_d_scratch);
+    node_diff_reduce_kernel<<<ew_blocks((size_t)g->g.n_nodes * 3), 256, 0, s>>>(g->g, g_d_scratch, g_x);
+    TR_CHECK("geom_bwd");
+}
+extern "C" int gb_coord_fwd(const gb_graph* g, const float* x, const float* u, const float* phi, float range, int use_tanh, float normf,
+                            float* x_out, float* tau, void* stream) {
+    coord_fwd_kernel<<<ew_blocks(g->g.n_edges), 256, 0, (cudaStream_t)stream>>>(g->g, x, u, phi, range, use_tanh, normf, x_out, tau);
+    TR_CHECK("coord_fwd");
+}
+extern "C" int gb_coord_bwd(const gb_graph* g, const float* u, const float* tau, const float* g_xout, float range, int use_tanh,
+                            float normf, float* g_phi, float* g_u, float* g_x, void* stream) {
+    coord_bwd_kernel<<<ew_blocks(g->g.n_edges), 256, 0, (cudaStream_t)stream>>>(g->g, u, tau, g_xout, range, use_tanh, normf, g_phi, g_u, g_x);
+    TR_CHECK("coord_bwd");
+}
+extern "C" int gb_resmask(const float* a, const float* b, const float* mask, int M, int N, float* out, void* stream) {
+    resmask_kernel<<<ew_blocks((size_t)M * N), 256, 0, (cudaStream_t)stream>>>(a, b, mask, M, N, out);
+    TR_CHECK("resmask");
+}
+extern "C" int gb_den_finish_bwd(const float* g_eps, const float* mask, int B, int N, int F, float* g_xfin, float* g_h3, void* stream) {
+    den_finish_bwd_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(g_eps, mask, B, N, F, g_xfin, g_h3);
+    TR_CHECK("den_finish_bwd");
+}
+extern "C" int gb_train_loss(const float* net, const float* eps, const float* zt, const float* xh, const float* mask, const float* t_int,
+                             const float* gamma_t, float gamma_T, float norm_h, float bias_h, int B, int N, int F, float* loss,
+                             float* g_net, void* stream) {
+    if (F > 16) return gb_train_fail("train_loss: too many classes");
+    train_loss_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(net, eps, zt, xh, mask, t_int, gamma_t, gamma_T, norm_h, bias_h, B, N, F, loss, g_net);
+    TR_CHECK("train_loss");
+}

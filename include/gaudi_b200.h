@@ -147,6 +147,54 @@ int gb_pred_layer_forward(const gb_net* net, const gb_graph* g, int layer, const
 int gb_pred_egnn_forward(const gb_net* net, const gb_graph* g, const float* h_in, const float* x_in, const float* a_edge,
                          float* h_out, float* x_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- training step (BASELINE config 5): unfused ops of the EDM denoising loss and its backward.
+ * Replaces torch autograd over EnVariationalDiffusion.forward (edm/equivariant_diffusion/en_diffusion.py:777-797,
+ * 644-775) -> EGNN_dynamics._forward (edm/egnn/models.py:76-152) -> EquivariantBlock (edm/egnn/egnn_new.py:42-235) as
+ * driven by train_edm.compute_loss (train_edm.py:36-49).  All pointers are fp32 device memory, row-major.
+ * gb_gemm        mode 0: C[M,N] = A[M,K] B[N,K]^T (+bias[N])   1: C = A[M,K] B[K,N]   2: C = A[K,M]^T B[K,N];
+ *                accumulate != 0 adds into C.  (nn.Linear forward / dgrad / wgrad)
+ * gb_colsum      out[k] (+)= sum_m w[m] X[m][k]   (w NULL: 1)      bias and weight-column gradients
+ * gb_rowdot      out[m] = bias + X[m,:] . v                         att_mlp logit / coord_mlp last layer / dL/dr
+ * gb_silu_*      SiLU and its backward;  gb_outer_dsilu: G[m][k] = s[m] v[k] SiLU'(pre[m][k])
+ * gb_edge_pre    pre[e] = Pa[row_e] + Pb[col_e] + wr r_e + wd d0_e   (first edge Linear, factorised; egnn_new.py:43-47)
+ * gb_rowcol_reduce  out_row[i] = scale * sum_{e: row_e = i} G[e], out_col[j] = scale * sum_{e: col_e = j} G[e]
+ *                   (unsorted_segment_sum, egnn_new.py:403-419, and the backward of gb_edge_pre); either may be NULL
+ * gb_gather_rows out[e] = scale * X[row_e]                          backward of the row segment sum
+ * gb_gate_*      attention gate ef = m * sigmoid(logit) (egnn_new.py:49-56) and its backward (coef = dL/dlogit)
+ * gb_geom_*      coord2diff (egnn_new.py:394-400) and its backward into the coordinates (g_d_scratch [n_edges,3])
+ * gb_coord_*     x' = (x + sum_row u * tanh(phi) * range / normf) * mask (egnn_new.py:122-155) and its backward
+ * gb_resmask     out = (a + b) * mask[row]  (b NULL: a * mask)
+ * gb_den_finish_bwd  backward of the EGNN_dynamics tail (models.py:116-152): g_xfin [n,3], g_h3 [n,F+1]
+ * gb_train_loss  loss[b] of compute_loss(t0_always = False), training mode, loss_type 'l2', include_charges = False,
+ *                and g_net = d loss[b] / d net_out.  gamma_t [B], t_int [B] (as float). */
+int gb_gemm(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+            const float* bias, int accumulate, void* stream);
+int gb_colsum(const float* X, int ld, int M, int N, const float* w, float* out, int accumulate, void* stream);
+int gb_rowdot(const float* X, int ld, int M, int N, const float* v, float bias, float* out, void* stream);
+int gb_silu_fwd(const float* x, float* y, size_t n, void* stream);
+int gb_silu_bwd(const float* x, const float* gy, float* gx, size_t n, void* stream);
+int gb_outer_dsilu(const float* s_row, const float* v, const float* pre, float* G, int M, int N, void* stream);
+int gb_edge_pre(const gb_graph* g, const float* Pa, const float* Pb, const float* r, const float* d0, const float* wr,
+                const float* wd, int H, float* pre, void* stream);
+int gb_rowcol_reduce(const gb_graph* g, const float* G, int H, float scale, float* out_row, float* out_col, void* stream);
+int gb_gather_rows(const gb_graph* g, const float* X, int H, float scale, float* out, void* stream);
+int gb_gate_fwd(const float* m, const float* logit, int E, int H, float* ef, float* gate, void* stream);
+int gb_gate_bwd(const float* m, const float* gate, const float* wa, const float* g_ef, int E, int H, float* g_m,
+                float* coef, void* stream);
+int gb_geom_fwd(const gb_graph* g, const float* x, float norm_constant, float* r, float* u, void* stream);
+int gb_geom_bwd(const gb_graph* g, const float* x, float norm_constant, const float* g_r, const float* g_u,
+                float* g_d_scratch, float* g_x, void* stream);
+int gb_coord_fwd(const gb_graph* g, const float* x, const float* u, const float* phi, float range, int use_tanh,
+                 float normf, float* x_out, float* tau, void* stream);
+int gb_coord_bwd(const gb_graph* g, const float* u, const float* tau, const float* g_xout, float range, int use_tanh,
+                 float normf, float* g_phi, float* g_u, float* g_x, void* stream);
+int gb_resmask(const float* a, const float* b, const float* mask, int M, int N, float* out, void* stream);
+int gb_den_finish_bwd(const float* g_eps, const float* mask, int B, int N, int F, float* g_xfin, float* g_h3,
+                      void* stream);
+int gb_train_loss(const float* net, const float* eps, const float* zt, const float* xh, const float* mask,
+                  const float* t_int, const float* gamma_t, float gamma_T, float norm_h, float bias_h, int B, int N,
+                  int F, float* loss, float* g_net, void* stream);
+
 /* ---- measurement aid (bench.py roofline leg): re-launch ONE kernel `repeats` times on the workspace left by the
  * last forward / input-gradient call.  which: 0 denoiser GCL edge, 1 denoiser EquivariantUpdate edge (denoiser
  * workspace); 2 predictor edge forward, 3 predictor edge backward, 4 node-MLP Linear (predictor grad workspace). */

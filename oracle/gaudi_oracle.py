@@ -457,3 +457,63 @@ def e_gcl_layer(w: Weights, key: str, h: Tensor, x: Tensor, row: Tensor, col: Te
     agg = _segment_sum(ef, row, h.size(0))
     upd = _lin(w, key + "node_mlp.2", F.silu(_lin(w, key + "node_mlp.0", torch.cat([h, agg], dim=1))))
     return (h + upd) * nm, x_new * nm
+
+
+# --------------------------------------------------------------------------
+# training loss: EnVariationalDiffusion.forward in train mode, loss_type 'l2',
+# include_charges = False, as driven by train_edm.compute_loss (train_edm.py:36-49)
+# --------------------------------------------------------------------------
+def _sum_except_batch(x: Tensor) -> Tensor:
+    return x.reshape(x.size(0), -1).sum(-1)
+
+
+def _cdf_std_gaussian(x: Tensor) -> Tensor:
+    return 0.5 * (1.0 + torch.erf(x / math.sqrt(2)))                 # en_diffusion.py:160-161
+
+
+def training_loss(w: Weights, cfg: DenoiserCfg, gamma: Tensor, x: Tensor, h_cat: Tensor, node_mask: Tensor,
+                  edge_mask: Tensor, t_int: Tensor, eps: Tensor) -> Tuple[Tensor, Tensor]:
+    """(loss [B], z_t) of compute_loss(t0_always=False) with the two random draws (t_int [B,1] float, eps [B,N,D])
+    injected.  en_diffusion.py:777-804 (forward), :384-404 (normalize), :644-775 (compute_loss), :459-491 (kl_prior),
+    :568-642 (log_pxh_given_z0_without_constants), :507-520 (compute_error)."""
+    B, N, _ = x.shape
+    T = cfg.timesteps
+    x = x / cfg.norm_values[0]                                        # normalize, :385
+    hc = (h_cat.float() - cfg.norm_biases[1]) / cfg.norm_values[1] * node_mask
+    t_is_zero = (t_int == 0).float()
+    t = t_int / T                                                     # :666
+    g_t = gamma[torch.round(t * T).long()].view(B, 1, 1)              # PredefinedNoiseSchedule.forward, :228-230
+    alpha_t, sigma_t = torch.sqrt(torch.sigmoid(-g_t)), torch.sqrt(torch.sigmoid(g_t))
+    xh = torch.cat([x, hc], dim=2)                                    # :683 (the integer part is empty)
+    z_t = alpha_t * xh + sigma_t * eps                                # :685
+    net_out = denoiser_forward(w, cfg, z_t, t, node_mask, edge_mask)   # per-sample time column (models.py:100-103)
+    denom = (3 + cfg.in_node_nf) * N                                  # compute_error, :511-514 (training, l2)
+    error = _sum_except_batch((eps - net_out) ** 2) / denom
+    loss_t_larger_than_zero = 0.5 * error                             # SNR_weight = 1, :695-701
+    # kl_prior, :459-491
+    g_T = gamma[T].view(1, 1, 1).expand(B, 1, 1)
+    alpha_T = torch.sqrt(torch.sigmoid(-g_T))
+    mu_T = alpha_T * xh
+    mu_T_x, mu_T_h = mu_T[:, :, :3], mu_T[:, :, 3:]
+    sigma_T_x = torch.sqrt(torch.sigmoid(g_T)).squeeze()
+    sigma_T_h = torch.sqrt(torch.sigmoid(g_T))
+    kl_h = _sum_except_batch((torch.log(1.0 / sigma_T_h) + 0.5 * (sigma_T_h ** 2 + mu_T_h ** 2) - 0.5) * node_mask)  # :131-145
+    d_sub = (node_mask.squeeze(2).sum(1) - 1) * 3                     # :379-382
+    mu_norm2 = _sum_except_batch(mu_T_x ** 2)
+    kl_x = d_sub * torch.log(1.0 / sigma_T_x) + 0.5 * (d_sub * sigma_T_x ** 2 + mu_norm2) - 0.5 * d_sub              # :148-157
+    kl_prior = kl_x + kl_h
+    # L0 term evaluated at (z_t, gamma_t) and selected by t == 0, :568-642
+    eps_x, net_x = eps[:, :, :3], net_out[:, :, :3]
+    log_p_x = -0.5 * _sum_except_batch((eps_x - net_x) ** 2) / denom  # compute_error on the x part (same denom: eps_t.shape[1] = N)
+    sigma_0_cat = sigma_t * cfg.norm_values[1]
+    onehot = hc * cfg.norm_values[1] + cfg.norm_biases[1]
+    centered = z_t[:, :, 3:] * cfg.norm_values[1] + cfg.norm_biases[1] - 1
+    log_prop = torch.log(_cdf_std_gaussian((centered + 0.5) / sigma_0_cat)
+                         - _cdf_std_gaussian((centered - 0.5) / sigma_0_cat) + 1e-10)
+    log_probs = log_prop - torch.logsumexp(log_prop, dim=2, keepdim=True)
+    log_ph_cat = _sum_except_batch(log_probs * onehot * node_mask)
+    loss_term_0 = -(log_p_x + log_ph_cat)                             # the integer part sums to 0 over an empty tensor
+    tz = t_is_zero.squeeze(1)
+    loss = kl_prior + loss_term_0 * tz + (1 - tz) * loss_t_larger_than_zero     # :744-760; constants and delta_log_px are zeroed
+    return loss, z_t
+

@@ -207,10 +207,63 @@ def chain(dataset, nodesxsample, guided, target_name, scale, std, seed, record_e
     return rec
 
 
+def train_step(dataset, nodesxsample, t_list, seed):
+    """One training-loss evaluation + backward of the reference (train_edm.py:36-49, 71-75) with the two random draws of
+    compute_loss (en_diffusion.py:657-659 t_int, :677-679 eps) pinned so that the oracle / product can be fed the same."""
+    args, model, pred, prop = build(dataset)
+    for n_, p_ in model.named_parameters():
+        p_.requires_grad_(not n_.endswith("gamma.gamma"))          # the noise table is a frozen Parameter (en_diffusion.py:214-216)
+    model.train()
+    F_in = 1 if dataset == "cata" else 12
+    gen = torch.Generator().manual_seed(seed)
+    nm, em = ref_masks(args, nodesxsample)
+    B, N = nm.shape[0], nm.shape[1]
+    x = remove_mean_with_mask(torch.randn((B, N, 3), generator=gen) * 2.5 * nm, nm)
+    cls = torch.randint(0, F_in, (B, N), generator=gen)
+    h = torch.nn.functional.one_hot(cls, F_in).float() * nm
+    t_int = torch.tensor(t_list, dtype=torch.int64).view(B, 1)
+    eps = processed_noise(gen, (B, N, 3 + F_in), nm)
+    real_randint = torch.randint
+    torch.randint = lambda *a, **k: t_int.clone()
+    inner = model.module if hasattr(model, "module") else model     # get_model may wrap the model (MyDataParallel)
+    inner.sample_combined_position_feature_noise = lambda n_samples, n_nodes, node_mask, std=1.0: eps.clone()
+    try:
+        hd = {"categorical": h, "integer": torch.zeros(0)}          # train_edm.py:42
+        loss_b = model(x, hd, nm, em.view(B, N * N))
+        loss = loss_b.mean(0)                                       # train_edm.py:47
+        loss.backward()
+    finally:
+        torch.randint = real_randint
+    full = ["dynamics.egnn.embedding.weight", "dynamics.egnn.embedding.bias", "dynamics.egnn.embedding_out.weight",
+            "dynamics.egnn.e_block_0.gcl_0.att_mlp.0.weight", "dynamics.egnn.e_block_4.gcl_0.edge_mlp.0.bias",
+            "dynamics.egnn.e_block_8.gcl_equiv.coord_mlp.4.weight", "dynamics.egnn.e_block_0.gcl_equiv.coord_mlp.0.weight"]
+    names, norms = [], []
+    out = dict(nodesxsample=nodesxsample.numpy(), x=x.numpy(), h=h.numpy(), t_int=t_int.numpy(), eps=eps.numpy(),
+               loss_b=loss_b.detach().numpy(), loss=loss.detach().numpy())
+    for n_, p_ in model.named_parameters():
+        if p_.grad is None:
+            continue
+        n_ = n_[len("module."):] if n_.startswith("module.") else n_
+        names.append(n_)
+        norms.append(float(p_.grad.double().norm()))
+        if n_ in full:
+            out["grad:" + n_] = p_.grad.numpy()
+    out["grad_names"] = np.array(names)
+    out["grad_norms"] = np.array(norms, dtype=np.float64)
+    return out
+
+
 def main():
     meta = {"torch": torch.__version__, "seed_denoiser": SEED_DEN, "seed_predictor": SEED_PRED,
             "prop_mean": MEAN5.tolist(), "prop_std": STD5.tolist()}
     steps = [1000, 999, 750, 500, 250, 2, 1]
+
+    if "--only-train" in sys.argv:          # add the training fixtures without regenerating the (slow) chains
+        np.savez_compressed(os.path.join(HERE, "train_cata.npz"),
+                            **train_step("cata", torch.tensor([11, 10, 9, 11, 7, 2]), [1000, 613, 0, 1, 250, 0], seed=555))
+        np.savez_compressed(os.path.join(HERE, "train_hetro.npz"),
+                            **train_step("hetro", torch.tensor([10, 8, 3]), [777, 0, 12], seed=556))
+        return
 
     # masks, both datasets, ragged sizes incl. minimum
     for ds, nx in [("cata", [11, 10, 9, 11, 7, 2]), ("hetro", [10, 8, 10, 3, 1])]:
@@ -237,6 +290,12 @@ def main():
     rec = chain("cata", torch.tensor([11, 10, 8]), False, None, 0.0, 0.7, seed=78)
     np.savez_compressed(os.path.join(HERE, "chain_cata_unguided.npz"), **rec)
     print("chain unguided done", flush=True)
+
+    np.savez_compressed(os.path.join(HERE, "train_cata.npz"),
+                        **train_step("cata", torch.tensor([11, 10, 9, 11, 7, 2]), [1000, 613, 0, 1, 250, 0], seed=555))
+    np.savez_compressed(os.path.join(HERE, "train_hetro.npz"),
+                        **train_step("hetro", torch.tensor([10, 8, 3]), [777, 0, 12], seed=556))
+    print("train done", flush=True)
 
     with open(os.path.join(HERE, "meta.json"), "w") as f:
         json.dump(meta, f, indent=1, sort_keys=True)

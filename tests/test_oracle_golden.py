@@ -101,3 +101,25 @@ def test_fp64_oracle_agrees_with_fp32():
     e32 = O.denoiser_forward(wd, dcfg, z, t, nm, em)
     e64 = O.denoiser_forward({k: v.double() for k, v in wd.items()}, dcfg, z.double(), t.double(), nm.double(), em.double())
     assert maxabs(e32, e64) <= 1e-5
+
+
+@pytest.mark.parametrize("ds", ["cata", "hetro"])
+def test_training_loss_and_gradients_match_reference(ds):
+    """Row a19: loss [B] of the reference's train-mode forward (t_int / eps pinned, incl. t = 0 and t = T samples) and
+    its parameter gradients (all 139 norms, 7 full tensors)."""
+    g = golden(f"train_{ds}.npz")
+    args, model, pred, prop = build_models(ds, "cpu")
+    dcfg, _ = oracle_cfgs(ds)
+    w = {k: v.detach().clone().requires_grad_(not k.endswith("gamma.gamma")) for k, v in model.state_dict().items()}
+    nm, em = O.build_masks(torch.from_numpy(g["nodesxsample"]), 11 if ds == "cata" else 10, ds == "hetro")
+    loss, _ = O.training_loss(w, dcfg, O.gamma_table(dcfg), torch.from_numpy(g["x"]), torch.from_numpy(g["h"]), nm, em,
+                              torch.from_numpy(g["t_int"]).float(), torch.from_numpy(g["eps"]))
+    assert maxabs(loss, g["loss_b"]) <= 1e-6
+    loss.mean(0).backward()
+    assert abs(float(loss.mean(0)) - float(g["loss"])) <= 1e-6
+    for name, norm in zip(g["grad_names"], g["grad_norms"]):
+        assert abs(float(w[str(name)].grad.double().norm()) - norm) <= 1e-5 * max(norm, 1e-6), name
+    for k in g.files:
+        if k.startswith("grad:"):
+            ref = torch.from_numpy(g[k])
+            assert maxabs(w[k[5:]].grad, ref) <= 1e-6 * max(1.0, float(ref.abs().max())), k
