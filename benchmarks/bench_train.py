@@ -1,0 +1,97 @@
+#!/usr/bin/env python
+"""BASELINE.json config 5: EDM training step (denoising loss forward + backward + AdamW) on a synthetic cc-PBH batch of 512.
+
+One JSON line: CUDA-event time per step (zero_grad, loss, backward, optimizer step, as train_edm.py:71-82), molecules/s,
+our kernel launches per step, and -- unless --no-cpu -- the CPU oracle's autograd step on a bounded sample beside it.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import torch  # noqa: E402
+
+import gaudi_b200 as gb  # noqa: E402
+from gaudi_b200 import _lib  # noqa: E402
+from bench_shapes import models  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=32)
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    a, model, pred, nodes_dist, prop = models("cata", dev)
+    for n_, p_ in model.named_parameters():
+        p_.requires_grad_(not n_.endswith("gamma.gamma"))
+    model.train()
+    torch.manual_seed(0)
+    B, N = args.batch, 11
+    nx = nodes_dist.sample(B)
+    nm, em = gb.build_masks(nx, N, False, device=dev)
+    x = torch.randn(B, N, 3, device=dev) * 2.5 * nm
+    x = x - x.sum(1, keepdim=True) / nm.sum(1, keepdim=True) * nm
+    h = {"categorical": torch.ones(B, N, 1, device=dev) * nm, "integer": torch.zeros(0, device=dev)}
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, amsgrad=True, weight_decay=1e-12)
+
+    def step():
+        opt.zero_grad()
+        loss = model(x, h, nm, em).mean(0)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    l0 = _lib.lib().gb_launch_count(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    out = {"config": 5, "workload": "EDM training step (l2 denoising loss fwd+bwd+AdamW), cc-PBH shape, synthetic batch",
+           "batch": B, "edges": int(em.sum().item()), "ms_per_step": ms, "molecules_per_s": B / (ms * 1e-3),
+           "gpu_launches_per_step": (_lib.lib().gb_launch_count(0) - l0) / args.steps, "loss": float(loss)}
+    if not args.no_cpu:
+        import gaudi_oracle as O
+        cb = args.cpu_batch
+        dcfg = O.DenoiserCfg(in_node_nf=1)
+        w = {k: v.detach().cpu().clone().requires_grad_(not k.endswith("gamma.gamma")) for k, v in model.state_dict().items()}
+        nmc, emc = nm[:cb].cpu(), em.view(B, N * N)[:cb].reshape(-1, 1).cpu()
+        xc, hc = x[:cb].cpu(), h["categorical"][:cb].cpu()
+        copt = torch.optim.AdamW([v for v in w.values() if v.requires_grad], lr=1e-4, amsgrad=True, weight_decay=1e-12)
+        gamma = O.gamma_table(dcfg)
+
+        def cpu_step():
+            copt.zero_grad()
+            t_int = torch.randint(0, 1001, (cb, 1)).float()
+            eps = O.draw_noise(cb, N, 4, nmc)
+            l, _ = O.training_loss(w, dcfg, gamma, xc, hc, nmc, emc, t_int, eps)
+            l.mean(0).backward()
+            copt.step()
+
+        cpu_step()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            cpu_step()
+        dt = (time.perf_counter() - t0) / reps
+        out["cpu_oracle"] = {"batch": cb, "s_per_step": dt, "molecules_per_s": cb / dt, "threads": torch.get_num_threads()}
+        out["speedup_vs_cpu_oracle"] = out["molecules_per_s"] / (cb / dt)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -54,7 +54,7 @@ SIGNATURES = {
     # training step ops
     "gb_gemm": (_I, [_I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P]),
     "gb_colsum": (_I, [_P, _I, _I, _I, _P, _P, _I, _P]),
-    "gb_rowdot": (_I, [_P, _I, _I, _I, _P, _F, _P, _P]),
+    "gb_rowdot": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "gb_silu_fwd": (_I, [_P, _P, _SZ, _P]),
     "gb_silu_bwd": (_I, [_P, _P, _P, _SZ, _P]),
     "gb_outer_dsilu": (_I, [_P, _P, _P, _P, _I, _I, _P]),
@@ -69,6 +69,8 @@ SIGNATURES = {
     "gb_coord_bwd": (_I, [_P, _P, _P, _P, _F, _I, _F, _P, _P, _P, _P]),
     "gb_resmask": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "gb_den_finish_bwd": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "gb_den_finish_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "gb_make_zt": (_I, [_P, _P, _P, _P, _P, _P, _F, _F, _F, _I, _I, _I, _P, _P, _P, _P]),
     "gb_train_loss": (_I, [_P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _I, _I, _I, _P, _P, _P]),
 }
 

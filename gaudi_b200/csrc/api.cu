@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -17,7 +18,7 @@ using namespace gb;
 // error handling / launch counting
 // ------------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
-static thread_local long long g_launches = 0;
+static std::atomic<long long> g_launches{0};   // process-wide: autograd runs backward ops on its own thread
 
 static int fail(const char* fmt, ...) {
     char buf[512];
@@ -47,7 +48,7 @@ extern "C" int gb_abi_version(void) { return 1; }
 extern "C" const char* gb_last_error(void) { return g_err.c_str(); }
 extern "C" long long gb_launch_count(int reset) {
     long long v = g_launches;
-    if (reset) g_launches = 0;
+    if (reset) g_launches.store(0);
     return v;
 }
 

@@ -91,9 +91,9 @@ __global__ void colsum_kernel(const float* __restrict__ X, int ld, int M, int N,
     }
 }
 
-// out[m] = bias + sum_k X[m][k] v[k]     (one warp per row)
-__global__ void rowdot_kernel(const float* __restrict__ X, int ld, int M, int N, const float* __restrict__ v, float bias,
-                              float* __restrict__ out) {
+// out[m] = bias[0] + sum_k X[m][k] v[k]     (one warp per row; bias is a device scalar or null)
+__global__ void rowdot_kernel(const float* __restrict__ X, int ld, int M, int N, const float* __restrict__ v,
+                              const float* __restrict__ bias, float* __restrict__ out) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int nw = (gridDim.x * blockDim.x) >> 5;
     for (int m = warp; m < M; m += nw) {
@@ -101,7 +101,7 @@ __global__ void rowdot_kernel(const float* __restrict__ X, int ld, int M, int N,
         for (int k = lane; k < N; k += 32) s = fmaf(X[(size_t)m * ld + k], v[k], s);
 #pragma unroll
         for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (lane == 0) out[m] = s + bias;
+        if (lane == 0) out[m] = s + (bias ? bias[0] : 0.f);
     }
 }
 
@@ -112,13 +112,13 @@ __global__ void silu_fwd_kernel(const float* __restrict__ x, float* __restrict__
 __global__ void silu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) gx[i] = gy[i] * dsilu_f(x[i]);
 }
-// G[e][k] = s[e] * v[k] * SiLU'(pre[e][k])   (backward of  phi = v . SiLU(pre))
+// G[e][k] = s[e] * v[k] * SiLU'(pre[e][k])   (backward of  phi = v . SiLU(pre); pre == null: plain outer product)
 __global__ void outer_dsilu_kernel(const float* __restrict__ s, const float* __restrict__ v, const float* __restrict__ pre,
                                    float* __restrict__ G, int M, int N) {
     const size_t n = (size_t)M * N;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int e = (int)(i / N), k = (int)(i % N);
-        G[i] = s[e] * v[k] * dsilu_f(pre[i]);
+        G[i] = s[e] * v[k] * (pre ? dsilu_f(pre[i]) : 1.f);
     }
 }
 
@@ -348,6 +348,52 @@ __global__ void train_loss_kernel(const float* __restrict__ net, const float* __
     }
 }
 
+// EGNN_dynamics tail (edm/egnn/models.py:116-152): eps = [remove_mean((x_fin - x_in) mask), h3[:, :F]]
+__global__ void den_finish_fwd_kernel(const float* __restrict__ x_fin, const float* __restrict__ x_in, const float* __restrict__ h3,
+                                      const float* __restrict__ mask, int B, int N, int F, float* __restrict__ eps) {
+    const int D = 3 + F;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    float s[3] = {0.f, 0.f, 0.f}, cnt = 0.f;
+    for (int i = lane; i < N; i += 32) {
+        const int node = b * N + i;
+        const float mk = mask[node];
+        cnt += mk;
+        for (int d = 0; d < 3; ++d) s[d] += (x_fin[3 * node + d] - x_in[3 * node + d]) * mk;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        for (int d = 0; d < 3; ++d) s[d] += __shfl_xor_sync(0xffffffffu, s[d], off);
+    }
+    cnt = fmaxf(cnt, 1.f);
+    for (int i = lane; i < N; i += 32) {
+        const int node = b * N + i;
+        const float mk = mask[node];
+        for (int d = 0; d < 3; ++d) eps[(size_t)node * D + d] = (x_fin[3 * node + d] - x_in[3 * node + d]) * mk - s[d] / cnt * mk;
+        for (int k = 0; k < F; ++k) eps[(size_t)node * D + 3 + k] = h3[(size_t)node * (F + 1) + k];
+    }
+}
+
+// normalize (en_diffusion.py:384-404) + q(z_t | x, h) (:661-685): xh = [x / nx, (h - bh) / nh * mask], z_t = alpha_t xh + sigma_t eps,
+// with gamma_t looked up on the device from the schedule table at round(t_int) (PredefinedNoiseSchedule.forward, :228-230)
+__global__ void make_zt_kernel(const float* __restrict__ x, const float* __restrict__ h, const float* __restrict__ mask,
+                               const float* __restrict__ eps, const float* __restrict__ gamma, const float* __restrict__ t_int,
+                               float norm_x, float norm_h, float bias_h, int B, int N, int F, float* __restrict__ xh,
+                               float* __restrict__ zt, float* __restrict__ gamma_t) {
+    const int D = 3 + F;
+    const size_t n = (size_t)B * N * D;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int node = (int)(i / D), d = (int)(i % D), b = node / N;
+        const float g = gamma[(int)t_int[b]];
+        const float alpha = sqrtf(1.f / (1.f + expf(g))), sigma = sqrtf(1.f / (1.f + expf(-g)));
+        const float v = d < 3 ? x[(size_t)node * 3 + d] / norm_x : (h[(size_t)node * F + d - 3] - bias_h) / norm_h * mask[node];
+        xh[i] = v;
+        zt[i] = alpha * v + sigma * eps[i];
+        if (d == 0 && node % N == 0) gamma_t[b] = g;
+    }
+}
+
 static inline int ew_blocks(size_t n) { size_t b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
 
 }  // namespace gb
@@ -385,7 +431,7 @@ extern "C" int gb_colsum(const float* X, int ld, int M, int N, const float* w, f
     colsum_kernel<<<dim3((N + 31) / 32, gy), 256, 0, s>>>(X, ld, M, N, w, out, accumulate);
     TR_CHECK("colsum");
 }
-extern "C" int gb_rowdot(const float* X, int ld, int M, int N, const float* v, float bias, float* out, void* stream) {
+extern "C" int gb_rowdot(const float* X, int ld, int M, int N, const float* v, const float* bias, float* out, void* stream) {
     rowdot_kernel<<<ew_blocks((size_t)M * 32), 256, 0, (cudaStream_t)stream>>>(X, ld, M, N, v, bias, out);
     TR_CHECK("rowdot");
 }
@@ -458,4 +504,16 @@ extern "C" int gb_train_loss(const float* net, const float* eps, const float* zt
     if (F > 16) return gb_train_fail("train_loss: too many classes");
     train_loss_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(net, eps, zt, xh, mask, t_int, gamma_t, gamma_T, norm_h, bias_h, B, N, F, loss, g_net);
     TR_CHECK("train_loss");
+}
+extern "C" int gb_den_finish_fwd(const float* x_fin, const float* x_in, const float* h3, const float* mask, int B, int N, int F,
+                                 float* eps, void* stream) {
+    den_finish_fwd_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x_fin, x_in, h3, mask, B, N, F, eps);
+    TR_CHECK("den_finish_fwd");
+}
+extern "C" int gb_make_zt(const float* x, const float* h, const float* mask, const float* eps, const float* gamma, const float* t_int,
+                          float norm_x, float norm_h, float bias_h, int B, int N, int F, float* xh, float* zt, float* gamma_t,
+                          void* stream) {
+    make_zt_kernel<<<ew_blocks((size_t)B * N * (3 + F)), 256, 0, (cudaStream_t)stream>>>(x, h, mask, eps, gamma, t_int, norm_x, norm_h,
+                                                                                       bias_h, B, N, F, xh, zt, gamma_t);
+    TR_CHECK("make_zt");
 }

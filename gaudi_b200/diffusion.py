@@ -211,8 +211,26 @@ class EnVariationalDiffusion(torch.nn.Module):
             h_int = h_int * node_mask
         return x, h_cat, h_int
 
-    def forward(self, x, h, node_mask=None, edge_mask=None, context=None):
-        raise NotImplementedError("the training loss is outside the guided-sampling hot path (SURVEY.md 8: config 5 is 'next')")
+    def _gamma_T(self) -> float:
+        """gamma(1) as a host float (cached: the schedule table is frozen)."""
+        g = self.gamma.gamma
+        key = (g.data_ptr(), g._version)
+        cache = self.__dict__.get("_gT")
+        if cache is None or cache[0] != key:
+            cache = (key, float(g.detach()[-1].cpu()))
+            self.__dict__["_gT"] = cache
+        return cache[1]
+
+    def forward(self, x, h, node_mask=None, edge_mask=None, context=None, t_int=None, eps=None):
+        """Training loss [B] (en_diffusion.py:777-804): train mode, loss_type 'l2' -- the configuration train_edm.py runs.
+        ``t_int`` / ``eps`` optionally pin the two random draws of compute_loss (tests).  The eval-mode NLL estimator
+        (t0_always=True, two network passes, SNR weighting) is not built."""
+        if context is not None:
+            raise NotImplementedError("context conditioning is unused by GaUDI")
+        if not self.training:
+            raise NotImplementedError("eval-mode NLL (compute_loss(t0_always=True)) is not implemented; call .train()")
+        from . import training
+        return training.training_loss(self, x, h, node_mask, edge_mask, t_int=t_int, eps=eps)
 
     # ---- noise -------------------------------------------------------------------------------------------------
     def sample_combined_position_feature_noise(self, n_samples, n_nodes, node_mask, std=1.0):

@@ -1,0 +1,391 @@
+"""Training step of the EDM denoiser (BASELINE config 5).
+
+Replaces torch autograd over ``EnVariationalDiffusion.forward`` (edm/equivariant_diffusion/en_diffusion.py:777-804,
+644-775) -> ``EGNN_dynamics._forward`` (edm/egnn/models.py:76-152) -> ``EquivariantBlock`` (edm/egnn/egnn_new.py:42-235)
+as driven by ``train_edm.compute_loss`` / ``train_epoch`` (train_edm.py:36-49, 71-75).
+
+The batch is small (512 molecules), so unlike the sampler this path is unfused: each op below is one or a few
+hand-written kernels behind the C ABI (``gb_gemm``, ``gb_edge_pre``, ...; csrc/train_ops.cu) with an explicit backward
+that also produces the weight gradients.  ``torch.autograd.Function`` only chains them and accumulates ``.grad``;
+``torch.optim`` stays the optimiser, as in the reference.  The message passing runs on the compacted edge list of
+``graph.build_topology`` (masked edges contribute exact zeros in the reference).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .runtime import _ptr, _stream, _need_cuda, graph_for
+
+_F = C.c_float
+
+
+def _call(name: str, *args) -> None:
+    _lib.check(getattr(_lib.lib(), name)(*args, _stream()))
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _gemm(mode: int, M: int, N: int, K: int, A, lda, B, ldb, Cm, ldc, bias=None, acc=False) -> None:
+    _call("gb_gemm", mode, M, N, K, _ptr(A), lda, _ptr(B), ldb, _ptr(Cm), ldc, _ptr(bias), int(acc))
+
+
+def _colsum(X, M: int, N: int, w=None) -> torch.Tensor:
+    out = torch.empty(N, dtype=torch.float32, device=X.device)
+    _call("gb_colsum", _ptr(X), N, M, N, _ptr(w), _ptr(out), 0)
+    return out
+
+
+def _new(ref: torch.Tensor, *shape) -> torch.Tensor:
+    return torch.empty(*shape, dtype=torch.float32, device=ref.device)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class _Linear(torch.autograd.Function):
+    """y = (x W^T + b) [* mask]  -- nn.Linear (+ the node mask of egnn_new.py:318)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, mask):
+        x, W = _c(x), _c(W)
+        M, K = x.shape
+        N = W.shape[0]
+        y = _new(x, M, N)
+        _gemm(0, M, N, K, x, K, W, K, y, N, b)
+        if mask is not None:
+            _call("gb_resmask", _ptr(y), None, _ptr(mask), M, N, _ptr(y))
+        ctx.save_for_backward(x, W, mask)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W, mask = ctx.saved_tensors
+        M, K = x.shape
+        N = W.shape[0]
+        gy = _c(gy)
+        if mask is not None:
+            gm = _new(gy, M, N)
+            _call("gb_resmask", _ptr(gy), None, _ptr(mask), M, N, _ptr(gm))
+            gy = gm
+        gx = _new(gy, M, K)
+        _gemm(1, M, K, N, gy, N, W, K, gx, K)
+        gW = _new(gy, N, K)
+        _gemm(2, N, K, M, gy, N, x, K, gW, K)
+        gb = _colsum(gy, M, N) if ctx.has_bias else None
+        return gx, gW, gb, None
+
+
+class _Geometry(torch.autograd.Function):
+    """coord2diff (egnn_new.py:394-400) on the compacted edges: r [E], u [E,3]."""
+
+    @staticmethod
+    def forward(ctx, x, g, norm_constant):
+        x = _c(x)
+        E = g.topo.n_edges
+        r, u = _new(x, E), _new(x, E, 3)
+        _call("gb_geom_fwd", g.handle, _ptr(x), _F(norm_constant), _ptr(r), _ptr(u))
+        ctx.save_for_backward(x)
+        ctx.g, ctx.c = g, norm_constant
+        return r, u
+
+    @staticmethod
+    def backward(ctx, g_r, g_u):
+        (x,) = ctx.saved_tensors
+        E = ctx.g.topo.n_edges
+        g_r = None if g_r is None else _c(g_r)
+        g_u = None if g_u is None else _c(g_u)
+        scratch, gx = _new(x, E, 3), torch.empty_like(x)
+        _call("gb_geom_bwd", ctx.g.handle, _ptr(x), _F(ctx.c), _ptr(g_r), _ptr(g_u), _ptr(scratch), _ptr(gx))
+        return gx, None, None
+
+
+class _EdgeMLP(torch.autograd.Function):
+    """m = SiLU(W2 SiLU(W1 [h_i, h_j, r, d0] + b1) + b2) per edge (edge_mlp of GCL, egnn_new.py:43-47, and the first
+    two layers of coord_mlp, :110-117).  The first Linear is factorised into per-node projections."""
+
+    @staticmethod
+    def forward(ctx, h, r, d0, W1, b1, W2, b2, g):
+        h, W1, W2 = _c(h), _c(W1), _c(W2)
+        n, H = h.shape
+        E, ld1 = g.topo.n_edges, W1.shape[1]
+        Pa, Pb = _new(h, n, H), _new(h, n, H)
+        _gemm(0, n, H, H, h, H, W1, ld1, Pa, H, b1)
+        _gemm(0, n, H, H, h, H, W1[:, H:], ld1, Pb, H)
+        wr, wd = W1[:, 2 * H].contiguous(), W1[:, 2 * H + 1].contiguous()
+        pre1, s1 = _new(h, E, H), _new(h, E, H)
+        _call("gb_edge_pre", g.handle, _ptr(Pa), _ptr(Pb), _ptr(r), _ptr(d0), _ptr(wr), _ptr(wd), H, _ptr(pre1))
+        _call("gb_silu_fwd", _ptr(pre1), _ptr(s1), E * H)
+        pre2 = _new(h, E, H)
+        _gemm(0, E, H, H, s1, H, W2, H, pre2, H, b2)
+        m = s1                                                         # reuse the buffer: s1 is recomputed in backward
+        _call("gb_silu_fwd", _ptr(pre2), _ptr(m), E * H)
+        ctx.save_for_backward(h, r, d0, W1, W2, pre1, pre2)
+        ctx.g = g
+        return m
+
+    @staticmethod
+    def backward(ctx, g_m):
+        h, r, d0, W1, W2, pre1, pre2 = ctx.saved_tensors
+        g = ctx.g
+        n, H = h.shape
+        E, ld1 = g.topo.n_edges, W1.shape[1]
+        g_m = _c(g_m)
+        G2 = _new(h, E, H)
+        _call("gb_silu_bwd", _ptr(pre2), _ptr(g_m), _ptr(G2), E * H)
+        s1 = _new(h, E, H)
+        _call("gb_silu_fwd", _ptr(pre1), _ptr(s1), E * H)
+        gW2 = _new(h, H, H)
+        _gemm(2, H, H, E, G2, H, s1, H, gW2, H)
+        gb2 = _colsum(G2, E, H)
+        G1 = s1                                                        # s1 is dead after the wgrad
+        _gemm(1, E, H, H, G2, H, W2, H, G1, H)
+        _call("gb_silu_bwd", _ptr(pre1), _ptr(G1), _ptr(G1), E * H)
+        gPa, gPb = _new(h, n, H), _new(h, n, H)
+        _call("gb_rowcol_reduce", g.handle, _ptr(G1), H, _F(1.0), _ptr(gPa), _ptr(gPb))
+        gW1 = _new(h, H, ld1)
+        _gemm(2, H, H, n, gPa, H, h, H, gW1, ld1)
+        _gemm(2, H, H, n, gPb, H, h, H, gW1[:, H:], ld1)
+        gW1[:, 2 * H].copy_(_colsum(G1, E, H, r))
+        gW1[:, 2 * H + 1].copy_(_colsum(G1, E, H, d0))
+        gb1 = _colsum(gPa, n, H)
+        gh = _new(h, n, H)
+        _gemm(1, n, H, H, gPa, H, W1, ld1, gh, H)
+        _gemm(1, n, H, H, gPb, H, W1[:, H:], ld1, gh, H, acc=True)
+        g_r = _new(h, E)
+        wr = W1[:, 2 * H].contiguous()
+        _call("gb_rowdot", _ptr(G1), H, E, H, _ptr(wr), None, _ptr(g_r))
+        return gh, g_r, None, gW1, gb1, gW2, gb2, None
+
+
+class _AttAgg(torch.autograd.Function):
+    """agg_i = sum_{j} m_ij * sigmoid(w_a . m_ij + b_a) / normalization_factor (egnn_new.py:49-56, 58-66, 403-419)."""
+
+    @staticmethod
+    def forward(ctx, m, wa, ba, g, normf):
+        m = _c(m)
+        E, H = m.shape
+        n = g.topo.B * g.topo.N
+        agg = _new(m, n, H)
+        if wa is None:
+            _call("gb_rowcol_reduce", g.handle, _ptr(m), H, _F(1.0 / normf), _ptr(agg), None)
+            ctx.save_for_backward(m)
+        else:
+            wv = _c(wa.reshape(-1))
+            logit, gate, ef = _new(m, E), _new(m, E), _new(m, E, H)
+            _call("gb_rowdot", _ptr(m), H, E, H, _ptr(wv), _ptr(ba), _ptr(logit))
+            _call("gb_gate_fwd", _ptr(m), _ptr(logit), E, H, _ptr(ef), _ptr(gate))
+            _call("gb_rowcol_reduce", g.handle, _ptr(ef), H, _F(1.0 / normf), _ptr(agg), None)
+            ctx.save_for_backward(m, wv, gate)
+        ctx.g, ctx.normf, ctx.att = g, normf, wa is not None
+        return agg
+
+    @staticmethod
+    def backward(ctx, g_agg):
+        g = ctx.g
+        g_agg = _c(g_agg)
+        if not ctx.att:
+            (m,) = ctx.saved_tensors
+            E, H = m.shape
+            gm = _new(m, E, H)
+            _call("gb_gather_rows", g.handle, _ptr(g_agg), H, _F(1.0 / ctx.normf), _ptr(gm))
+            return gm, None, None, None, None
+        m, wv, gate = ctx.saved_tensors
+        E, H = m.shape
+        g_ef = _new(m, E, H)
+        _call("gb_gather_rows", g.handle, _ptr(g_agg), H, _F(1.0 / ctx.normf), _ptr(g_ef))
+        gm, coef = _new(m, E, H), _new(m, E)
+        _call("gb_gate_bwd", _ptr(m), _ptr(gate), _ptr(wv), _ptr(g_ef), E, H, _ptr(gm), _ptr(coef))
+        gwa = _colsum(m, E, H, coef).reshape(1, H)
+        gba = _colsum(coef, E, 1)
+        return gm, gwa, gba, None, None
+
+
+class _NodeMLP(torch.autograd.Function):
+    """h' = (h + W4 SiLU(W3 [h, agg] + b3) + b4) * mask (node_model, egnn_new.py:58-73, and the mask of :87-88)."""
+
+    @staticmethod
+    def forward(ctx, h, agg, W3, b3, W4, b4, mask):
+        h, agg, W3, W4 = _c(h), _c(agg), _c(W3), _c(W4)
+        n, H = h.shape
+        pre = _new(h, n, H)
+        _gemm(0, n, H, H, h, H, W3, 2 * H, pre, H, b3)
+        _gemm(0, n, H, H, agg, H, W3[:, H:], 2 * H, pre, H, acc=True)
+        sn = _new(h, n, H)
+        _call("gb_silu_fwd", _ptr(pre), _ptr(sn), n * H)
+        out = _new(h, n, H)
+        _gemm(0, n, H, H, sn, H, W4, H, out, H, b4)
+        _call("gb_resmask", _ptr(out), _ptr(h), _ptr(mask), n, H, _ptr(out))
+        ctx.save_for_backward(h, agg, W3, W4, pre, sn, mask)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        h, agg, W3, W4, pre, sn, mask = ctx.saved_tensors
+        n, H = h.shape
+        gt = _new(h, n, H)
+        _call("gb_resmask", _ptr(_c(g_out)), None, _ptr(mask), n, H, _ptr(gt))
+        gW4 = _new(h, H, H)
+        _gemm(2, H, H, n, gt, H, sn, H, gW4, H)
+        gb4 = _colsum(gt, n, H)
+        gpre = _new(h, n, H)
+        _gemm(1, n, H, H, gt, H, W4, H, gpre, H)
+        _call("gb_silu_bwd", _ptr(pre), _ptr(gpre), _ptr(gpre), n * H)
+        gW3 = _new(h, H, 2 * H)
+        _gemm(2, H, H, n, gpre, H, h, H, gW3, 2 * H)
+        _gemm(2, H, H, n, gpre, H, agg, H, gW3[:, H:], 2 * H)
+        gb3 = _colsum(gpre, n, H)
+        gh = gt                                                        # residual branch, then += gpre W3[:, :H]
+        _gemm(1, n, H, H, gpre, H, W3, 2 * H, gh, H, acc=True)
+        gagg = _new(h, n, H)
+        _gemm(1, n, H, H, gpre, H, W3[:, H:], 2 * H, gagg, H)
+        return gh, gagg, gW3, gb3, gW4, gb4, None
+
+
+class _CoordUpdate(torch.autograd.Function):
+    """x' = (x + sum_j u_ij * tanh(w7 . c_ij) * range / normalization_factor) * mask (egnn_new.py:122-155)."""
+
+    @staticmethod
+    def forward(ctx, x, u, c2, w7, g, rng, use_tanh, normf):
+        x, u, c2 = _c(x), _c(u), _c(c2)
+        E, H = c2.shape
+        wv = _c(w7.reshape(-1))
+        phi, tau, xo = _new(x, E), _new(x, E), torch.empty_like(x)
+        _call("gb_rowdot", _ptr(c2), H, E, H, _ptr(wv), None, _ptr(phi))
+        _call("gb_coord_fwd", g.handle, _ptr(x), _ptr(u), _ptr(phi), _F(rng), int(use_tanh), _F(normf), _ptr(xo), _ptr(tau))
+        ctx.save_for_backward(u, c2, wv, tau)
+        ctx.g, ctx.cfg = g, (rng, use_tanh, normf)
+        return xo
+
+    @staticmethod
+    def backward(ctx, g_xo):
+        u, c2, wv, tau = ctx.saved_tensors
+        g = ctx.g
+        rng, use_tanh, normf = ctx.cfg
+        E, H = c2.shape
+        g_xo = _c(g_xo)
+        g_phi, g_u, g_x = _new(u, E), _new(u, E, 3), torch.empty_like(g_xo)
+        _call("gb_coord_bwd", g.handle, _ptr(u), _ptr(tau), _ptr(g_xo), _F(rng), int(use_tanh), _F(normf), _ptr(g_phi), _ptr(g_u),
+              _ptr(g_x))
+        g_c2 = _new(u, E, H)
+        _call("gb_outer_dsilu", _ptr(g_phi), _ptr(wv), None, _ptr(g_c2), E, H)
+        g_w7 = _colsum(c2, E, H, g_phi).reshape(1, H)
+        return g_x, g_u, g_c2, g_w7, None, None, None, None
+
+
+class _DenFinish(torch.autograd.Function):
+    """eps = [remove_mean((x_fin - x_in) * mask), h3[:, :F]] (edm/egnn/models.py:116-152)."""
+
+    @staticmethod
+    def forward(ctx, x_fin, h3, x_in, mask, B, N, F):
+        eps = _new(x_fin, B, N, 3 + F)
+        _call("gb_den_finish_fwd", _ptr(_c(x_fin)), _ptr(x_in), _ptr(_c(h3)), _ptr(mask), B, N, F, _ptr(eps))
+        ctx.save_for_backward(mask)
+        ctx.dims = (B, N, F)
+        return eps
+
+    @staticmethod
+    def backward(ctx, g_eps):
+        (mask,) = ctx.saved_tensors
+        B, N, F = ctx.dims
+        gx, gh = _new(mask, B * N, 3), _new(mask, B * N, F + 1)
+        _call("gb_den_finish_bwd", _ptr(_c(g_eps)), _ptr(mask), B, N, F, _ptr(gx), _ptr(gh))
+        return gx, gh, None, None, None, None, None
+
+
+class _TrainLoss(torch.autograd.Function):
+    """loss [B] of compute_loss(t0_always=False) in train mode with loss_type 'l2' (en_diffusion.py:644-775)."""
+
+    @staticmethod
+    def forward(ctx, net, eps, zt, xh, mask, t_int, gamma_t, gamma_T, norm_h, bias_h):
+        B, N, D = net.shape
+        loss, g_net = _new(net, B), torch.empty_like(net)
+        _call("gb_train_loss", _ptr(_c(net)), _ptr(eps), _ptr(zt), _ptr(xh), _ptr(mask), _ptr(t_int), _ptr(gamma_t), _F(gamma_T),
+              _F(norm_h), _F(bias_h), B, N, D - 3, _ptr(loss), _ptr(g_net))
+        ctx.save_for_backward(g_net)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        (g_net,) = ctx.saved_tensors
+        B, N, D = g_net.shape
+        out = torch.empty_like(g_net)
+        _call("gb_resmask", _ptr(g_net), None, _ptr(_c(g_loss)), B, N * D, _ptr(out))
+        return (out,) + (None,) * 9
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def denoiser_forward_train(dyn, t: torch.Tensor, xh: torch.Tensor, node_mask: torch.Tensor, edge_mask: torch.Tensor) -> torch.Tensor:
+    """Differentiable (w.r.t. the parameters) ``EGNN_dynamics._forward`` (edm/egnn/models.py:76-152)."""
+    _need_cuda(xh, "xh")
+    B, N, D = xh.shape
+    F = D - 3
+    egnn, hy = dyn.egnn, dyn.hyper
+    if getattr(egnn, "sin_embedding", None) is not None:
+        raise NotImplementedError("sin_embedding is not implemented")
+    g = graph_for(node_mask, edge_mask, B, N)
+    mask = g.topo.node_mask                                            # [n] fp32
+    n = B * N
+    z = xh.detach().to(torch.float32).reshape(n, D)
+    x_in = _new(z, n, 3)
+    _call("gb_resmask", _ptr(_c(z[:, :3])), None, _ptr(mask), n, 3, _ptr(x_in))
+    hf = _new(z, n, F)
+    _call("gb_resmask", _ptr(_c(z[:, 3:])), None, _ptr(mask), n, F, _ptr(hf))
+    tt = torch.as_tensor(t, dtype=torch.float32, device=z.device).reshape(-1)
+    tcol = (tt.expand(B) if tt.numel() == 1 else tt).reshape(B, 1).expand(B, N).reshape(n, 1)
+    h = _Linear.apply(torch.cat([hf, tcol], dim=1), egnn.embedding.weight, egnn.embedding.bias, None)
+    d0 = _new(z, g.topo.n_edges)
+    _call("gb_geom_fwd", g.handle, _ptr(x_in), _F(1.0), _ptr(d0), None)  # egnn_new.py:301: the EGNN-level radial uses norm_constant 1
+    x = x_in
+    normf = hy["normalization_factor"]
+    for b in range(egnn.n_layers):
+        blk = getattr(egnn, f"e_block_{b}")
+        r, u = _Geometry.apply(x, g, float(blk.norm_constant))
+        for s in range(blk.n_layers):
+            gcl = getattr(blk, f"gcl_{s}")
+            m = _EdgeMLP.apply(h, r, d0, gcl.edge_mlp[0].weight, gcl.edge_mlp[0].bias, gcl.edge_mlp[2].weight,
+                               gcl.edge_mlp[2].bias, g)
+            wa, ba = (gcl.att_mlp[0].weight, gcl.att_mlp[0].bias) if gcl.attention else (None, None)
+            agg = _AttAgg.apply(m, wa, ba, g, float(normf))
+            h = _NodeMLP.apply(h, agg, gcl.node_mlp[0].weight, gcl.node_mlp[0].bias, gcl.node_mlp[2].weight,
+                               gcl.node_mlp[2].bias, mask)
+        eq = blk.gcl_equiv
+        c2 = _EdgeMLP.apply(h, r, d0, eq.coord_mlp[0].weight, eq.coord_mlp[0].bias, eq.coord_mlp[2].weight,
+                            eq.coord_mlp[2].bias, g)
+        x = _CoordUpdate.apply(x, u, c2, eq.coord_mlp[4].weight, g, float(eq.coords_range), bool(eq.tanh), float(normf))
+    h3 = _Linear.apply(h, egnn.embedding_out.weight, egnn.embedding_out.bias, mask)
+    return _DenFinish.apply(x, h3, x_in, mask, B, N, F)
+
+
+def training_loss(model, x, h, node_mask, edge_mask, t_int: Optional[torch.Tensor] = None,
+                  eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``EnVariationalDiffusion.forward`` in train mode with loss_type 'l2' and include_charges False: loss [B].
+
+    ``t_int`` [B,1] / ``eps`` [B,N,D] may be injected (tests); otherwise they are drawn like the reference does
+    (torch.randint, en_diffusion.py:657-659; centre-of-gravity-free Gaussian noise, :677-679)."""
+    _need_cuda(x, "x")
+    if model.loss_type != "l2" or model.include_charges:
+        raise NotImplementedError("the training step implements loss_type 'l2' without charges (the args_edm defaults)")
+    B, N, _ = x.shape
+    F = model.in_node_nf
+    dev = x.device
+    h_cat = h["categorical"] if isinstance(h, dict) else h
+    if t_int is None:
+        t_int = torch.randint(0, model.T + 1, size=(B, 1), device=dev)
+    t_f = t_int.to(torch.float32).reshape(B).contiguous()
+    g = graph_for(node_mask, edge_mask, B, N)
+    mask = g.topo.node_mask
+    if eps is None:
+        eps = model.sample_combined_position_feature_noise(B, N, node_mask)
+    eps = _c(eps.to(torch.float32))
+    gamma = model.gamma.gamma.detach().to(torch.float32).contiguous()
+    xh, zt, gamma_t = _new(eps, B, N, 3 + F), _new(eps, B, N, 3 + F), _new(eps, B)
+    _call("gb_make_zt", _ptr(_c(x.to(torch.float32))), _ptr(_c(h_cat.to(torch.float32))), _ptr(mask), _ptr(eps), _ptr(gamma), _ptr(t_f),
+          _F(model.norm_values[0]), _F(model.norm_values[1]), _F(model.norm_biases[1]), B, N, F, _ptr(xh), _ptr(zt), _ptr(gamma_t))
+    net = denoiser_forward_train(model.dynamics, t_f / model.T, zt, node_mask, edge_mask)
+    return _TrainLoss.apply(net, eps, zt, xh, mask, t_f, gamma_t, model._gamma_T(), float(model.norm_values[1]),
+                            float(model.norm_biases[1]))

@@ -154,7 +154,7 @@ int gb_pred_egnn_forward(const gb_net* net, const gb_graph* g, const float* h_in
  * gb_gemm        mode 0: C[M,N] = A[M,K] B[N,K]^T (+bias[N])   1: C = A[M,K] B[K,N]   2: C = A[K,M]^T B[K,N];
  *                accumulate != 0 adds into C.  (nn.Linear forward / dgrad / wgrad)
  * gb_colsum      out[k] (+)= sum_m w[m] X[m][k]   (w NULL: 1)      bias and weight-column gradients
- * gb_rowdot      out[m] = bias + X[m,:] . v                         att_mlp logit / coord_mlp last layer / dL/dr
+ * gb_rowdot      out[m] = bias[0] + X[m,:] . v (bias: device scalar or NULL)                       att_mlp logit / coord_mlp last layer / dL/dr
  * gb_silu_*      SiLU and its backward;  gb_outer_dsilu: G[m][k] = s[m] v[k] SiLU'(pre[m][k])
  * gb_edge_pre    pre[e] = Pa[row_e] + Pb[col_e] + wr r_e + wd d0_e   (first edge Linear, factorised; egnn_new.py:43-47)
  * gb_rowcol_reduce  out_row[i] = scale * sum_{e: row_e = i} G[e], out_col[j] = scale * sum_{e: col_e = j} G[e]
@@ -170,7 +170,7 @@ int gb_pred_egnn_forward(const gb_net* net, const gb_graph* g, const float* h_in
 int gb_gemm(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
             const float* bias, int accumulate, void* stream);
 int gb_colsum(const float* X, int ld, int M, int N, const float* w, float* out, int accumulate, void* stream);
-int gb_rowdot(const float* X, int ld, int M, int N, const float* v, float bias, float* out, void* stream);
+int gb_rowdot(const float* X, int ld, int M, int N, const float* v, const float* bias, float* out, void* stream);
 int gb_silu_fwd(const float* x, float* y, size_t n, void* stream);
 int gb_silu_bwd(const float* x, const float* gy, float* gx, size_t n, void* stream);
 int gb_outer_dsilu(const float* s_row, const float* v, const float* pre, float* G, int M, int N, void* stream);
@@ -191,6 +191,13 @@ int gb_coord_bwd(const gb_graph* g, const float* u, const float* tau, const floa
 int gb_resmask(const float* a, const float* b, const float* mask, int M, int N, float* out, void* stream);
 int gb_den_finish_bwd(const float* g_eps, const float* mask, int B, int N, int F, float* g_xfin, float* g_h3,
                       void* stream);
+ /* gb_den_finish_fwd: eps [B,N,3+F] from x_fin/x_in [n,3], h3 [n,F+1].  gb_make_zt: normalize (en_diffusion.py:384-404) and
+  * z_t = alpha_t xh + sigma_t eps (:661-685); gamma [T+1] schedule table, writes xh, zt [B,N,3+F] and gamma_t [B]. */
+int gb_den_finish_fwd(const float* x_fin, const float* x_in, const float* h3, const float* mask, int B, int N, int F,
+                      float* eps, void* stream);
+int gb_make_zt(const float* x, const float* h, const float* mask, const float* eps, const float* gamma,
+               const float* t_int, float norm_x, float norm_h, float bias_h, int B, int N, int F, float* xh, float* zt,
+               float* gamma_t, void* stream);
 int gb_train_loss(const float* net, const float* eps, const float* zt, const float* xh, const float* mask,
                   const float* t_int, const float* gamma_t, float gamma_T, float norm_h, float bias_h, int B, int N,
                   int F, float* loss, float* g_net, void* stream);
