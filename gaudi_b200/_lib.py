@@ -52,13 +52,15 @@ SIGNATURES = {
     "gb_pred_layer_forward": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "gb_pred_egnn_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     # training step ops
+    "gb_linear_scratch_bytes": (_SZ, [_I, _I, _I]),
+    "gb_linear": (_I, [_I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "gb_gemm": (_I, [_I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P]),
     "gb_colsum": (_I, [_P, _I, _I, _I, _P, _P, _I, _P]),
     "gb_rowdot": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "gb_silu_fwd": (_I, [_P, _P, _SZ, _P]),
     "gb_silu_bwd": (_I, [_P, _P, _P, _SZ, _P]),
     "gb_outer_dsilu": (_I, [_P, _P, _P, _P, _I, _I, _P]),
-    "gb_edge_pre": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
+    "gb_edge_pre": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
     "gb_rowcol_reduce": (_I, [_P, _P, _I, _F, _P, _P, _P]),
     "gb_gather_rows": (_I, [_P, _P, _I, _F, _P, _P]),
     "gb_gate_fwd": (_I, [_P, _P, _I, _I, _P, _P, _P]),

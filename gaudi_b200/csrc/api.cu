@@ -889,6 +889,41 @@ extern "C" int gb_sample_loop(const gb_net* den, const gb_net* pred, const gb_gr
 //          2 predictor edge forward (saving), 3 predictor edge backward, 4 node MLP first Linear (predictor
 //          workspace after gb_predictor_forward(save)+gb_predictor_input_grad)
 // ------------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------------
+// training step: one Linear on the tcgen05 path (weights are re-packed on every call: they change every step)
+// ------------------------------------------------------------------------------------------------------
+extern "C" size_t gb_linear_scratch_bytes(int N, int K1, int K2) {
+    return (size_t)((K1 + 31) / 32 + (K2 + 31) / 32) * 2 * tc_np(N) * 32 * sizeof(float);
+}
+extern "C" int gb_linear(int M, int N, int K1, int K2, const float* A1, int lda1, const float* A2, int lda2, const float* W,
+                         int ldw, int transpose_w, const float* bias, int epi, float* out, float* out2, const float* res_or_aux,
+                         const float* mask, void* wimg, size_t wimg_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (M <= 0) return 0;
+    if (N > 256 || (N & 3) || (K1 & 3) || (K2 & 3) || (lda1 & 3) || (K2 && (lda2 & 3)))
+        return fail("gb_linear: needs N <= 256 and N, K1, K2, lda multiples of 4 (got N=%d K1=%d K2=%d)", N, K1, K2);
+    if (K2 && transpose_w) return fail("gb_linear: a K-concatenated input is only supported with transpose_w = 0");
+    if (wimg_bytes < gb_linear_scratch_bytes(N, K1, K2)) return fail("gb_linear: scratch too small");
+    const int NP = tc_np(N), na1 = (K1 + 31) / 32, na2 = (K2 + 31) / 32;
+    float* img = (float*)wimg;
+    launch_pack_tc(img, W, ldw, 0, 0, K1, N, NP, na1, transpose_w, s);
+    if (K2) launch_pack_tc(img + (size_t)na1 * 2 * NP * 32, W, ldw, K1, 0, K2, N, NP, na2, 0, s);
+    LinArgs a{};
+    a.A1 = A1; a.lda1 = lda1; a.K1 = K1; a.A2 = A2; a.lda2 = lda2; a.K2 = K2;
+    a.bias = bias; a.out = out; a.ldo = N; a.out2 = out2; a.ldo2 = N; a.M = M; a.ncb = 1; a.res_cb = -1;
+    switch (epi) {
+        case 0: a.epi = EPI_BIAS; break;
+        case 1: a.epi = EPI_SILU; break;
+        case 2: a.epi = EPI_RES_MASK; a.res = res_or_aux; a.ldr = N; a.mask = mask; break;
+        case 3: a.epi = EPI_MUL_DSILU; a.aux = res_or_aux; a.ldaux = N; break;
+        case 4: a.epi = EPI_ADD_RES; a.res = res_or_aux; a.ldr = N; break;
+        default: return fail("gb_linear: unknown epilogue %d", epi);
+    }
+    launch_lin_tc(N, a, img, s);
+    GB_LAUNCHED(K2 ? 3 : 2);
+    return check_launch("gb_linear");
+}
+
 extern "C" int gb_profile_kernel(const gb_net* n, const gb_graph* gg, int which, int layer, void* ws, size_t ws_bytes,
                                  int repeats, void* stream) {
     if (!n || !gg || !ws) return fail("null argument");

@@ -80,7 +80,19 @@ __global__ void colsum_kernel(const float* __restrict__ X, int ld, int M, int N,
     const int col = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
     float s = 0.f;
     if (col < N)
-        for (int m = slice + 8 * blockIdx.y; m < M; m += 8 * gridDim.y) s += (w ? w[m] : 1.f) * X[(size_t)m * ld + col];
+    {
+        const int step = 8 * gridDim.y;
+        int m = slice + 8 * blockIdx.y;
+        float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        for (; m + 3 * step < M; m += 4 * step) {
+            s += (w ? w[m] : 1.f) * X[(size_t)m * ld + col];
+            s1 += (w ? w[m + step] : 1.f) * X[(size_t)(m + step) * ld + col];
+            s2 += (w ? w[m + 2 * step] : 1.f) * X[(size_t)(m + 2 * step) * ld + col];
+            s3 += (w ? w[m + 3 * step] : 1.f) * X[(size_t)(m + 3 * step) * ld + col];
+        }
+        for (; m < M; m += step) s += (w ? w[m] : 1.f) * X[(size_t)m * ld + col];
+        s += s1 + s2 + s3;
+    }
     red[slice][threadIdx.x & 31] = s;
     __syncthreads();
     if (slice == 0 && col < N) {
@@ -125,11 +137,13 @@ __global__ void outer_dsilu_kernel(const float* __restrict__ s, const float* __r
 // pre[e][k] = Pa[row_e][k] + Pb[col_e][k] + wr[k] r_e + wd[k] d0_e      (GCL.edge_model / coord_model input, factorised)
 __global__ void edge_pre_kernel(Graph g, const float* __restrict__ Pa, const float* __restrict__ Pb, const float* __restrict__ r,
                                 const float* __restrict__ d0, const float* __restrict__ wr, const float* __restrict__ wd,
-                                int H, float* __restrict__ pre) {
+                                int H, float* __restrict__ pre, float* __restrict__ act) {
     const size_t n = (size_t)g.n_edges * H;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int e = (int)(i / H), k = (int)(i % H);
-        pre[i] = Pa[(size_t)g.erow[e] * H + k] + Pb[(size_t)g.ecol[e] * H + k] + wr[k] * r[e] + wd[k] * d0[e];
+        const float v = Pa[(size_t)g.erow[e] * H + k] + Pb[(size_t)g.ecol[e] * H + k] + wr[k] * r[e] + wd[k] * d0[e];
+        pre[i] = v;
+        if (act) act[i] = silu_f(v);
     }
 }
 
@@ -414,8 +428,14 @@ extern "C" int gb_gemm(int mode, int M, int N, int K, const float* A, int lda, c
                        const float* bias, int accumulate, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (M <= 0 || N <= 0) return 0;
+    // wgrad: the output is small (hidden x hidden) and the reduction runs over every edge, so the parallelism has to come
+    // from splitting K: ~6 resident CTAs per SM hide the global-load latency of the unpipelined tile loop.
     int splits = 1;
-    if (mode == 2 && K > 4096) { splits = (K + 4095) / 4096; if (splits > 32) splits = 32; }
+    if (mode == 2 && K > 1024) {
+        const int tiles = ((N + 63) / 64) * ((M + 63) / 64);
+        splits = (148 * 6 + tiles - 1) / tiles;
+        if (splits > (K + 255) / 256) splits = (K + 255) / 256;
+    }
     const int kps = ((K + splits - 1) / splits + 15) / 16 * 16;
     if (splits > 1 && !accumulate) cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, s);
     dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
@@ -426,7 +446,8 @@ extern "C" int gb_gemm(int mode, int M, int N, int K, const float* A, int lda, c
 }
 extern "C" int gb_colsum(const float* X, int ld, int M, int N, const float* w, float* out, int accumulate, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    int gy = M > 8192 ? 16 : 1;
+    int gy = M > 2048 ? (M + 255) / 256 : 1;           // enough row slices to fill the machine; partials meet in atomics
+    if (gy > 256) gy = 256;
     if (gy > 1 && !accumulate) cudaMemsetAsync(out, 0, (size_t)N * 4, s);
     colsum_kernel<<<dim3((N + 31) / 32, gy), 256, 0, s>>>(X, ld, M, N, w, out, accumulate);
     TR_CHECK("colsum");
@@ -448,8 +469,8 @@ extern "C" int gb_outer_dsilu(const float* s_row, const float* v, const float* p
     TR_CHECK("outer_dsilu");
 }
 extern "C" int gb_edge_pre(const gb_graph* g, const float* Pa, const float* Pb, const float* r, const float* d0, const float* wr,
-                           const float* wd, int H, float* pre, void* stream) {
-    edge_pre_kernel<<<ew_blocks((size_t)g->g.n_edges * H), 256, 0, (cudaStream_t)stream>>>(g->g, Pa, Pb, r, d0, wr, wd, H, pre);
+                           const float* wd, int H, float* pre, float* act, void* stream) {
+    edge_pre_kernel<<<ew_blocks((size_t)g->g.n_edges * H), 256, 0, (cudaStream_t)stream>>>(g->g, Pa, Pb, r, d0, wr, wd, H, pre, act);
     TR_CHECK("edge_pre");
 }
 extern "C" int gb_rowcol_reduce(const gb_graph* g, const float* G, int H, float scale, float* out_row, float* out_col, void* stream) {

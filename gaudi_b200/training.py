@@ -13,6 +13,7 @@ that also produces the weight gradients.  ``torch.autograd.Function`` only chain
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -43,6 +44,42 @@ def _colsum(X, M: int, N: int, w=None) -> torch.Tensor:
 
 def _new(ref: torch.Tensor, *shape) -> torch.Tensor:
     return torch.empty(*shape, dtype=torch.float32, device=ref.device)
+
+
+# GAUDI_B200_TRAIN_GEMM=fp32 keeps every Linear on the FP32 CUDA-core GEMM (gb_gemm); the default runs the hidden-width
+# Linears (forward and dgrad) on the sampler's tcgen05 / 3xTF32 node-Linear kernel with its fused epilogues (gb_linear).
+_TC = os.environ.get("GAUDI_B200_TRAIN_GEMM", "tc") != "fp32"
+_scratch = {}
+EPI_NONE, EPI_SILU, EPI_RES_MASK, EPI_MUL_DSILU, EPI_ADD = 0, 1, 2, 3, 4
+
+
+def _linear(A1, W, K1, N, bias=None, A2=None, K2=0, transpose=False, epi=EPI_NONE, out2=None, aux=None, mask=None):
+    """out = epi([A1 | A2] op(W) + bias); W may be a column/row view of a Linear weight (row stride W.stride(0))."""
+    M, ldw = A1.shape[0], W.stride(0)
+    out = _new(A1, M, N)
+    if _TC and N <= 256 and N % 4 == 0 and K1 % 4 == 0 and K2 % 4 == 0:
+        L = _lib.lib()
+        nbytes = L.gb_linear_scratch_bytes(N, K1, K2)
+        key = A1.device.index
+        if key not in _scratch or _scratch[key].numel() < nbytes:
+            _scratch[key] = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=A1.device)
+        _call("gb_linear", M, N, K1, K2, _ptr(A1), A1.stride(0), _ptr(A2), 0 if A2 is None else A2.stride(0), _ptr(W), ldw,
+              int(transpose), _ptr(bias), epi, _ptr(out), _ptr(out2), _ptr(aux), _ptr(mask), _ptr(_scratch[key]), nbytes)
+        return out
+    if epi == EPI_ADD:
+        out.copy_(aux)
+    _gemm(1 if transpose else 0, M, N, K1, A1, A1.stride(0), W, ldw, out, N, bias, acc=epi == EPI_ADD)
+    if A2 is not None:
+        _gemm(0, M, N, K2, A2, A2.stride(0), W[:, K1:], ldw, out, N, acc=True)
+    if epi == EPI_SILU:
+        if out2 is not None:
+            out2.copy_(out)
+        _call("gb_silu_fwd", _ptr(out), _ptr(out), M * N)
+    elif epi == EPI_RES_MASK:
+        _call("gb_resmask", _ptr(out), _ptr(aux), _ptr(mask), M, N, _ptr(out))
+    elif epi == EPI_MUL_DSILU:
+        _call("gb_silu_bwd", _ptr(aux), _ptr(out), _ptr(out), M * N)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -112,19 +149,14 @@ class _EdgeMLP(torch.autograd.Function):
     def forward(ctx, h, r, d0, W1, b1, W2, b2, g):
         h, W1, W2 = _c(h), _c(W1), _c(W2)
         n, H = h.shape
-        E, ld1 = g.topo.n_edges, W1.shape[1]
-        Pa, Pb = _new(h, n, H), _new(h, n, H)
-        _gemm(0, n, H, H, h, H, W1, ld1, Pa, H, b1)
-        _gemm(0, n, H, H, h, H, W1[:, H:], ld1, Pb, H)
+        E = g.topo.n_edges
+        Pa = _linear(h, W1, H, H, b1)
+        Pb = _linear(h, W1[:, H:], H, H)
         wr, wd = W1[:, 2 * H].contiguous(), W1[:, 2 * H + 1].contiguous()
-        pre1, s1 = _new(h, E, H), _new(h, E, H)
-        _call("gb_edge_pre", g.handle, _ptr(Pa), _ptr(Pb), _ptr(r), _ptr(d0), _ptr(wr), _ptr(wd), H, _ptr(pre1))
-        _call("gb_silu_fwd", _ptr(pre1), _ptr(s1), E * H)
-        pre2 = _new(h, E, H)
-        _gemm(0, E, H, H, s1, H, W2, H, pre2, H, b2)
-        m = s1                                                         # reuse the buffer: s1 is recomputed in backward
-        _call("gb_silu_fwd", _ptr(pre2), _ptr(m), E * H)
-        ctx.save_for_backward(h, r, d0, W1, W2, pre1, pre2)
+        pre1, s1, pre2 = _new(h, E, H), _new(h, E, H), _new(h, E, H)
+        _call("gb_edge_pre", g.handle, _ptr(Pa), _ptr(Pb), _ptr(r), _ptr(d0), _ptr(wr), _ptr(wd), H, _ptr(pre1), _ptr(s1))
+        m = _linear(s1, W2, H, H, b2, epi=EPI_SILU, out2=pre2)
+        ctx.save_for_backward(h, r, d0, W1, W2, pre1, pre2)     # SiLU(pre1) is recomputed in backward
         ctx.g = g
         return m
 
@@ -142,9 +174,8 @@ class _EdgeMLP(torch.autograd.Function):
         gW2 = _new(h, H, H)
         _gemm(2, H, H, E, G2, H, s1, H, gW2, H)
         gb2 = _colsum(G2, E, H)
-        G1 = s1                                                        # s1 is dead after the wgrad
-        _gemm(1, E, H, H, G2, H, W2, H, G1, H)
-        _call("gb_silu_bwd", _ptr(pre1), _ptr(G1), _ptr(G1), E * H)
+        del s1
+        G1 = _linear(G2, W2, H, H, transpose=True, epi=EPI_MUL_DSILU, aux=pre1)
         gPa, gPb = _new(h, n, H), _new(h, n, H)
         _call("gb_rowcol_reduce", g.handle, _ptr(G1), H, _F(1.0), _ptr(gPa), _ptr(gPb))
         gW1 = _new(h, H, ld1)
@@ -153,9 +184,8 @@ class _EdgeMLP(torch.autograd.Function):
         gW1[:, 2 * H].copy_(_colsum(G1, E, H, r))
         gW1[:, 2 * H + 1].copy_(_colsum(G1, E, H, d0))
         gb1 = _colsum(gPa, n, H)
-        gh = _new(h, n, H)
-        _gemm(1, n, H, H, gPa, H, W1, ld1, gh, H)
-        _gemm(1, n, H, H, gPb, H, W1[:, H:], ld1, gh, H, acc=True)
+        gh = _linear(gPa, W1, H, H, transpose=True)
+        gh = _linear(gPb, W1[:, H:], H, H, transpose=True, epi=EPI_ADD, aux=gh)
         g_r = _new(h, E)
         wr = W1[:, 2 * H].contiguous()
         _call("gb_rowdot", _ptr(G1), H, E, H, _ptr(wr), None, _ptr(g_r))
@@ -213,13 +243,8 @@ class _NodeMLP(torch.autograd.Function):
         h, agg, W3, W4 = _c(h), _c(agg), _c(W3), _c(W4)
         n, H = h.shape
         pre = _new(h, n, H)
-        _gemm(0, n, H, H, h, H, W3, 2 * H, pre, H, b3)
-        _gemm(0, n, H, H, agg, H, W3[:, H:], 2 * H, pre, H, acc=True)
-        sn = _new(h, n, H)
-        _call("gb_silu_fwd", _ptr(pre), _ptr(sn), n * H)
-        out = _new(h, n, H)
-        _gemm(0, n, H, H, sn, H, W4, H, out, H, b4)
-        _call("gb_resmask", _ptr(out), _ptr(h), _ptr(mask), n, H, _ptr(out))
+        sn = _linear(h, W3, H, H, b3, A2=agg, K2=H, epi=EPI_SILU, out2=pre)
+        out = _linear(sn, W4, H, H, b4, epi=EPI_RES_MASK, aux=h, mask=mask)
         ctx.save_for_backward(h, agg, W3, W4, pre, sn, mask)
         return out
 
@@ -232,17 +257,13 @@ class _NodeMLP(torch.autograd.Function):
         gW4 = _new(h, H, H)
         _gemm(2, H, H, n, gt, H, sn, H, gW4, H)
         gb4 = _colsum(gt, n, H)
-        gpre = _new(h, n, H)
-        _gemm(1, n, H, H, gt, H, W4, H, gpre, H)
-        _call("gb_silu_bwd", _ptr(pre), _ptr(gpre), _ptr(gpre), n * H)
+        gpre = _linear(gt, W4, H, H, transpose=True, epi=EPI_MUL_DSILU, aux=pre)
         gW3 = _new(h, H, 2 * H)
         _gemm(2, H, H, n, gpre, H, h, H, gW3, 2 * H)
         _gemm(2, H, H, n, gpre, H, agg, H, gW3[:, H:], 2 * H)
         gb3 = _colsum(gpre, n, H)
-        gh = gt                                                        # residual branch, then += gpre W3[:, :H]
-        _gemm(1, n, H, H, gpre, H, W3, 2 * H, gh, H, acc=True)
-        gagg = _new(h, n, H)
-        _gemm(1, n, H, H, gpre, H, W3[:, H:], 2 * H, gagg, H)
+        gh = _linear(gpre, W3, H, H, transpose=True, epi=EPI_ADD, aux=gt)      # residual branch + gpre W3[:, :H]
+        gagg = _linear(gpre, W3[:, H:], H, H, transpose=True)
         return gh, gagg, gW3, gb3, gW4, gb4, None
 
 

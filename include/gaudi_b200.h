@@ -156,7 +156,8 @@ int gb_pred_egnn_forward(const gb_net* net, const gb_graph* g, const float* h_in
  * gb_colsum      out[k] (+)= sum_m w[m] X[m][k]   (w NULL: 1)      bias and weight-column gradients
  * gb_rowdot      out[m] = bias[0] + X[m,:] . v (bias: device scalar or NULL)                       att_mlp logit / coord_mlp last layer / dL/dr
  * gb_silu_*      SiLU and its backward;  gb_outer_dsilu: G[m][k] = s[m] v[k] SiLU'(pre[m][k])
- * gb_edge_pre    pre[e] = Pa[row_e] + Pb[col_e] + wr r_e + wd d0_e   (first edge Linear, factorised; egnn_new.py:43-47)
+ * gb_edge_pre    pre[e] = Pa[row_e] + Pb[col_e] + wr r_e + wd d0_e, act = SiLU(pre) if non-NULL (first edge Linear,
+ *                factorised; egnn_new.py:43-47)
  * gb_rowcol_reduce  out_row[i] = scale * sum_{e: row_e = i} G[e], out_col[j] = scale * sum_{e: col_e = j} G[e]
  *                   (unsorted_segment_sum, egnn_new.py:403-419, and the backward of gb_edge_pre); either may be NULL
  * gb_gather_rows out[e] = scale * X[row_e]                          backward of the row segment sum
@@ -167,6 +168,14 @@ int gb_pred_egnn_forward(const gb_net* net, const gb_graph* g, const float* h_in
  * gb_den_finish_bwd  backward of the EGNN_dynamics tail (models.py:116-152): g_xfin [n,3], g_h3 [n,F+1]
  * gb_train_loss  loss[b] of compute_loss(t0_always = False), training mode, loss_type 'l2', include_charges = False,
  *                and g_net = d loss[b] / d net_out.  gamma_t [B], t_int [B] (as float). */
+ /* gb_linear: out[M,N] = epi([A1 | A2] op(W) + bias) on the tcgen05 (3xTF32) node-Linear kernel of the sampler; the weight
+  * image is re-packed into `wimg` (gb_linear_scratch_bytes) on every call.  transpose_w 0: op(W)[k][n] = W[n*ldw+k]
+  * (nn.Linear forward), 1: W[k*ldw+n] (dgrad).  epi 0: none; 1: SiLU, pre-activation also stored to out2 if non-NULL;
+  * 2: (res + y) * mask[row]; 3: y * SiLU'(aux); 4: y + res.  N <= 256; N, K1, K2, lda multiples of 4. */
+size_t gb_linear_scratch_bytes(int N, int K1, int K2);
+int gb_linear(int M, int N, int K1, int K2, const float* A1, int lda1, const float* A2, int lda2, const float* W, int ldw,
+              int transpose_w, const float* bias, int epi, float* out, float* out2, const float* res_or_aux,
+              const float* mask, void* wimg, size_t wimg_bytes, void* stream);
 int gb_gemm(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
             const float* bias, int accumulate, void* stream);
 int gb_colsum(const float* X, int ld, int M, int N, const float* w, float* out, int accumulate, void* stream);
@@ -175,7 +184,7 @@ int gb_silu_fwd(const float* x, float* y, size_t n, void* stream);
 int gb_silu_bwd(const float* x, const float* gy, float* gx, size_t n, void* stream);
 int gb_outer_dsilu(const float* s_row, const float* v, const float* pre, float* G, int M, int N, void* stream);
 int gb_edge_pre(const gb_graph* g, const float* Pa, const float* Pb, const float* r, const float* d0, const float* wr,
-                const float* wd, int H, float* pre, void* stream);
+                const float* wd, int H, float* pre, float* act, void* stream);
 int gb_rowcol_reduce(const gb_graph* g, const float* G, int H, float scale, float* out_row, float* out_col, void* stream);
 int gb_gather_rows(const gb_graph* g, const float* X, int H, float scale, float* out, void* stream);
 int gb_gate_fwd(const float* m, const float* logit, int E, int H, float* ef, float* gate, void* stream);

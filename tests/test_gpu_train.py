@@ -49,9 +49,42 @@ def test_gemm_modes_match_fp64(mode):
         assert maxabs(c2, ref2) <= 4e-5 * max(1.0, float(ref2.abs().max()))
 
 
-@pytest.mark.parametrize("ds", ["cata", "hetro"])
-def test_training_loss_and_gradients_match_reference_golden(ds):
+@pytest.mark.parametrize("epi", [0, 1, 2, 3, 4])
+def test_tensor_core_linear_matches_fp64(epi):
+    """gb_linear (tcgen05, 3xTF32) with every epilogue the training step uses, forward and dgrad orientation."""
     dev = _dev()
+    torch.manual_seed(epi)
+    for (M, N, K1, K2, tr) in [(1000, 192, 192, 0, False), (777, 192, 192, 192, False), (130, 64, 64, 0, True), (5000, 192, 192, 0, True)]:
+        a1, a2 = torch.randn(M, K1, device=dev), (torch.randn(M, K2, device=dev) if K2 else None)
+        Wfull = torch.randn(N + 5, K1 + K2 + 3, device=dev) if not tr else torch.randn(K1 + 2, N + 7, device=dev)
+        W = Wfull[:N, :K1 + K2] if not tr else Wfull[:K1, 3:3 + N]        # strided views, like W1[:, H:2H]
+        bias = torch.randn(N, device=dev)
+        aux, mask = torch.randn(M, N, device=dev), (torch.rand(M, device=dev) > 0.3).float()
+        out2 = torch.empty(M, N, device=dev) if epi == 1 else None
+        y = training._linear(a1, W, K1, N, bias, A2=a2, K2=K2, transpose=tr, epi=epi, out2=out2,
+                             aux=aux if epi in (2, 3, 4) else None, mask=mask if epi == 2 else None)
+        A = torch.cat([a1, a2], 1).double() if K2 else a1.double()
+        pre = A @ (W.double() if tr else W.double().T) + bias.double()
+        if epi == 1:
+            ref = torch.nn.functional.silu(pre)
+            assert maxabs(out2, pre) <= 2e-5 * float(pre.abs().max())
+        elif epi == 2:
+            ref = (aux.double() + pre) * mask.double()[:, None]
+        elif epi == 3:
+            sg = torch.sigmoid(aux.double())
+            ref = pre * (sg * (1 + aux.double() * (1 - sg)))
+        elif epi == 4:
+            ref = pre + aux.double()
+        else:
+            ref = pre
+        assert maxabs(y, ref) <= 2e-5 * max(1.0, float(ref.abs().max())), (epi, M, N, K1, K2, tr)
+
+
+@pytest.mark.parametrize("gemm", ["tc", "fp32"])
+@pytest.mark.parametrize("ds", ["cata", "hetro"])
+def test_training_loss_and_gradients_match_reference_golden(ds, gemm, monkeypatch):
+    dev = _dev()
+    monkeypatch.setattr(training, "_TC", gemm == "tc")
     g = golden(f"train_{ds}.npz")
     args, model = _train_model(ds, dev)
     nm, em = gb.build_masks(torch.from_numpy(g["nodesxsample"]), 11 if ds == "cata" else 10, ds == "hetro", device=dev)
@@ -78,7 +111,7 @@ def test_training_loss_and_gradients_match_reference_golden(ds):
             e = maxabs(params[k[5:]].grad, ref) / max(1.0, float(ref.abs().max()))
             worst_abs = max(worst_abs, e)
             assert e <= 1e-4, f"{k}: {e:.3e}"
-    print(f"[train parity {ds}] loss max-abs {maxabs(loss_b, g['loss_b']):.2e}, worst grad-norm rel {worst_rel:.2e}, "
+    print(f"[train parity {ds} {gemm}] loss max-abs {maxabs(loss_b, g['loss_b']):.2e}, worst grad-norm rel {worst_rel:.2e}, "
           f"worst full-tensor abs {worst_abs:.2e}")
 
 
