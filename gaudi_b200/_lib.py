@@ -73,6 +73,8 @@ SIGNATURES = {
     "gb_den_finish_bwd": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "gb_den_finish_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "gb_make_zt": (_I, [_P, _P, _P, _P, _P, _P, _F, _F, _F, _I, _I, _I, _P, _P, _P, _P]),
+    "gb_check_stability": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _F, _P, _P, _P, _F, _F, _I, _P, _P]),
+    "gb_positions2adj": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "gb_train_loss": (_I, [_P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _I, _I, _I, _P, _P, _P]),
 }
 

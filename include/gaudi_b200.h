@@ -211,6 +211,24 @@ int gb_train_loss(const float* net, const float* eps, const float* zt, const flo
                   const float* t_int, const float* gamma_t, float gamma_T, float norm_h, float bias_h, int B, int N,
                   int F, float* loss, float* g_net, void* stream);
 
+/* ---- geometric validity of generated ring graphs -----------------------------------------------
+ * gb_check_stability replaces the per-molecule Python of check_stability (analyze/analyze.py:50-100): positions2adj
+ * (utils/helpers.py:172-196), minimum-distance test, connectivity (networkx), find_triplets_quads / angel3 / angel4
+ * (analyze.py:234-318) and check_angels3 / check_angels4 (:19-47), one thread per molecule.
+ *   x [B,N,3] fp32, ring_type [B,N] int32, node_mask [B,N] fp32 (cat[m,m] layout when orientation_type >= 0)
+ *   pair_lo/pair_hi [n_types^2]: lo*(1-tol), hi*(1+tol) of the ring-pair distance table (+inf / -inf where absent)
+ *   a3_lo/a3_hi [n_types*4], a3_cnt [n_types] (-1: symbol absent): angle ranges per centre ring; a4_hi = a4["180"]*(1-tol),
+ *   a4_lo = a4["0"]*(1+tol); check_a4 = 1 for cata.
+ *   flags [B][8] uint8: orientation_nodes, dist_stable, connected, angels3, angels4, all-of-the-five, error bits
+ *   (1 no ring nodes, 2 more than 16 rings, 4 centre symbol missing from the angle table), number of rings.
+ * gb_positions2adj: dist, adj [B,N,N] fp32 exactly as positions2adj returns them (no mask argument there either). */
+int gb_check_stability(const float* x, const int* ring_type, const float* node_mask, int B, int N, int n_types,
+                       int orientation_type, const float* pair_lo, const float* pair_hi, float min_dist,
+                       const float* a3_lo, const float* a3_hi, const int* a3_cnt, float a4_hi, float a4_lo, int check_a4,
+                       unsigned char* flags, void* stream);
+int gb_positions2adj(const float* x, const int* ring_type, int B, int N, int n_types, const float* pair_lo,
+                     const float* pair_hi, float* dist, float* adj, void* stream);
+
 /* ---- measurement aid (bench.py roofline leg): re-launch ONE kernel `repeats` times on the workspace left by the
  * last forward / input-gradient call.  which: 0 denoiser GCL edge, 1 denoiser EquivariantUpdate edge (denoiser
  * workspace); 2 predictor edge forward, 3 predictor edge backward, 4 node-MLP Linear (predictor grad workspace). */
