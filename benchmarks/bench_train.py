@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=32)
+    ap.add_argument("--model", choices=["denoiser", "predictor"], default="denoiser",
+                    help="denoiser: EDM l2 loss (train_edm.py); predictor: l1 property loss on z_t (train_cond_predictor.py)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     a, model, pred, nodes_dist, prop = models("cata", dev)
@@ -38,17 +40,34 @@ def main():
     B, N = args.batch, 11
     nx = nodes_dist.sample(B)
     nm, em = gb.build_masks(nx, N, False, device=dev)
-    x = torch.randn(B, N, 3, device=dev) * 2.5 * nm
+    x = torch.randn(B, N, 3, device=dev) * 2.4 * nm
     x = x - x.sum(1, keepdim=True) / nm.sum(1, keepdim=True) * nm
     h = {"categorical": torch.ones(B, N, 1, device=dev) * nm, "integer": torch.zeros(0, device=dev)}
-    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, amsgrad=True, weight_decay=1e-12)
+    if args.model == "predictor":
+        from gaudi_b200 import training
+        for p_ in pred.parameters():
+            p_.requires_grad_(True)
+        pred.train()
+        y = torch.randn(B, 5, device=dev)
+        opt = torch.optim.AdamW(pred.parameters(), lr=1e-3, amsgrad=True, weight_decay=1e-12)
 
-    def step():
-        opt.zero_grad()
-        loss = model(x, h, nm, em).mean(0)
-        loss.backward()
-        opt.step()
-        return loss
+        def step():
+            opt.zero_grad()
+            t = torch.randint(0, model.T + 1, size=(B, 1), device=dev).float() / model.T
+            zt = training.sample_edm_t(x, h["categorical"], model, t, nm)
+            loss = torch.nn.functional.l1_loss(pred(zt, nm, em, t), y)
+            loss.backward()
+            opt.step()
+            return loss
+    else:
+        opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, amsgrad=True, weight_decay=1e-12)
+
+        def step():
+            opt.zero_grad()
+            loss = model(x, h, nm, em).mean(0)
+            loss.backward()
+            opt.step()
+            return loss
 
     for _ in range(args.warmup):
         step()
@@ -61,10 +80,36 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
-    out = {"config": 5, "workload": "EDM training step (l2 denoising loss fwd+bwd+AdamW), cc-PBH shape, synthetic batch",
+    out = {"config": 5 if args.model == "denoiser" else "8f-2",
+           "workload": "EDM training step (l2 denoising loss fwd+bwd+AdamW), cc-PBH shape, synthetic batch" if args.model == "denoiser"
+           else "property-predictor training step (sample_edm_t + l1 loss fwd+bwd+AdamW), cc-PBH shape, synthetic batch",
            "batch": B, "edges": int(em.sum().item()), "ms_per_step": ms, "molecules_per_s": B / (ms * 1e-3),
-           "gpu_launches_per_step": (_lib.lib().gb_launch_count(0) - l0) / args.steps, "loss": float(loss)}
-    if not args.no_cpu:
+           "gpu_launches_per_step": (_lib.lib().gb_launch_count(0) - l0) / args.steps, "loss": float(loss.detach())}
+    if not args.no_cpu and args.model == "predictor":
+        import gaudi_oracle as O
+        cb = args.cpu_batch
+        dcfg, pcfg = O.DenoiserCfg(in_node_nf=1), O.PredictorCfg(in_node_nf=1)
+        w = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in pred.state_dict().items()}
+        nmc, emc = nm[:cb].cpu(), em.view(B, N * N)[:cb].reshape(-1, 1).cpu()
+        xc, hc, yc = x[:cb].cpu(), h["categorical"][:cb].cpu(), y[:cb].cpu()
+        copt = torch.optim.AdamW(list(w.values()), lr=1e-3, amsgrad=True, weight_decay=1e-12)
+        gamma = O.gamma_table(dcfg)
+
+        def cpu_step():
+            copt.zero_grad()
+            t = torch.randint(0, 1001, (cb, 1)).float() / 1000
+            zt = O.sample_edm_t(dcfg, gamma, xc, hc, nmc, t, O.draw_noise(cb, N, 4, nmc))
+            torch.nn.functional.l1_loss(O.predictor_forward(w, pcfg, zt, nmc, emc, t), yc).backward()
+            copt.step()
+
+        cpu_step()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            cpu_step()
+        dt = (time.perf_counter() - t0) / 3
+        out["cpu_oracle"] = {"batch": cb, "s_per_step": dt, "molecules_per_s": cb / dt, "threads": torch.get_num_threads()}
+        out["speedup_vs_cpu_oracle"] = out["molecules_per_s"] / (cb / dt)
+    elif not args.no_cpu:
         import gaudi_oracle as O
         cb = args.cpu_batch
         dcfg = O.DenoiserCfg(in_node_nf=1)

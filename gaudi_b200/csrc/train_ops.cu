@@ -408,6 +408,23 @@ __global__ void make_zt_kernel(const float* __restrict__ x, const float* __restr
     }
 }
 
+// pred[b][c] = mean over the N padded nodes of h[b*N+i][c] (edm/egnn_predictor/models.py:456-457), and its backward
+__global__ void pool_mean_fwd_kernel(const float* __restrict__ h, int B, int N, int Cn, float* __restrict__ pred) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * Cn; i += gridDim.x * blockDim.x) {
+        const int b = i / Cn, c = i % Cn;
+        float s = 0.f;
+        for (int k = 0; k < N; ++k) s += h[((size_t)b * N + k) * Cn + c];
+        pred[i] = s / (float)N;
+    }
+}
+__global__ void pool_mean_bwd_kernel(const float* __restrict__ g_pred, int B, int N, int Cn, float* __restrict__ g_h) {
+    const size_t n = (size_t)B * N * Cn;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cn), b = (int)(i / ((size_t)N * Cn));
+        g_h[i] = g_pred[(size_t)b * Cn + c] / (float)N;
+    }
+}
+
 static inline int ew_blocks(size_t n) { size_t b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
 
 }  // namespace gb
@@ -537,4 +554,12 @@ extern "C" int gb_make_zt(const float* x, const float* h, const float* mask, con
     make_zt_kernel<<<ew_blocks((size_t)B * N * (3 + F)), 256, 0, (cudaStream_t)stream>>>(x, h, mask, eps, gamma, t_int, norm_x, norm_h,
                                                                                        bias_h, B, N, F, xh, zt, gamma_t);
     TR_CHECK("make_zt");
+}
+extern "C" int gb_pool_mean(const float* h, int B, int N, int C, float* pred, void* stream) {
+    pool_mean_fwd_kernel<<<ew_blocks((size_t)B * C), 256, 0, (cudaStream_t)stream>>>(h, B, N, C, pred);
+    TR_CHECK("pool_mean");
+}
+extern "C" int gb_pool_mean_bwd(const float* g_pred, int B, int N, int C, float* g_h, void* stream) {
+    pool_mean_bwd_kernel<<<ew_blocks((size_t)B * N * C), 256, 0, (cudaStream_t)stream>>>(g_pred, B, N, C, g_h);
+    TR_CHECK("pool_mean_bwd");
 }

@@ -99,7 +99,12 @@ class EGNN_predictor(nn.Module):
                           out_nf=out_nf, in_node_nf=in_node_nf, coords_range=float(coords_range))
 
     def forward(self, xh, node_mask, edge_mask, t=torch.zeros(1)):
-        """pred [B, out_nf]; differentiable w.r.t. ``xh`` (edm/egnn_predictor/models.py:433-457)."""
+        """pred [B, out_nf] (edm/egnn_predictor/models.py:433-457).  Differentiable w.r.t. ``xh`` (the guidance gradient,
+        hand-written input-gradient kernels) or -- when ``xh`` needs no gradient and the parameters do, i.e. while training
+        the predictor (cond_prediction/train_cond_predictor.py:65-81) -- w.r.t. the parameters."""
+        if torch.is_grad_enabled() and not xh.requires_grad and any(p.requires_grad for p in self.parameters()):
+            from . import training
+            return training.predictor_forward_train(self, xh, node_mask, edge_mask, t)
         return runtime.predictor_forward(self, xh, node_mask, edge_mask, t)
 
     def unnormalize(self, pred):

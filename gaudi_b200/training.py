@@ -84,24 +84,29 @@ def _linear(A1, W, K1, N, bias=None, A2=None, K2=0, transpose=False, epi=EPI_NON
 
 # ------------------------------------------------------------------------------------------------------------------
 class _Linear(torch.autograd.Function):
-    """y = (x W^T + b) [* mask]  -- nn.Linear (+ the node mask of egnn_new.py:318)."""
+    """y = act(x W^T + b) [* mask]  -- nn.Linear, optionally followed by SiLU or the node mask of egnn_new.py:318."""
 
     @staticmethod
-    def forward(ctx, x, W, b, mask):
+    def forward(ctx, x, W, b, mask, act=False):
         x, W = _c(x), _c(W)
         M, K = x.shape
         N = W.shape[0]
-        y = _new(x, M, N)
-        _gemm(0, M, N, K, x, K, W, K, y, N, b)
-        if mask is not None:
-            _call("gb_resmask", _ptr(y), None, _ptr(mask), M, N, _ptr(y))
-        ctx.save_for_backward(x, W, mask)
+        pre = None
+        if act:
+            pre = _new(x, M, N)
+            y = _linear(x, W, K, N, b, epi=EPI_SILU, out2=pre)
+        else:
+            y = _new(x, M, N)
+            _gemm(0, M, N, K, x, K, W, K, y, N, b)
+            if mask is not None:
+                _call("gb_resmask", _ptr(y), None, _ptr(mask), M, N, _ptr(y))
+        ctx.save_for_backward(x, W, mask, pre)
         ctx.has_bias = b is not None
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, W, mask = ctx.saved_tensors
+        x, W, mask, pre = ctx.saved_tensors
         M, K = x.shape
         N = W.shape[0]
         gy = _c(gy)
@@ -109,12 +114,17 @@ class _Linear(torch.autograd.Function):
             gm = _new(gy, M, N)
             _call("gb_resmask", _ptr(gy), None, _ptr(mask), M, N, _ptr(gm))
             gy = gm
-        gx = _new(gy, M, K)
-        _gemm(1, M, K, N, gy, N, W, K, gx, K)
+        if pre is not None:
+            gp = _new(gy, M, N)
+            _call("gb_silu_bwd", _ptr(pre), _ptr(gy), _ptr(gp), M * N)
+            gy = gp
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = _linear(gy, W, N, K, transpose=True)
         gW = _new(gy, N, K)
         _gemm(2, N, K, M, gy, N, x, K, gW, K)
         gb = _colsum(gy, M, N) if ctx.has_bias else None
-        return gx, gW, gb, None
+        return gx, gW, gb, None, None
 
 
 class _Geometry(torch.autograd.Function):
@@ -233,6 +243,69 @@ class _AttAgg(torch.autograd.Function):
         gwa = _colsum(m, E, H, coef).reshape(1, H)
         gba = _colsum(coef, E, 1)
         return gm, gwa, gba, None, None
+
+
+class _Gate(torch.autograd.Function):
+    """ef = m * sigmoid(w_a . m + b_a)  (gcl.py:232-237; the edge mask is implicit in the compacted edge list)."""
+
+    @staticmethod
+    def forward(ctx, m, wa, ba):
+        m = _c(m)
+        E, H = m.shape
+        wv = _c(wa.reshape(-1))
+        logit, gate, ef = _new(m, E), _new(m, E), _new(m, E, H)
+        _call("gb_rowdot", _ptr(m), H, E, H, _ptr(wv), _ptr(ba), _ptr(logit))
+        _call("gb_gate_fwd", _ptr(m), _ptr(logit), E, H, _ptr(ef), _ptr(gate))
+        ctx.save_for_backward(m, wv, gate)
+        return ef
+
+    @staticmethod
+    def backward(ctx, g_ef):
+        m, wv, gate = ctx.saved_tensors
+        E, H = m.shape
+        gm, coef = _new(m, E, H), _new(m, E)
+        _call("gb_gate_bwd", _ptr(m), _ptr(gate), _ptr(wv), _ptr(_c(g_ef)), E, H, _ptr(gm), _ptr(coef))
+        return gm, _colsum(m, E, H, coef).reshape(1, H), _colsum(coef, E, 1)
+
+
+class _SegSum(torch.autograd.Function):
+    """agg_i = scale * sum_{e: row_e = i} ef_e  (unsorted_segment_sum, gcl.py:417-423)."""
+
+    @staticmethod
+    def forward(ctx, ef, g, scale):
+        ef = _c(ef)
+        E, H = ef.shape
+        agg = _new(ef, g.topo.B * g.topo.N, H)
+        _call("gb_rowcol_reduce", g.handle, _ptr(ef), H, _F(scale), _ptr(agg), None)
+        ctx.g, ctx.scale, ctx.shape = g, scale, (E, H)
+        return agg
+
+    @staticmethod
+    def backward(ctx, g_agg):
+        E, H = ctx.shape
+        g_ef = _new(g_agg, E, H)
+        _call("gb_gather_rows", ctx.g.handle, _ptr(_c(g_agg)), H, _F(ctx.scale), _ptr(g_ef))
+        return g_ef, None, None
+
+
+class _PoolMean(torch.autograd.Function):
+    """pred = h.view(B, N, C).mean(1)  (edm/egnn_predictor/models.py:456-457: mean over the padded N)."""
+
+    @staticmethod
+    def forward(ctx, h, B, N):
+        h = _c(h)
+        Cn = h.shape[1]
+        pred = _new(h, B, Cn)
+        _call("gb_pool_mean", _ptr(h), B, N, Cn, _ptr(pred))
+        ctx.dims = (B, N, Cn)
+        return pred
+
+    @staticmethod
+    def backward(ctx, g_pred):
+        B, N, Cn = ctx.dims
+        gh = _new(g_pred, B * N, Cn)
+        _call("gb_pool_mean_bwd", _ptr(_c(g_pred)), B, N, Cn, _ptr(gh))
+        return gh, None, None
 
 
 class _NodeMLP(torch.autograd.Function):
@@ -410,3 +483,60 @@ def training_loss(model, x, h, node_mask, edge_mask, t_int: Optional[torch.Tenso
     net = denoiser_forward_train(model.dynamics, t_f / model.T, zt, node_mask, edge_mask)
     return _TrainLoss.apply(net, eps, zt, xh, mask, t_f, gamma_t, model._gamma_T(), float(model.norm_values[1]),
                             float(model.norm_biases[1]))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# property predictor: cond_prediction/train_cond_predictor.py:47-81
+# ------------------------------------------------------------------------------------------------------------------
+def predictor_forward_train(pred_module, xh: torch.Tensor, node_mask: torch.Tensor, edge_mask: torch.Tensor, t) -> torch.Tensor:
+    """``EGNN_predictor.forward`` (edm/egnn_predictor/models.py:433-457, 543-560; gcl.py:225-316), differentiable w.r.t. the
+    PARAMETERS (the guidance path, differentiable w.r.t. the input, is runtime.predictor_forward)."""
+    _need_cuda(xh, "xh")
+    B, N, D = xh.shape
+    F = D - 3
+    egnn = pred_module.egnn
+    g = graph_for(node_mask, edge_mask, B, N)
+    mask = g.topo.node_mask
+    n = B * N
+    z = xh.detach().to(torch.float32).reshape(n, D)
+    x = _new(z, n, 3)
+    _call("gb_resmask", _ptr(_c(z[:, :3])), None, _ptr(mask), n, 3, _ptr(x))
+    hf = _new(z, n, F)
+    _call("gb_resmask", _ptr(_c(z[:, 3:])), None, _ptr(mask), n, F, _ptr(hf))
+    if pred_module.condition_time:
+        tt = torch.as_tensor(t, dtype=torch.float32, device=z.device).reshape(-1)
+        tcol = (tt.expand(B) if tt.numel() == 1 else tt).reshape(B, 1).expand(B, N).reshape(n, 1)
+        hf = torch.cat([hf, tcol], dim=1)
+    a = _new(z, g.topo.n_edges)
+    _call("gb_geom_fwd", g.handle, _ptr(x), _F(1.0), _ptr(a), None)       # models.py:452: edge_attr = |x_i - x_j|^2 of the input
+    h = _Linear.apply(hf, egnn.embedding.weight, egnn.embedding.bias, None)
+    for l in range(egnn.n_layers):
+        lay = getattr(egnn, f"gcl_{l}")
+        r, u = _Geometry.apply(x, g, 1.0)                                 # gcl.py:308-316 (norm_diff: / (sqrt(r + 1e-8) + 1))
+        e = _EdgeMLP.apply(h, r, a, lay.edge_mlp[0].weight, lay.edge_mlp[0].bias, lay.edge_mlp[2].weight, lay.edge_mlp[2].bias, g)
+        ef = _Gate.apply(e, lay.att_mlp[0].weight, lay.att_mlp[0].bias) if lay.attention else e
+        c = _Linear.apply(ef, lay.coord_mlp[0].weight, lay.coord_mlp[0].bias, None, True)
+        x_new = _CoordUpdate.apply(x, u, c, lay.coord_mlp[2].weight, g, float(getattr(lay, "coords_range", 1.0)), bool(lay.tanh), 1.0)
+        agg = _SegSum.apply(ef, g, 1.0)
+        h = _NodeMLP.apply(h, agg, lay.node_mlp[0].weight, lay.node_mlp[0].bias, lay.node_mlp[2].weight, lay.node_mlp[2].bias, mask)
+        x = x_new
+    hout = _Linear.apply(h, egnn.embedding_out.weight, egnn.embedding_out.bias, mask)
+    return _PoolMean.apply(hout, B, N)
+
+
+def sample_edm_t(x, h, edm_model, t, node_mask, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """z_t ~ q(z_t | x, h) at the per-sample times ``t`` [B,1] in [0,1] (cond_prediction/train_cond_predictor.py:47-62)."""
+    _need_cuda(x, "x")
+    B, N, _ = x.shape
+    F = h.shape[2]
+    mask = node_mask.detach().reshape(B * N).to(torch.float32).contiguous()
+    if eps is None:
+        eps = edm_model.sample_combined_position_feature_noise(B, N, node_mask)
+    eps = _c(eps.to(torch.float32))
+    t_idx = torch.round(t.reshape(B).to(torch.float32) * edm_model.T).contiguous()       # PredefinedNoiseSchedule.forward
+    gamma = edm_model.gamma.gamma.detach().to(torch.float32).contiguous()
+    xh, zt, gamma_t = _new(eps, B, N, 3 + F), _new(eps, B, N, 3 + F), _new(eps, B)
+    _call("gb_make_zt", _ptr(_c(x.to(torch.float32))), _ptr(_c(h.to(torch.float32))), _ptr(mask), _ptr(eps), _ptr(gamma), _ptr(t_idx),
+          _F(edm_model.norm_values[0]), _F(edm_model.norm_values[1]), _F(edm_model.norm_biases[1]), B, N, F, _ptr(xh), _ptr(zt),
+          _ptr(gamma_t))
+    return zt

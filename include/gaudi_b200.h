@@ -207,6 +207,9 @@ int gb_den_finish_fwd(const float* x_fin, const float* x_in, const float* h3, co
 int gb_make_zt(const float* x, const float* h, const float* mask, const float* eps, const float* gamma,
                const float* t_int, float norm_x, float norm_h, float bias_h, int B, int N, int F, float* xh, float* zt,
                float* gamma_t, void* stream);
+/* gb_pool_mean[_bwd]: pred [B,C] = mean over the N padded nodes of h [B*N,C] (edm/egnn_predictor/models.py:456-457). */
+int gb_pool_mean(const float* h, int B, int N, int C, float* pred, void* stream);
+int gb_pool_mean_bwd(const float* g_pred, int B, int N, int C, float* g_h, void* stream);
 int gb_train_loss(const float* net, const float* eps, const float* zt, const float* xh, const float* mask,
                   const float* t_int, const float* gamma_t, float gamma_T, float norm_h, float bias_h, int B, int N,
                   int F, float* loss, float* g_net, void* stream);

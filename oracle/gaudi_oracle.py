@@ -517,3 +517,15 @@ def training_loss(w: Weights, cfg: DenoiserCfg, gamma: Tensor, x: Tensor, h_cat:
     loss = kl_prior + loss_term_0 * tz + (1 - tz) * loss_t_larger_than_zero     # :744-760; constants and delta_log_px are zeroed
     return loss, z_t
 
+
+
+# --------------------------------------------------------------------------
+# predictor training inputs: cond_prediction/train_cond_predictor.py:47-81
+# --------------------------------------------------------------------------
+def sample_edm_t(cfg: DenoiserCfg, gamma: Tensor, x: Tensor, h_cat: Tensor, node_mask: Tensor, t: Tensor, eps: Tensor) -> Tensor:
+    """z_t = alpha_t [x/3, h/4*mask] + sigma_t eps at per-sample t [B,1] (train_cond_predictor.py:47-62); the loss on top is
+    l1_loss(predictor_forward(z_t, t), target) (:65-81)."""
+    B = x.shape[0]
+    xh = torch.cat([x / cfg.norm_values[0], (h_cat.float() - cfg.norm_biases[1]) / cfg.norm_values[1] * node_mask], dim=-1)
+    g_t = gamma[torch.round(t * cfg.timesteps).long()].view(B, 1, 1)
+    return torch.sqrt(torch.sigmoid(-g_t)) * xh + torch.sqrt(torch.sigmoid(g_t)) * eps

@@ -26,7 +26,7 @@ REF = os.environ.get("GAUDI_REFERENCE", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.dont_write_bytecode = True
 sys.path.insert(0, REF)
-for _m in ["rdkit", "rdkit.Chem", "rdkit.Chem.Draw", "matplotlib", "matplotlib.pyplot", "imageio"]:
+for _m in ["rdkit", "rdkit.Chem", "rdkit.Chem.Draw", "matplotlib", "matplotlib.pyplot", "imageio", "torch.utils.tensorboard"]:
     sys.modules[_m] = MagicMock()
 
 from utils.args_edm import Args_EDM  # noqa: E402
@@ -253,11 +253,63 @@ def train_step(dataset, nodesxsample, t_list, seed):
     return out
 
 
+def predictor_train_step(dataset, nodesxsample, t_list, seed):
+    """One loss + backward of the reference's predictor training (cond_prediction/train_cond_predictor.py:65-81, 104-111)
+    with its two random draws (t_int, eps of sample_edm_t) pinned."""
+    from cond_prediction import train_cond_predictor as TCP
+    args, model, pred, prop = build(dataset)
+    for p_ in pred.parameters():
+        p_.requires_grad_(True)
+    pred.train()
+    inner = model.module if hasattr(model, "module") else model
+    F_in = 1 if dataset == "cata" else 12
+    gen = torch.Generator().manual_seed(seed)
+    nm, em = ref_masks(args, nodesxsample)
+    B, N = nm.shape[0], nm.shape[1]
+    x = remove_mean_with_mask(torch.randn((B, N, 3), generator=gen) * 2.5 * nm, nm)
+    h = torch.nn.functional.one_hot(torch.randint(0, F_in, (B, N), generator=gen), F_in).float() * nm
+    y = torch.randn((B, 5), generator=gen)
+    t_int = torch.tensor(t_list, dtype=torch.int64).view(B, 1)
+    eps = processed_noise(gen, (B, N, 3 + F_in), nm)
+    real_randint = torch.randint
+    torch.randint = lambda *a, **k: t_int.clone()
+    inner.sample_combined_position_feature_noise = lambda n_samples, n_nodes, node_mask, std=1.0: eps.clone()
+    try:
+        loss, err = TCP.compute_loss(pred, x, h, nm, em, y, inner, Namespace(diffusion_steps=inner.T))
+        loss.backward()
+        with torch.no_grad():
+            z_t = TCP.sample_edm_t(x, h, inner, t_int.float() / inner.T, nm)
+    finally:
+        torch.randint = real_randint
+        del inner.sample_combined_position_feature_noise
+    out = dict(nodesxsample=nodesxsample.numpy(), x=x.numpy(), h=h.numpy(), y=y.numpy(), t_int=t_int.numpy(), eps=eps.numpy(),
+               loss=loss.detach().numpy(), abs_err=err.numpy(), z_t=z_t.numpy())
+    full = ["egnn.embedding.weight", "egnn.embedding_out.weight", "egnn.embedding_out.bias", "egnn.gcl_0.att_mlp.0.weight",
+            "egnn.gcl_5.coord_mlp.0.bias", "egnn.gcl_10.coord_mlp.2.weight", "egnn.gcl_3.edge_mlp.0.weight"]
+    names, norms = [], []
+    for n_, p_ in pred.named_parameters():
+        n_ = n_[len("module."):] if n_.startswith("module.") else n_
+        if p_.grad is None:                      # the last layer's coordinate branch never reaches the output
+            continue
+        names.append(n_)
+        norms.append(float(p_.grad.double().norm()))
+        if n_ in full:
+            out["grad:" + n_] = p_.grad.numpy()
+    out["grad_names"], out["grad_norms"] = np.array(names), np.array(norms, dtype=np.float64)
+    return out
+
+
 def main():
     meta = {"torch": torch.__version__, "seed_denoiser": SEED_DEN, "seed_predictor": SEED_PRED,
             "prop_mean": MEAN5.tolist(), "prop_std": STD5.tolist()}
     steps = [1000, 999, 750, 500, 250, 2, 1]
 
+    if "--only-pred-train" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "pred_train_cata.npz"),
+                            **predictor_train_step("cata", torch.tensor([11, 10, 9, 11, 7, 2]), [1000, 613, 0, 1, 250, 0], seed=666))
+        np.savez_compressed(os.path.join(HERE, "pred_train_hetro.npz"),
+                            **predictor_train_step("hetro", torch.tensor([10, 8, 3]), [777, 0, 12], seed=667))
+        return
     if "--only-train" in sys.argv:          # add the training fixtures without regenerating the (slow) chains
         np.savez_compressed(os.path.join(HERE, "train_cata.npz"),
                             **train_step("cata", torch.tensor([11, 10, 9, 11, 7, 2]), [1000, 613, 0, 1, 250, 0], seed=555))
@@ -295,6 +347,10 @@ def main():
                         **train_step("cata", torch.tensor([11, 10, 9, 11, 7, 2]), [1000, 613, 0, 1, 250, 0], seed=555))
     np.savez_compressed(os.path.join(HERE, "train_hetro.npz"),
                         **train_step("hetro", torch.tensor([10, 8, 3]), [777, 0, 12], seed=556))
+    np.savez_compressed(os.path.join(HERE, "pred_train_cata.npz"),
+                        **predictor_train_step("cata", torch.tensor([11, 10, 9, 11, 7, 2]), [1000, 613, 0, 1, 250, 0], seed=666))
+    np.savez_compressed(os.path.join(HERE, "pred_train_hetro.npz"),
+                        **predictor_train_step("hetro", torch.tensor([10, 8, 3]), [777, 0, 12], seed=667))
     print("train done", flush=True)
 
     with open(os.path.join(HERE, "meta.json"), "w") as f:

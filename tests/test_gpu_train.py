@@ -169,3 +169,41 @@ def test_optimizer_steps_reduce_the_loss():
         opt.step()
         losses.append(float(loss))
     assert np.isfinite(losses).all() and losses[-1] < 0.7 * losses[0], losses
+
+
+@pytest.mark.parametrize("gemm", ["tc", "fp32"])
+@pytest.mark.parametrize("ds", ["cata", "hetro"])
+def test_predictor_training_step_matches_reference_golden(ds, gemm, monkeypatch):
+    """8f rank 2: sample_edm_t, predictor forward in training mode, l1 loss, parameter gradients (train_cond_predictor.py:47-81)."""
+    dev = _dev()
+    monkeypatch.setattr(training, "_TC", gemm == "tc")
+    g = golden(f"pred_train_{ds}.npz")
+    args, model, pred, prop = build_models(ds, dev)
+    for p_ in pred.parameters():
+        p_.requires_grad_(True)
+    pred.train()
+    nm, em = gb.build_masks(torch.from_numpy(g["nodesxsample"]), 11 if ds == "cata" else 10, ds == "hetro", device=dev)
+    x, h, y = (torch.from_numpy(g[k]).to(dev) for k in ("x", "h", "y"))
+    t = torch.from_numpy(g["t_int"]).to(dev).float() / model.T
+    zt = training.sample_edm_t(x, h, model, t, nm, eps=torch.from_numpy(g["eps"]).to(dev))
+    assert maxabs(zt, g["z_t"]) <= 1e-6
+    p = pred(zt, nm, em, t)
+    loss = torch.nn.functional.l1_loss(p, y)                 # train_cond_predictor.py:80
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["loss"])) <= 1e-4
+    assert maxabs((p.detach() - y).abs(), g["abs_err"]) <= 1e-4
+    params = dict(pred.named_parameters())
+    worst = 0.0
+    for name, norm in zip(g["grad_names"], g["grad_norms"]):
+        gn = float(params[str(name)].grad.double().norm())
+        worst = max(worst, abs(gn - norm) / max(norm, 1e-6))
+        assert abs(gn - norm) <= 2e-3 * max(norm, 1e-6), f"{name}: {gn:.6e} vs {norm:.6e}"
+    for k in g.files:
+        if k.startswith("grad:"):
+            ref = torch.from_numpy(g[k])
+            assert maxabs(params[k[5:]].grad, ref) <= 1e-4 * max(1.0, float(ref.abs().max())), k
+    # the guidance path (input gradient) is untouched by parameters that require grad
+    z2 = zt.clone().requires_grad_()
+    (gz,) = torch.autograd.grad(pred(z2, nm, em, t)[:, 1].sum(), z2)
+    assert gz.shape == zt.shape and torch.isfinite(gz).all()
+    print(f"[predictor train parity {ds} {gemm}] loss diff {abs(float(loss.detach()) - float(g['loss'])):.2e}, worst grad-norm rel {worst:.2e}")

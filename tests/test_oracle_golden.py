@@ -123,3 +123,27 @@ def test_training_loss_and_gradients_match_reference(ds):
         if k.startswith("grad:"):
             ref = torch.from_numpy(g[k])
             assert maxabs(w[k[5:]].grad, ref) <= 1e-6 * max(1.0, float(ref.abs().max())), k
+
+
+@pytest.mark.parametrize("ds", ["cata", "hetro"])
+def test_predictor_training_loss_and_gradients_match_reference(ds):
+    """8f rank 2: sample_edm_t + l1 loss of the reference's predictor training step and its parameter gradients."""
+    g = golden(f"pred_train_{ds}.npz")
+    args, model, pred, prop = build_models(ds, "cpu")
+    dcfg, pcfg = oracle_cfgs(ds)
+    w = {k: v.detach().clone().requires_grad_(True) for k, v in pred.state_dict().items()}
+    nm, em = O.build_masks(torch.from_numpy(g["nodesxsample"]), 11 if ds == "cata" else 10, ds == "hetro")
+    t = torch.from_numpy(g["t_int"]).float() / dcfg.timesteps
+    zt = O.sample_edm_t(dcfg, O.gamma_table(dcfg), torch.from_numpy(g["x"]), torch.from_numpy(g["h"]), nm, t, torch.from_numpy(g["eps"]))
+    assert maxabs(zt, g["z_t"]) == 0.0
+    p = O.predictor_forward(w, pcfg, zt, nm, em, t)
+    loss = torch.nn.functional.l1_loss(p, torch.from_numpy(g["y"]))
+    assert abs(float(loss.detach()) - float(g["loss"])) <= 1e-6
+    assert maxabs((p.detach() - torch.from_numpy(g["y"])).abs(), g["abs_err"]) <= 1e-6
+    loss.backward()
+    for name, norm in zip(g["grad_names"], g["grad_norms"]):
+        assert abs(float(w[str(name)].grad.double().norm()) - norm) <= 1e-5 * max(norm, 1e-6), name
+    for k in g.files:
+        if k.startswith("grad:"):
+            ref = torch.from_numpy(g[k])
+            assert maxabs(w[k[5:]].grad, ref) <= 1e-6 * max(1.0, float(ref.abs().max())), k
