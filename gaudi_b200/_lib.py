@@ -75,6 +75,7 @@ SIGNATURES = {
     "gb_make_zt": (_I, [_P, _P, _P, _P, _P, _P, _F, _F, _F, _I, _I, _I, _P, _P, _P, _P]),
     "gb_check_stability": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _F, _P, _P, _P, _F, _F, _I, _P, _P]),
     "gb_positions2adj": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "gb_vlb_loss": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _I, _I, _I, _P, _P, _P]),
     "gb_pool_mean": (_I, [_P, _I, _I, _I, _P, _P]),
     "gb_pool_mean_bwd": (_I, [_P, _I, _I, _I, _P, _P]),
     "gb_train_loss": (_I, [_P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _I, _I, _I, _P, _P, _P]),

@@ -425,6 +425,66 @@ __global__ void pool_mean_bwd_kernel(const float* __restrict__ g_pred, int B, in
     }
 }
 
+// Variational bound of EnVariationalDiffusion.forward in eval mode: compute_loss(t0_always = True) (en_diffusion.py:644-775,
+// 777-804) with include_charges = False.  Two network outputs per molecule: net_t at (z_t, t ~ U{1..T}) and net_0 at (z_0, 0).
+//   nll_b = kl_prior + T * 0.5 (SNR(gamma_s - gamma_t) - 1) |eps_t - net_t|^2 - log_constants + L0(z_0) - delta_log_px
+__global__ void vlb_loss_kernel(const float* __restrict__ net_t, const float* __restrict__ eps_t, const float* __restrict__ net_0,
+                                const float* __restrict__ eps_0, const float* __restrict__ z0, const float* __restrict__ xh,
+                                const float* __restrict__ mask, const float* __restrict__ t_int, const float* __restrict__ gamma,
+                                int T, float norm_x, float norm_h, float bias_h, int B, int N, int F, float* __restrict__ loss,
+                                float* __restrict__ error_out) {
+    const int D = 3 + F;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const int ti = (int)t_int[b];
+    const float g_t = gamma[ti], g_s = gamma[ti - 1], g_0 = gamma[0], g_T = gamma[T];
+    const float sigma0_cat = sqrtf(sigmoid_f(g_0)) * norm_h;
+    const float alpha_T = sqrtf(1.f / (1.f + expf(g_T))), sigma_T = sqrtf(1.f / (1.f + expf(-g_T)));
+    float err = 0.f, err0_x = 0.f, logph = 0.f, mu2_x = 0.f, kl_h = 0.f, n_nodes = 0.f;
+    for (int i = lane; i < N; i += 32) {
+        const size_t o = (size_t)(b * N + i) * D;
+        const float mk = mask[b * N + i];
+        n_nodes += mk;
+        for (int d = 0; d < D; ++d) {
+            const float df = eps_t[o + d] - net_t[o + d];
+            err += df * df;
+            if (d < 3) { const float d0 = eps_0[o + d] - net_0[o + d]; err0_x += d0 * d0; }
+            const float mu = alpha_T * xh[o + d];
+            if (d < 3) mu2_x += mu * mu;
+            else kl_h += (logf(1.f / sigma_T) + 0.5f * (sigma_T * sigma_T + mu * mu) - 0.5f) * mk;
+        }
+        float lp[16], mx = -INFINITY;
+        for (int k = 0; k < F; ++k) {
+            const float c = z0[o + 3 + k] * norm_h + bias_h - 1.f;
+            const float hi = 0.5f * (1.f + erff((c + 0.5f) / sigma0_cat * 0.70710678118654752f));
+            const float lo = 0.5f * (1.f + erff((c - 0.5f) / sigma0_cat * 0.70710678118654752f));
+            lp[k] = logf(hi - lo + 1e-10f);
+            mx = fmaxf(mx, lp[k]);
+        }
+        float se = 0.f;
+        for (int k = 0; k < F; ++k) se += expf(lp[k] - mx);
+        const float logZ = mx + logf(se);
+        for (int k = 0; k < F; ++k) logph += (lp[k] - logZ) * (xh[o + 3 + k] * norm_h + bias_h) * mk;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        err += __shfl_xor_sync(0xffffffffu, err, off); err0_x += __shfl_xor_sync(0xffffffffu, err0_x, off);
+        logph += __shfl_xor_sync(0xffffffffu, logph, off); mu2_x += __shfl_xor_sync(0xffffffffu, mu2_x, off);
+        kl_h += __shfl_xor_sync(0xffffffffu, kl_h, off); n_nodes += __shfl_xor_sync(0xffffffffu, n_nodes, off);
+    }
+    if (lane == 0) {
+        const float dsub = (n_nodes - 1.f) * 3.f;
+        const float kl_x = dsub * logf(1.f / sigma_T) + 0.5f * (dsub * sigma_T * sigma_T + mu2_x) - 0.5f * dsub;
+        const float snr_w = expf(-(g_s - g_t)) - 1.f;
+        const float loss_t = 0.5f * snr_w * err;
+        const float neg_log_const = -(dsub * (-0.5f * g_0 - 0.5f * 1.8378770664093453f));      // log(2 pi)
+        const float loss_0 = -(-0.5f * err0_x + logph);
+        const float delta_log_px = -dsub * logf(norm_x);
+        loss[b] = kl_x + kl_h + (float)T * loss_t + neg_log_const + loss_0 - delta_log_px;
+        if (error_out) error_out[b] = err;
+    }
+}
+
 static inline int ew_blocks(size_t n) { size_t b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
 
 }  // namespace gb
@@ -562,4 +622,12 @@ extern "C" int gb_pool_mean(const float* h, int B, int N, int C, float* pred, vo
 extern "C" int gb_pool_mean_bwd(const float* g_pred, int B, int N, int C, float* g_h, void* stream) {
     pool_mean_bwd_kernel<<<ew_blocks((size_t)B * N * C), 256, 0, (cudaStream_t)stream>>>(g_pred, B, N, C, g_h);
     TR_CHECK("pool_mean_bwd");
+}
+extern "C" int gb_vlb_loss(const float* net_t, const float* eps_t, const float* net_0, const float* eps_0, const float* z0,
+                           const float* xh, const float* mask, const float* t_int, const float* gamma, int T, float norm_x, float norm_h,
+                           float bias_h, int B, int N, int F, float* loss, float* error_out, void* stream) {
+    if (F > 16) return gb_train_fail("vlb_loss: too many classes");
+    vlb_loss_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(net_t, eps_t, net_0, eps_0, z0, xh, mask, t_int, gamma, T, norm_x, norm_h,
+                                                                  bias_h, B, N, F, loss, error_out);
+    TR_CHECK("vlb_loss");
 }

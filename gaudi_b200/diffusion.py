@@ -221,15 +221,15 @@ class EnVariationalDiffusion(torch.nn.Module):
             self.__dict__["_gT"] = cache
         return cache[1]
 
-    def forward(self, x, h, node_mask=None, edge_mask=None, context=None, t_int=None, eps=None):
-        """Training loss [B] (en_diffusion.py:777-804): train mode, loss_type 'l2' -- the configuration train_edm.py runs.
-        ``t_int`` / ``eps`` optionally pin the two random draws of compute_loss (tests).  The eval-mode NLL estimator
-        (t0_always=True, two network passes, SNR weighting) is not built."""
+    def forward(self, x, h, node_mask=None, edge_mask=None, context=None, t_int=None, eps=None, eps0=None):
+        """Loss [B] (en_diffusion.py:777-804).  Train mode with loss_type 'l2' (what train_edm.py optimises): the denoising
+        loss with parameter gradients; eval mode: the variational bound compute_loss(t0_always=True) that val_epoch / test
+        report (forward only).  ``t_int`` / ``eps`` (/ ``eps0``) optionally pin the random draws of compute_loss (tests)."""
         if context is not None:
             raise NotImplementedError("context conditioning is unused by GaUDI")
-        if not self.training:
-            raise NotImplementedError("eval-mode NLL (compute_loss(t0_always=True)) is not implemented; call .train()")
         from . import training
+        if not self.training:
+            return training.vlb_loss(self, x, h, node_mask, edge_mask, t_int=t_int, eps=eps, eps0=eps0)
         return training.training_loss(self, x, h, node_mask, edge_mask, t_int=t_int, eps=eps)
 
     # ---- noise -------------------------------------------------------------------------------------------------
@@ -447,5 +447,23 @@ class EnVariationalDiffusion(torch.nn.Module):
             last = self.sample_combined_position_feature_noise(n_samples, n_nodes, node_mask)
         return self._finish(z, node_mask, edge_mask, fix_noise, last)
 
-    def sample_chain(self, *a, **k):
-        raise NotImplementedError("sample_chain is a visualisation helper outside the hot path")
+    @torch.no_grad()
+    def sample_chain(self, n_samples, n_nodes, node_mask, edge_mask, context=None, keep_frames=None, std=1.0, noise=None):
+        """Unguided sampling that keeps intermediate states (en_diffusion.py:1118-1174): returns the un-normalised frames
+        flattened to [n_samples * keep_frames, N, D]; frame 0 is the final (x, h).  Runs the eager per-step path."""
+        z = self._initial_z(n_samples, n_nodes, node_mask, False, std, noise)
+        keep_frames = self.T if keep_frames is None else keep_frames
+        assert keep_frames <= self.T
+        chain = torch.zeros((keep_frames,) + z.size(), device=z.device)
+        stats = torch.zeros(self.T, 8, dtype=torch.float32, device=z.device)
+        for s in reversed(range(self.T)):
+            s_arr = torch.full((n_samples, 1), fill_value=s, device=z.device) / self.T
+            z = self.sample_p_zs_given_zt(s_arr, s_arr + 1.0 / self.T, z, node_mask, edge_mask, context,
+                                          noise=None if noise is None else noise[self.T - s], stats=stats[s])
+            x, h_cat, _ = self.unnormalize(z[:, :, :self.n_dims], z[:, :, self.n_dims:], z[:, :, :0], node_mask)
+            chain[(s * keep_frames) // self.T] = torch.cat([x, h_cat], dim=2)
+        self._check_stats(stats)
+        last = noise[self.T + 1] if noise is not None else self.sample_combined_position_feature_noise(n_samples, n_nodes, node_mask)
+        x, h = self._finish(z, node_mask, edge_mask, False, last)
+        chain[0] = torch.cat([x, h["categorical"], h["integer"]], dim=2)
+        return chain.view(n_samples * keep_frames, *z.size()[1:])

@@ -540,3 +540,44 @@ def sample_edm_t(x, h, edm_model, t, node_mask, eps: Optional[torch.Tensor] = No
           _F(edm_model.norm_values[0]), _F(edm_model.norm_values[1]), _F(edm_model.norm_biases[1]), B, N, F, _ptr(xh), _ptr(zt),
           _ptr(gamma_t))
     return zt
+
+
+def vlb_loss(model, x, h, node_mask, edge_mask, t_int: Optional[torch.Tensor] = None, eps: Optional[torch.Tensor] = None,
+             eps0: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``EnVariationalDiffusion.forward`` in eval mode: the -log p(x,h) estimator compute_loss(t0_always=True) [B]
+    (en_diffusion.py:644-804; used by train_edm.val_epoch / test).  Forward only: the two denoiser passes run on the
+    sampler's fused inference kernels.  ``t_int`` [B,1] in 1..T, ``eps`` / ``eps0`` [B,N,D] optionally pin the draws."""
+    from . import runtime
+    _need_cuda(x, "x")
+    if model.include_charges:
+        raise NotImplementedError("include_charges=True is not used by GaUDI")
+    B, N, _ = x.shape
+    F = model.in_node_nf
+    dev = x.device
+    h_cat = h["categorical"] if isinstance(h, dict) else h
+    with torch.no_grad():
+        if t_int is None:
+            t_int = torch.randint(1, model.T + 1, size=(B, 1), device=dev)
+        t_f = t_int.to(torch.float32).reshape(B).contiguous()
+        g = graph_for(node_mask, edge_mask, B, N)
+        mask = g.topo.node_mask
+        if eps is None:
+            eps = model.sample_combined_position_feature_noise(B, N, node_mask)
+        if eps0 is None:
+            eps0 = model.sample_combined_position_feature_noise(B, N, node_mask)
+        eps, eps0 = _c(eps.to(torch.float32)), _c(eps0.to(torch.float32))
+        gamma = model.gamma.gamma.detach().to(torch.float32).contiguous()
+        xs, hs = _c(x.to(torch.float32)), _c(h_cat.to(torch.float32))
+        nv, nb = model.norm_values, model.norm_biases
+        xh, zt, z0, gt = _new(eps, B, N, 3 + F), _new(eps, B, N, 3 + F), _new(eps, B, N, 3 + F), _new(eps, B)
+        zeros = torch.zeros(B, dtype=torch.float32, device=dev)
+        _call("gb_make_zt", _ptr(xs), _ptr(hs), _ptr(mask), _ptr(eps), _ptr(gamma), _ptr(t_f), _F(nv[0]), _F(nv[1]), _F(nb[1]), B, N, F,
+              _ptr(xh), _ptr(zt), _ptr(gt))
+        _call("gb_make_zt", _ptr(xs), _ptr(hs), _ptr(mask), _ptr(eps0), _ptr(gamma), _ptr(zeros), _F(nv[0]), _F(nv[1]), _F(nb[1]), B, N, F,
+              _ptr(xh), _ptr(z0), _ptr(gt))
+        net_t = runtime.denoiser_forward(model.dynamics, t_f / model.T, zt, node_mask, edge_mask)
+        net_0 = runtime.denoiser_forward(model.dynamics, zeros, z0, node_mask, edge_mask)
+        loss = _new(eps, B)
+        _call("gb_vlb_loss", _ptr(net_t), _ptr(eps), _ptr(net_0), _ptr(eps0), _ptr(z0), _ptr(xh), _ptr(mask), _ptr(t_f), _ptr(gamma),
+              int(model.T), _F(nv[0]), _F(nv[1]), _F(nb[1]), B, N, F, _ptr(loss), None)
+    return loss

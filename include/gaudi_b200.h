@@ -207,6 +207,11 @@ int gb_den_finish_fwd(const float* x_fin, const float* x_in, const float* h3, co
 int gb_make_zt(const float* x, const float* h, const float* mask, const float* eps, const float* gamma,
                const float* t_int, float norm_x, float norm_h, float bias_h, int B, int N, int F, float* xh, float* zt,
                float* gamma_t, void* stream);
+/* gb_vlb_loss: -log p(x,h) estimate of forward() in eval mode, compute_loss(t0_always = True) (en_diffusion.py:644-804):
+ * net_t / eps_t at (z_t, t_int in 1..T), net_0 / eps_0 / z0 at t = 0; gamma [T+1] schedule table; loss [B], error_out [B] or NULL. */
+int gb_vlb_loss(const float* net_t, const float* eps_t, const float* net_0, const float* eps_0, const float* z0,
+                const float* xh, const float* mask, const float* t_int, const float* gamma, int T, float norm_x,
+                float norm_h, float bias_h, int B, int N, int F, float* loss, float* error_out, void* stream);
 /* gb_pool_mean[_bwd]: pred [B,C] = mean over the N padded nodes of h [B*N,C] (edm/egnn_predictor/models.py:456-457). */
 int gb_pool_mean(const float* h, int B, int N, int C, float* pred, void* stream);
 int gb_pool_mean_bwd(const float* g_pred, int B, int N, int C, float* g_h, void* stream);

@@ -529,3 +529,39 @@ def sample_edm_t(cfg: DenoiserCfg, gamma: Tensor, x: Tensor, h_cat: Tensor, node
     xh = torch.cat([x / cfg.norm_values[0], (h_cat.float() - cfg.norm_biases[1]) / cfg.norm_values[1] * node_mask], dim=-1)
     g_t = gamma[torch.round(t * cfg.timesteps).long()].view(B, 1, 1)
     return torch.sqrt(torch.sigmoid(-g_t)) * xh + torch.sqrt(torch.sigmoid(g_t)) * eps
+
+
+def validation_nll(w: Weights, cfg: DenoiserCfg, gamma: Tensor, x: Tensor, h_cat: Tensor, node_mask: Tensor, edge_mask: Tensor,
+                   t_int: Tensor, eps: Tensor, eps0: Tensor) -> Tensor:
+    """-log p(x,h) estimate [B] of forward() in eval mode = compute_loss(t0_always=True) with its draws injected
+    (en_diffusion.py:644-775, 777-804; :517-531 log constants; :568-642 L0 term; :459-491 prior KL)."""
+    B, N, _ = x.shape
+    T = cfg.timesteps
+    d_sub = (node_mask.squeeze(2).sum(1) - 1) * 3
+    delta_log_px = -d_sub * np.log(cfg.norm_values[0])                 # normalize, :386-388
+    xh = torch.cat([x / cfg.norm_values[0], (h_cat.float() - cfg.norm_biases[1]) / cfg.norm_values[1] * node_mask], dim=2)
+    t, s = t_int / T, (t_int - 1) / T
+    g_t = gamma[torch.round(t * T).long()].view(B, 1, 1)
+    g_s = gamma[torch.round(s * T).long()].view(B, 1, 1)
+    z_t = torch.sqrt(torch.sigmoid(-g_t)) * xh + torch.sqrt(torch.sigmoid(g_t)) * eps
+    net_t = denoiser_forward(w, cfg, z_t, t, node_mask, edge_mask)
+    error = _sum_except_batch((eps - net_t) ** 2)                      # compute_error outside training: denom = 1
+    snr_w = (torch.exp(-(g_s - g_t)) - 1).squeeze(1).squeeze(1)
+    loss_t = 0.5 * snr_w * error
+    g_0 = gamma[0]
+    neg_log_constants = -(d_sub * (-(0.5 * g_0) - 0.5 * np.log(2 * np.pi)))
+    g_T = gamma[T].view(1, 1, 1).expand(B, 1, 1)
+    mu_T = torch.sqrt(torch.sigmoid(-g_T)) * xh
+    sig_T_x, sig_T_h = torch.sqrt(torch.sigmoid(g_T)).squeeze(), torch.sqrt(torch.sigmoid(g_T))
+    kl_h = _sum_except_batch((torch.log(1.0 / sig_T_h) + 0.5 * (sig_T_h ** 2 + mu_T[:, :, 3:] ** 2) - 0.5) * node_mask)
+    kl_x = d_sub * torch.log(1.0 / sig_T_x) + 0.5 * (d_sub * sig_T_x ** 2 + _sum_except_batch(mu_T[:, :, :3] ** 2)) - 0.5 * d_sub
+    z_0 = torch.sqrt(torch.sigmoid(-g_0)) * xh + torch.sqrt(torch.sigmoid(g_0)) * eps0
+    net_0 = denoiser_forward(w, cfg, z_0, torch.zeros(B, 1), node_mask, edge_mask)
+    log_p_x = -0.5 * _sum_except_batch((eps0[:, :, :3] - net_0[:, :, :3]) ** 2)
+    sigma_0_cat = torch.sqrt(torch.sigmoid(g_0)) * cfg.norm_values[1]
+    onehot = xh[:, :, 3:] * cfg.norm_values[1] + cfg.norm_biases[1]
+    centered = z_0[:, :, 3:] * cfg.norm_values[1] + cfg.norm_biases[1] - 1
+    log_prop = torch.log(_cdf_std_gaussian((centered + 0.5) / sigma_0_cat) - _cdf_std_gaussian((centered - 0.5) / sigma_0_cat) + 1e-10)
+    log_probs = log_prop - torch.logsumexp(log_prop, dim=2, keepdim=True)
+    loss_term_0 = -(log_p_x + _sum_except_batch(log_probs * onehot * node_mask))
+    return kl_x + kl_h + T * loss_t + neg_log_constants + loss_term_0 - delta_log_px

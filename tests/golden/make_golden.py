@@ -299,11 +299,43 @@ def predictor_train_step(dataset, nodesxsample, t_list, seed):
     return out
 
 
+def eval_nll(dataset, nodesxsample, t_list, seed):
+    """forward() of the reference in eval mode (the bound val_epoch reports, en_diffusion.py:777-804 with t0_always=True),
+    draws pinned: t_int (randint(1, T+1)), then eps for z_t, then eps_0 for z_0."""
+    args, model, pred, prop = build(dataset)
+    model.eval()
+    inner = model.module if hasattr(model, "module") else model
+    F_in = 1 if dataset == "cata" else 12
+    gen = torch.Generator().manual_seed(seed)
+    nm, em = ref_masks(args, nodesxsample)
+    B, N = nm.shape[0], nm.shape[1]
+    x = remove_mean_with_mask(torch.randn((B, N, 3), generator=gen) * 2.5 * nm, nm)
+    h = torch.nn.functional.one_hot(torch.randint(0, F_in, (B, N), generator=gen), F_in).float() * nm
+    t_int = torch.tensor(t_list, dtype=torch.int64).view(B, 1)
+    draws = [processed_noise(gen, (B, N, 3 + F_in), nm), processed_noise(gen, (B, N, 3 + F_in), nm)]
+    it = iter(draws)
+    real_randint = torch.randint
+    torch.randint = lambda *a, **k: t_int.clone()
+    inner.sample_combined_position_feature_noise = lambda n_samples, n_nodes, node_mask, std=1.0: next(it).clone()
+    try:
+        with torch.no_grad():
+            nll = model(x, {"categorical": h, "integer": torch.zeros(0)}, nm, em.view(B, N * N))
+    finally:
+        torch.randint = real_randint
+        del inner.sample_combined_position_feature_noise
+    return dict(nodesxsample=nodesxsample.numpy(), x=x.numpy(), h=h.numpy(), t_int=t_int.numpy(), eps=draws[0].numpy(),
+                eps0=draws[1].numpy(), nll=nll.numpy())
+
+
 def main():
     meta = {"torch": torch.__version__, "seed_denoiser": SEED_DEN, "seed_predictor": SEED_PRED,
             "prop_mean": MEAN5.tolist(), "prop_std": STD5.tolist()}
     steps = [1000, 999, 750, 500, 250, 2, 1]
 
+    if "--only-nll" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "nll_cata.npz"), **eval_nll("cata", torch.tensor([11, 10, 9, 11, 7, 2]), [1000, 613, 1, 2, 250, 77], seed=888))
+        np.savez_compressed(os.path.join(HERE, "nll_hetro.npz"), **eval_nll("hetro", torch.tensor([10, 8, 3]), [777, 1, 12], seed=889))
+        return
     if "--only-pred-train" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "pred_train_cata.npz"),
                             **predictor_train_step("cata", torch.tensor([11, 10, 9, 11, 7, 2]), [1000, 613, 0, 1, 250, 0], seed=666))
@@ -351,6 +383,8 @@ def main():
                         **predictor_train_step("cata", torch.tensor([11, 10, 9, 11, 7, 2]), [1000, 613, 0, 1, 250, 0], seed=666))
     np.savez_compressed(os.path.join(HERE, "pred_train_hetro.npz"),
                         **predictor_train_step("hetro", torch.tensor([10, 8, 3]), [777, 0, 12], seed=667))
+    np.savez_compressed(os.path.join(HERE, "nll_cata.npz"), **eval_nll("cata", torch.tensor([11, 10, 9, 11, 7, 2]), [1000, 613, 1, 2, 250, 77], seed=888))
+    np.savez_compressed(os.path.join(HERE, "nll_hetro.npz"), **eval_nll("hetro", torch.tensor([10, 8, 3]), [777, 1, 12], seed=889))
     print("train done", flush=True)
 
     with open(os.path.join(HERE, "meta.json"), "w") as f:

@@ -207,3 +207,45 @@ def test_predictor_training_step_matches_reference_golden(ds, gemm, monkeypatch)
     (gz,) = torch.autograd.grad(pred(z2, nm, em, t)[:, 1].sum(), z2)
     assert gz.shape == zt.shape and torch.isfinite(gz).all()
     print(f"[predictor train parity {ds} {gemm}] loss diff {abs(float(loss.detach()) - float(g['loss'])):.2e}, worst grad-norm rel {worst:.2e}")
+
+
+@pytest.mark.parametrize("ds", ["cata", "hetro"])
+def test_eval_mode_nll_matches_reference_golden(ds):
+    """forward() in eval mode: variational bound with two fused denoiser passes (en_diffusion.py:644-804, t0_always=True).
+    Tolerance: 1e-4 relative (the t-term multiplies the squared error by T/2 (SNR(gamma_s-gamma_t)-1), up to ~1e4)."""
+    dev = _dev()
+    g = golden(f"nll_{ds}.npz")
+    args, model, pred, prop = build_models(ds, dev)
+    model.eval()
+    nm, em = gb.build_masks(torch.from_numpy(g["nodesxsample"]), 11 if ds == "cata" else 10, ds == "hetro", device=dev)
+    x, h = torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["h"]).to(dev)
+    nll = model(x, {"categorical": h, "integer": torch.zeros(0, device=dev)}, nm, em, t_int=torch.from_numpy(g["t_int"]).to(dev),
+                eps=torch.from_numpy(g["eps"]).to(dev), eps0=torch.from_numpy(g["eps0"]).to(dev))
+    ref = torch.from_numpy(g["nll"])
+    rel = ((nll.cpu() - ref).abs() / ref.abs().clamp(min=1.0)).max()
+    print(f"[nll parity {ds}] worst relative error {float(rel):.2e}")
+    assert float(rel) <= 1e-4
+    assert torch.isfinite(model(x, {"categorical": h, "integer": torch.zeros(0, device=dev)}, nm, em)).all()   # own draws
+
+
+def test_sample_chain_frames():
+    """sample_chain (en_diffusion.py:1118-1174): frame k holds the un-normalised z of the last step written to it,
+    frame 0 the final (x, h); same injected noise as sample() gives the same molecules."""
+    dev = _dev()
+    args, model, pred, prop = build_models("cata", dev, timesteps=20)
+    T, keep = model.T, 5
+    nm, em = gb.build_masks(torch.tensor([11, 9, 4]), 11, False, device=dev)
+    B, N = nm.shape[:2]
+    torch.manual_seed(3)
+    noise = torch.stack([model.sample_combined_position_feature_noise(B, N, nm) for _ in range(T + 2)])
+    chain = model.sample_chain(B, N, nm, em, None, keep_frames=keep, noise=noise).view(keep, B, N, 4)
+    x, h = model.sample(B, N, nm, em, noise=noise)
+    assert maxabs(chain[0, :, :, :3], x) <= 1e-6 and torch.equal(chain[0, :, :, 3:], h["categorical"])
+    z = noise[0].clone()
+    frames = {}
+    for s in reversed(range(T)):
+        s_arr = torch.full((B, 1), s, device=dev) / T
+        z = model.sample_p_zs_given_zt(s_arr, s_arr + 1.0 / T, z, nm, em, None, noise=noise[T - s])
+        frames[(s * keep) // T] = torch.cat([z[:, :, :3] * model.norm_values[0], z[:, :, 3:] * model.norm_values[1] * nm], 2)
+    for k in range(1, keep):
+        assert maxabs(chain[k], frames[k]) <= 1e-6

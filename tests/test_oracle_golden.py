@@ -147,3 +147,17 @@ def test_predictor_training_loss_and_gradients_match_reference(ds):
         if k.startswith("grad:"):
             ref = torch.from_numpy(g[k])
             assert maxabs(w[k[5:]].grad, ref) <= 1e-6 * max(1.0, float(ref.abs().max())), k
+
+
+@pytest.mark.parametrize("ds", ["cata", "hetro"])
+def test_eval_mode_nll_matches_reference(ds):
+    """forward() in eval mode (compute_loss(t0_always=True), the bound val_epoch reports) with pinned draws."""
+    g = golden(f"nll_{ds}.npz")
+    args, model, pred, prop = build_models(ds, "cpu")
+    dcfg, _ = oracle_cfgs(ds)
+    wd, _ = cpu_weights(model, pred)
+    nm, em = O.build_masks(torch.from_numpy(g["nodesxsample"]), 11 if ds == "cata" else 10, ds == "hetro")
+    with torch.no_grad():
+        nll = O.validation_nll(wd, dcfg, O.gamma_table(dcfg), torch.from_numpy(g["x"]), torch.from_numpy(g["h"]), nm, em,
+                               torch.from_numpy(g["t_int"]).float(), torch.from_numpy(g["eps"]), torch.from_numpy(g["eps0"]))
+    assert maxabs(nll, g["nll"]) <= 1e-6 * float(np.abs(g["nll"]).max())
