@@ -251,3 +251,29 @@ def test_sharded_sampling_gathers_full_batch_world_size_2(tmp_path, ds):
                          env=env, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
     assert res.stdout.count("ok") == 2
+
+
+def test_training_loop_utilities(tmp_path):
+    """Queue / gradient_clipping (edm/utils.py:31-70) and the experiment-args loaders (utils/helpers.py:204-224)."""
+    import json
+    from gaudi_b200 import train_utils as TU
+    q = TU.Queue(max_len=3)
+    for v in (1.0, 2.0, 3.0, 4.0):
+        q.add(v)
+    assert q.items == [4.0, 3.0, 2.0] and len(q) == 3 and q.mean() == 3.0
+    lin = torch.nn.Linear(4, 4)
+    lin.weight.grad, lin.bias.grad = torch.full((4, 4), 10.0), torch.zeros(4)
+    q = TU.Queue()
+    q.add(1.0)                                    # allowed norm = 1.5 * 1 + 2 * 0
+    norm = TU.gradient_clipping(lin, q)
+    assert abs(float(norm) - 40.0) < 1e-4 and abs(float(lin.weight.grad.norm()) - 1.5) < 1e-4 and q.items[0] == 1.5
+    norm = TU.gradient_clipping(lin, q)            # now within 1.5 * mean + 2 * std: recorded as is
+    assert abs(q.items[0] - float(norm)) < 1e-6
+    a = gb.args_edm(dataset="hetro", nf=64)
+    d = {k: v for k, v in vars(a).items() if isinstance(v, (int, float, str, bool, list, tuple, type(None)))}
+    (tmp_path / "args.txt").write_text(json.dumps(d))
+    back = TU.get_edm_args(str(tmp_path))
+    assert back.restore is True and back.exp_dir == str(tmp_path) and back.nf == 64 and back.dataset == "hetro"
+    TU.save_model(lin, str(tmp_path / "m.pt"))
+    lin2 = TU.load_model(torch.nn.Linear(4, 4), str(tmp_path / "m.pt"))
+    assert torch.equal(lin2.weight, lin.weight) and not lin2.training
