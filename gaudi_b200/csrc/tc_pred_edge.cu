@@ -30,7 +30,23 @@ struct TcPredCfg {
     static constexpr int SCRATCH = 6 * NP * 4 + 4 * NPARTS * 128 * 4 + NPARTS * 128 * EF_STRIDE * 4 + 129 * 4 + 128 * 3 * 4 + 64 + 3 * 132 * 4;
     static constexpr int SMEM = S * STAGE_BYTES + 1024 + 256 + SCRATCH;
     static constexpr int D2_COL = 256;
+    // backward only: one extra producer warp streams the saved activations (16-column chunks of the float4 "Q layout",
+    // 4 planes x 128 rows x 16 B = 8 KB, contiguous in HBM) through a 4-slot ring that lives in the ef_s scratch area
+    static constexpr int BWD_THREADS = THREADS + 32;
+    static constexpr int SV_SLOTS = 4;
+    static constexpr int SV_SLOT_BYTES = 4 * 128 * 16;
+    static_assert(SV_SLOTS * SV_SLOT_BYTES <= NPARTS * 128 * EF_STRIDE * 4, "saved-activation ring must fit the ef scratch");
 };
+
+struct SvRing { unsigned char* buf; uint64_t* full; uint64_t* empty; };
+
+// consumer side of the saved-activation ring: wait for chunk q, return this row's first float4 (plane c at +128*c)
+__device__ __forceinline__ const float4* sv_acquire(const SvRing& sv, uint32_t q, int r) {
+    const uint32_t s = q & 3, rr = q >> 2;
+    mbar_wait(&sv.full[s], rr & 1);
+    return reinterpret_cast<const float4*>(sv.buf + s * 8192) + r;
+}
+__device__ __forceinline__ void sv_release(const SvRing& sv, uint32_t q) { mbar_arrive(&sv.empty[q & 3]); }
 
 template <int NPARTS>
 __device__ __forceinline__ float psum_parts(const float* red, int r) {
@@ -310,7 +326,7 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
 // backward (input gradient only)
 // ==================================================================================================================
 template <int NP>
-__global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_kernel(PredEdgeArgs a, const float* __restrict__ wcimg_nt,
+__global__ void __launch_bounds__(TcPredCfg<NP>::BWD_THREADS, 1) tc_pred_edge_bwd_kernel(PredEdgeArgs a, const float* __restrict__ wcimg_nt,
                                                                    const float* __restrict__ w2img_nt, int H) {
     using CF = TcPredCfg<NP>;
     extern __shared__ unsigned char smem_raw[];
@@ -318,20 +334,19 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::S * CF::STAGE_BYTES);
     TcPipe p{base, bars, bars + CF::S, bars + 2 * CF::S, CF::STAGE_BYTES, CF::S};
     uint64_t* d1_full = bars + 3 * CF::S; uint64_t* d2_full = d1_full + 1; uint64_t* d_empty = d2_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 1);
+    uint64_t* sv_full = d_empty + 1; uint64_t* sv_empty = sv_full + CF::SV_SLOTS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sv_empty + CF::SV_SLOTS);
     float* vec_s = reinterpret_cast<float*>(base + CF::S * CF::STAGE_BYTES + 256);    // [6][NP]: w_r, w_a, b2(unused), att_w, bc(unused), wc_last
     float* red_s = vec_s + 6 * NP;                                                       // [4][128]
-    float* ef_s = red_s + 4 * CF::NPARTS * 128;                                                       // [2][128][17]
+    float* ef_s = red_s + 4 * CF::NPARTS * 128;                                          // saved-activation ring (4 x 8 KB)
     int* seg_s = reinterpret_cast<int*>(ef_s + CF::NPARTS * 128 * CF::EF_STRIDE);
-    float* gd_s = reinterpret_cast<float*>(seg_s + 129);                                 // [128][3]
-    int* cperm_s = reinterpret_cast<int*>(gd_s + 3 * 128);                               // [128] rows grouped by column node
-    int* tcs_s = cperm_s + 132;                                                          // [<=129] group starts (tile local)
-    int* tcn_s = tcs_s + 132;                                                            // [<=128] column node of each group
+    const SvRing sv{reinterpret_cast<unsigned char*>(ef_s), sv_full, sv_empty};
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < CF::S; ++s) { mbar_init(&p.full_a[s], 256); mbar_init(&p.full_w[s], 1); mbar_init(&p.empty[s], 1); }
         mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d_empty, CF::NWORK);
+        for (int s = 0; s < CF::SV_SLOTS; ++s) { mbar_init(&sv_full[s], 1); mbar_init(&sv_empty[s], 128); }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -364,14 +379,34 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
                 mma_commit(d2_full);
             }
         }
+    } else if (warp == 2 + 4 * CF::NPARTS) {
+        // saved-activation producer: per tile the chunks of d3 (GEMM-1 operand), pre2 (epilogue 1), pre2 again (GEMM-2
+        // operand) and d1 (epilogue 2), in the order the worker parts consume them
+        if (lane == 0) {
+            const int nchunks = (H + 15) / 16, planes = H / 4;
+            uint32_t q = 0;
+            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+#pragma unroll 1
+                for (int ph = 0; ph < 4; ++ph) {
+                    const float* src = (ph == 0 ? a.sv_d3 : (ph == 3 ? a.sv_d1 : a.sv_pre2)) + (size_t)tile * planes * 512;
+                    for (int ch = 0; ch < nchunks; ++ch, ++q) {
+                        const uint32_t s = q & 3, rr = q >> 2;
+                        const uint32_t bytes = (uint32_t)min(4, planes - 4 * ch) * 2048u;
+                        if (rr > 0) mbar_wait(&sv_empty[s], (rr - 1) & 1);
+                        mbar_arrive_expect_tx(&sv_full[s], bytes);
+                        bulk_g2s(sv.buf + s * CF::SV_SLOT_BYTES, src + (size_t)ch * 2048, bytes, &sv_full[s]);
+                    }
+                }
+            }
+        }
     } else {
         const int group = warp & 3, part = (warp - 2) >> 2, half = part & 1;
         const int r = group * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(group * 32) << 16);
         const int nchunks = (H + 15) / 16;
-        float* my_ef = ef_s + part * 128 * CF::EF_STRIDE;
         uint32_t tcnt = 0;
         for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
+            const uint32_t q0 = tcnt * 4 * nchunks;                 // first saved-activation chunk of this tile
             const int node_lo = g.tile_ptr[tile], node_hi = g.tile_ptr[tile + 1];
             const int nn = node_hi - node_lo;
             const int e_lo = g.rowptr[node_lo], ne = g.rowptr[node_hi] - e_lo;
@@ -396,17 +431,21 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
             // ---- GEMM 1 operand: g_pre3 = g_phi * w_c * SiLU'(pre3) ----
             for (int j = part >> 1; j < na; j += CF::NPARTS / 2) {
                 float4 x[4];
+                const int ch = 2 * j + half;
+                const bool have = ch < nchunks;
+                const float4* d3p = have ? sv_acquire(sv, q0 + ch, r) : nullptr;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int k0 = j * ATOM_K + 16 * half + 4 * c;
                     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (k0 < H) {
-                        const float4 d3 = __ldg(reinterpret_cast<const float4*>(a.sv_d3 + (((size_t)tile * (H / 4) + (k0 >> 2)) * 128 + r) * 4));
+                        const float4 d3 = d3p[c * 128];
                         const float4 wl = *reinterpret_cast<const float4*>(vec_s + 5 * NP + k0);
                         t = make_float4(gphi * wl.x * d3.x, gphi * wl.y * d3.y, gphi * wl.z * d3.z, gphi * wl.w * d3.w);
                     }
                     x[c] = t;
                 }
+                if (have) sv_release(sv, q0 + ch);
                 put_chunk<NP>(p, it0 + j, r, half, x);
             }
             // ---- epilogue 1: g_ef = coordinate branch + aggregation branch; attention backward ----
@@ -420,12 +459,13 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
                 const int ch = part + CF::NPARTS * ci;
                 if (ch < nchunks) {
                     tmem_ld16(lane_addr + ch * 16, gef[ci]);
+                    const float4* p2p = sv_acquire(sv, q0 + nchunks + ch, r);
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         const int c0 = ch * 16 + 4 * c4;
                         if (c0 < H) {
                             const float4 ga = __ldg(reinterpret_cast<const float4*>(ga_row + c0));
-                            const float4 p2 = __ldg(reinterpret_cast<const float4*>(a.sv_pre2 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4));
+                            const float4 p2 = p2p[c4 * 128];
                             const float gadd[4] = {ga.x, ga.y, ga.z, ga.w};
                             const float pv[4] = {p2.x, p2.y, p2.z, p2.w};
 #pragma unroll
@@ -438,6 +478,7 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
                             }
                         }
                     }
+                    sv_release(sv, q0 + nchunks + ch);
                 }
             }
             red_s[part * 128 + r] = plog;
@@ -454,12 +495,13 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
                 const int ch = part + CF::NPARTS * ci;
                 if (ch < 2 * na) {
                     float4 x[4];
+                    const float4* p2p = ch < nchunks ? sv_acquire(sv, q0 + 2 * nchunks + ch, r) : nullptr;
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         const int c0 = ch * 16 + 4 * c4;
                         float t[4] = {0.f, 0.f, 0.f, 0.f};
                         if (ch < nchunks && c0 < H && valid) {
-                            const float4 p2 = __ldg(reinterpret_cast<const float4*>(a.sv_pre2 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4));
+                            const float4 p2 = p2p[c4 * 128];
                             const float pv[4] = {p2.x, p2.y, p2.z, p2.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
@@ -467,6 +509,7 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
                         }
                         x[c4] = make_float4(t[0], t[1], t[2], t[3]);
                     }
+                    if (ch < nchunks) sv_release(sv, q0 + 2 * nchunks + ch);
                     put_chunk<NP>(p, it0 + na + (ch >> 1), r, half, x);
                 }
             }
@@ -481,11 +524,12 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
             for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
                 float v[16];
                 tmem_ld16(lane_addr + CF::D2_COL + ch * 16, v);
+                const float4* d1p = sv_acquire(sv, q0 + 3 * nchunks + ch, r);
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
                     const int c0 = ch * 16 + 4 * c4;
                     if (c0 < H) {
-                        const float4 d1 = __ldg(reinterpret_cast<const float4*>(a.sv_d1 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4));
+                        const float4 d1 = d1p[c4 * 128];
                         const float4 gp = make_float4(v[4 * c4] * d1.x, v[4 * c4 + 1] * d1.y, v[4 * c4 + 2] * d1.z, v[4 * c4 + 3] * d1.w);
                         const float4 wr = *reinterpret_cast<const float4*>(vec_s + c0);
                         const float4 wa = *reinterpret_cast<const float4*>(vec_s + NP + c0);
@@ -494,6 +538,7 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ke
                         if (valid) *reinterpret_cast<float4*>(gp_row + c0) = gp;
                     }
                 }
+                sv_release(sv, q0 + 3 * nchunks + ch);
             }
             fence_before_sync();
             mbar_arrive(d_empty);
@@ -531,7 +576,7 @@ static void launch_bwd_t(const PredEdgeArgs& a, const float* wcimg_nt, const flo
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = a.g.n_tiles < sms ? a.g.n_tiles : sms;
-    tc_pred_edge_bwd_kernel<NP><<<grid, CF::THREADS, CF::SMEM, s>>>(a, wcimg_nt, w2img_nt, H);
+    tc_pred_edge_bwd_kernel<NP><<<grid, CF::BWD_THREADS, CF::SMEM, s>>>(a, wcimg_nt, w2img_nt, H);
 }
 
 void launch_pred_edge_bwd_tc(int H, const PredEdgeArgs& a, const float* wcimg_nt, const float* w2img_nt, cudaStream_t s) {
