@@ -36,6 +36,15 @@ def _gemm(mode: int, M: int, N: int, K: int, A, lda, B, ldb, Cm, ldc, bias=None,
     _call("gb_gemm", mode, M, N, K, _ptr(A), lda, _ptr(B), ldb, _ptr(Cm), ldc, _ptr(bias), int(acc))
 
 
+def _wgrad(G, X, out, M: int, N: int, K: int) -> None:
+    """out[M,N] (a view into a weight-gradient tensor, row stride out.stride(0)) = G[K,M]^T X[K,N]."""
+    if (_TC and M <= 256 and N <= 256 and M % 4 == 0 and N % 4 == 0 and G.stride(0) % 4 == 0 and X.stride(0) % 4 == 0
+            and G.data_ptr() % 16 == 0 and X.data_ptr() % 16 == 0):
+        _call("gb_wgrad", K, M, N, _ptr(G), G.stride(0), _ptr(X), X.stride(0), _ptr(out), out.stride(0), 0)
+    else:
+        _gemm(2, M, N, K, G, G.stride(0), X, X.stride(0), out, out.stride(0))
+
+
 def _colsum(X, M: int, N: int, w=None) -> torch.Tensor:
     out = torch.empty(N, dtype=torch.float32, device=X.device)
     _call("gb_colsum", _ptr(X), N, M, N, _ptr(w), _ptr(out), 0)
@@ -122,7 +131,7 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = _linear(gy, W, N, K, transpose=True)
         gW = _new(gy, N, K)
-        _gemm(2, N, K, M, gy, N, x, K, gW, K)
+        _wgrad(gy, x, gW, N, K, M)
         gb = _colsum(gy, M, N) if ctx.has_bias else None
         return gx, gW, gb, None, None
 
@@ -182,15 +191,15 @@ class _EdgeMLP(torch.autograd.Function):
         s1 = _new(h, E, H)
         _call("gb_silu_fwd", _ptr(pre1), _ptr(s1), E * H)
         gW2 = _new(h, H, H)
-        _gemm(2, H, H, E, G2, H, s1, H, gW2, H)
+        _wgrad(G2, s1, gW2, H, H, E)
         gb2 = _colsum(G2, E, H)
         del s1
         G1 = _linear(G2, W2, H, H, transpose=True, epi=EPI_MUL_DSILU, aux=pre1)
         gPa, gPb = _new(h, n, H), _new(h, n, H)
         _call("gb_rowcol_reduce", g.handle, _ptr(G1), H, _F(1.0), _ptr(gPa), _ptr(gPb))
         gW1 = _new(h, H, ld1)
-        _gemm(2, H, H, n, gPa, H, h, H, gW1, ld1)
-        _gemm(2, H, H, n, gPb, H, h, H, gW1[:, H:], ld1)
+        _wgrad(gPa, h, gW1, H, H, n)
+        _wgrad(gPb, h, gW1[:, H:], H, H, n)
         gW1[:, 2 * H].copy_(_colsum(G1, E, H, r))
         gW1[:, 2 * H + 1].copy_(_colsum(G1, E, H, d0))
         gb1 = _colsum(gPa, n, H)
@@ -328,12 +337,12 @@ class _NodeMLP(torch.autograd.Function):
         gt = _new(h, n, H)
         _call("gb_resmask", _ptr(_c(g_out)), None, _ptr(mask), n, H, _ptr(gt))
         gW4 = _new(h, H, H)
-        _gemm(2, H, H, n, gt, H, sn, H, gW4, H)
+        _wgrad(gt, sn, gW4, H, H, n)
         gb4 = _colsum(gt, n, H)
         gpre = _linear(gt, W4, H, H, transpose=True, epi=EPI_MUL_DSILU, aux=pre)
         gW3 = _new(h, H, 2 * H)
-        _gemm(2, H, H, n, gpre, H, h, H, gW3, 2 * H)
-        _gemm(2, H, H, n, gpre, H, agg, H, gW3[:, H:], 2 * H)
+        _wgrad(gpre, h, gW3, H, H, n)
+        _wgrad(gpre, agg, gW3[:, H:], H, H, n)
         gb3 = _colsum(gpre, n, H)
         gh = _linear(gpre, W3, H, H, transpose=True, epi=EPI_ADD, aux=gt)      # residual branch + gpre W3[:, :H]
         gagg = _linear(gpre, W3[:, H:], H, H, transpose=True)

@@ -176,6 +176,10 @@ size_t gb_linear_scratch_bytes(int N, int K1, int K2);
 int gb_linear(int M, int N, int K1, int K2, const float* A1, int lda1, const float* A2, int lda2, const float* W, int ldw,
               int transpose_w, const float* bias, int epi, float* out, float* out2, const float* res_or_aux,
               const float* mask, void* wimg, size_t wimg_bytes, void* stream);
+ /* gb_wgrad: C[M,N] (+)= G[K,M]^T X[K,N] on tcgen05 (3xTF32, both operands read row-major = MN-major, reduction split
+  * across CTAs, fp32 atomics into C).  M, N <= 256 and multiples of 4; ldg, ldx multiples of 4; 16-byte aligned G, X. */
+int gb_wgrad(int K, int M, int N, const float* G, int ldg, const float* X, int ldx, float* C, int ldc, int accumulate,
+             void* stream);
 int gb_gemm(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
             const float* bias, int accumulate, void* stream);
 int gb_colsum(const float* X, int ld, int M, int N, const float* w, float* out, int accumulate, void* stream);
