@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=32)
+    ap.add_argument("--graph", action="store_true", help="capture the whole step (loss, backward, AdamW) in one CUDA graph and replay it")
     ap.add_argument("--model", choices=["denoiser", "predictor"], default="denoiser",
                     help="denoiser: EDM l2 loss (train_edm.py); predictor: l1 property loss on z_t (train_cond_predictor.py)")
     args = ap.parse_args()
@@ -49,7 +50,7 @@ def main():
             p_.requires_grad_(True)
         pred.train()
         y = torch.randn(B, 5, device=dev)
-        opt = torch.optim.AdamW(pred.parameters(), lr=1e-3, amsgrad=True, weight_decay=1e-12)
+        opt = torch.optim.AdamW(pred.parameters(), lr=1e-3, amsgrad=True, weight_decay=1e-12, capturable=args.graph)
 
         def step():
             opt.zero_grad()
@@ -60,7 +61,8 @@ def main():
             opt.step()
             return loss
     else:
-        opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, amsgrad=True, weight_decay=1e-12)
+        opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, amsgrad=True, weight_decay=1e-12,
+                                capturable=args.graph)
 
         def step():
             opt.zero_grad()
@@ -69,6 +71,23 @@ def main():
             opt.step()
             return loss
 
+    eager_step = step
+    if args.graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                eager_step()
+        torch.cuda.current_stream().wait_stream(side)
+        cg = torch.cuda.CUDAGraph()
+        lc = _lib.lib().gb_launch_count(0)
+        with torch.cuda.graph(cg):
+            static_loss = eager_step()
+        captured = _lib.lib().gb_launch_count(0) - lc          # our kernels inside one replay
+
+        def step():
+            cg.replay()
+            return static_loss
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -84,7 +103,8 @@ def main():
            "workload": "EDM training step (l2 denoising loss fwd+bwd+AdamW), cc-PBH shape, synthetic batch" if args.model == "denoiser"
            else "property-predictor training step (sample_edm_t + l1 loss fwd+bwd+AdamW), cc-PBH shape, synthetic batch",
            "batch": B, "edges": int(em.sum().item()), "ms_per_step": ms, "molecules_per_s": B / (ms * 1e-3),
-           "gpu_launches_per_step": (_lib.lib().gb_launch_count(0) - l0) / args.steps, "loss": float(loss.detach())}
+           "gpu_launches_per_step": captured if args.graph else (_lib.lib().gb_launch_count(0) - l0) / args.steps, "loss": float(loss.detach()),
+           "cuda_graph": bool(args.graph)}
     if not args.no_cpu and args.model == "predictor":
         import gaudi_oracle as O
         cb = args.cpu_batch

@@ -53,7 +53,9 @@ void launch_lin(int HP, const LinArgs& a, cudaStream_t s);
 void launch_lin_tc(int H, const LinArgs& a, const float* wimg, cudaStream_t s);
 int tc_np(int H);
 // C[m][n] += sum_e G[e][m] X[e][n] on tcgen05 (both operands MN-major, 3xTF32); C must be zeroed / hold the value to add to
-void launch_wgrad_tc(int K, int M, int N, const float* G, int ldg, const float* X, int ldx, float* C, int ldc, cudaStream_t s);
+void launch_wgrad_tc(int K, int M, int N, const float* G, int ldg, const float* X, int ldx, float* C, int ldc, int accumulate,
+                     float* scratch, cudaStream_t s);
+size_t wgrad_tc_scratch_bytes(int M, int N);
 void launch_pack_tc(float* dst, const float* src, int ld, int k_off, int n_off, int Kv, int Nv, int NP, int atoms, int transpose, cudaStream_t s);
 
 // tiny-K input embedding of both networks:  h0 = W [feat*mask , t] + b ;  x = z[:, :3]*mask

@@ -40,7 +40,7 @@ __device__ __forceinline__ uint32_t idesc_tf32_mn(int N) {      // TF32 x TF32 -
 
 __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(int K, int M, int N, const float* __restrict__ G, int ldg,
                                                                 const float* __restrict__ X, int ldx, float* __restrict__ C, int ldc,
-                                                                int kt_per_cta) {
+                                                                int kt_per_cta, float* __restrict__ partial) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(base + WG_STAGES * WG_STAGE);
@@ -126,10 +126,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(int K, int M, i
                     float v[16];
                     tmem_ld16(taddr + ch * 16, v);
                     if (m < M) {
-                        float* crow = C + (size_t)m * ldc + ch * 16;
+                        if (partial) {                    // deterministic two-phase reduction: this CTA's slab [M][NP]
+                            float4* prow = reinterpret_cast<float4*>(partial + ((size_t)blockIdx.x * M + m) * NP + ch * 16);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (ch * 16 + j < N) atomicAdd(crow + j, v[j]);
+                            for (int j = 0; j < 4; ++j) prow[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+                            float* crow = C + (size_t)m * ldc + ch * 16;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (ch * 16 + j < N) atomicAdd(crow + j, v[j]);
+                        }
                     }
                 }
             }
@@ -140,22 +146,45 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(int K, int M, i
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-void launch_wgrad_tc(int K, int M, int N, const float* G, int ldg, const float* X, int ldx, float* C, int ldc, cudaStream_t s) {
+// C[m][n] = (accumulate ? C : 0) + sum over the CTA slabs, fixed order
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_slabs, int M, int N, int NP, float* __restrict__ C, int ldc,
+                                    int accumulate) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M * N; i += gridDim.x * blockDim.x) {
+        const int m = i / N, n = i - m * N;
+        float s0 = 0.f, s1 = 0.f;
+        int g = 0;
+        for (; g + 1 < n_slabs; g += 2) {
+            s0 += partial[((size_t)g * M + m) * NP + n];
+            s1 += partial[((size_t)(g + 1) * M + m) * NP + n];
+        }
+        if (g < n_slabs) s0 += partial[((size_t)g * M + m) * NP + n];
+        float* c = C + (size_t)m * ldc + n;
+        *c = (accumulate ? *c : 0.f) + (s0 + s1);
+    }
+}
+
+size_t wgrad_tc_scratch_bytes(int M, int N) { return (size_t)148 * M * ((N + 15) & ~15) * sizeof(float); }
+
+// scratch (>= wgrad_tc_scratch_bytes) selects the deterministic two-phase reduction; without it C must hold the value to add
+// to (zero or the accumulation target) and the CTAs add their partial sums with fp32 atomics
+void launch_wgrad_tc(int K, int M, int N, const float* G, int ldg, const float* X, int ldx, float* C, int ldc, int accumulate,
+                     float* scratch, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
         configured = true;
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_kt = (K + WG_KT - 1) / WG_KT;
-    int grid = n_kt / 8;                                  // at least 128 reduction rows per CTA: the epilogue costs M x N atomics
+    int grid = n_kt / 8;                                  // at least 128 reduction rows per CTA
     if (grid < 1) grid = 1;
-    if (grid > sms) grid = sms;
+    if (grid > 148) grid = 148;
     const int per = (n_kt + grid - 1) / grid;
     grid = (n_kt + per - 1) / per;
-    tc_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM, s>>>(K, M, N, G, ldg, X, ldx, C, ldc, per);
+    tc_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM, s>>>(K, M, N, G, ldg, X, ldx, C, ldc, per, scratch);
+    if (scratch) {
+        const int total = M * N;
+        wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(scratch, grid, M, N, (N + 15) & ~15, C, ldc, accumulate);
+    }
 }
 
 }  // namespace gb

@@ -40,7 +40,11 @@ def _wgrad(G, X, out, M: int, N: int, K: int) -> None:
     """out[M,N] (a view into a weight-gradient tensor, row stride out.stride(0)) = G[K,M]^T X[K,N]."""
     if (_TC and M <= 256 and N <= 256 and M % 4 == 0 and N % 4 == 0 and G.stride(0) % 4 == 0 and X.stride(0) % 4 == 0
             and G.data_ptr() % 16 == 0 and X.data_ptr() % 16 == 0):
-        _call("gb_wgrad", K, M, N, _ptr(G), G.stride(0), _ptr(X), X.stride(0), _ptr(out), out.stride(0), 0)
+        nbytes = _lib.lib().gb_wgrad_scratch_bytes(M, N)
+        key = ("wgrad", G.device.index)
+        if key not in _scratch or _scratch[key].numel() < nbytes:
+            _scratch[key] = torch.empty(nbytes, dtype=torch.uint8, device=G.device)
+        _call("gb_wgrad", K, M, N, _ptr(G), G.stride(0), _ptr(X), X.stride(0), _ptr(out), out.stride(0), 0, _ptr(_scratch[key]), nbytes)
     else:
         _gemm(2, M, N, K, G, G.stride(0), X, X.stride(0), out, out.stride(0))
 
