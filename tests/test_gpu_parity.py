@@ -8,6 +8,7 @@ import pytest
 import torch
 
 import gaudi_b200 as gb
+from gaudi_b200 import runtime
 import gaudi_oracle as O
 from helpers import (build_models, cpu_weights, golden, maxabs, oracle_cfgs, oracle_target, product_target)
 
@@ -219,3 +220,31 @@ def test_less_travelled_paths_fix_noise_hetro_unconditional_and_per_molecule_tim
     t = torch.tensor([[0.1], [0.5], [0.9]])
     assert maxabs(model.phi(z.to(dev), t.to(dev), nm, em, None), O.denoiser_forward(wd, dcfg, z, t, nm.cpu(), em.cpu())) <= TOL
     assert maxabs(pred(z.to(dev), nm, em, t.to(dev)), O.predictor_forward(wp, pcfg, z, nm.cpu(), em.cpu(), t)) <= TOL
+
+
+@pytest.mark.parametrize("dataset,reps", [("cata", 2000), ("hetro", 4167)])
+def test_full_size_batch_replicas_are_identical_and_match_golden(dataset, reps):
+    """BASELINE sizes (configs 2 / 3: 10 000 cc-PBH molecules, 12 500 PASs molecules per GPU) through a size-independent
+    property: molecules are independent, so a batch made of `reps` copies of the golden molecules (ragged sizes, so tiles
+    cut the copies at different offsets) must give every copy the golden's guided step -- bit-identically across copies."""
+    dev = _dev()
+    g = golden(f"step_{dataset}.npz")
+    args, model, pred, prop = build_models(dataset, dev)
+    tf = product_target(dataset, pred, prop, True)
+    nm0, em0 = torch.from_numpy(g["node_mask"]), torch.from_numpy(g["edge_mask"])
+    b0, N = nm0.shape[0], nm0.shape[1]
+    B = b0 * reps
+    nm = nm0.repeat(reps, 1, 1).to(dev)
+    em = em0.view(b0, N * N).repeat(reps, 1).reshape(-1, 1).to(dev)
+    t = 500
+    zt = torch.from_numpy(g[f"zt_{t}"]).repeat(reps, 1, 1).to(dev)
+    noise = torch.from_numpy(g[f"noise_{t}"]).repeat(reps, 1, 1).to(dev)
+    s_arr = torch.full((B, 1), t - 1, device=dev) / model.T
+    t_arr = torch.full((B, 1), t, device=dev) / model.T
+    out = model.sample_p_zs_given_zt_guidance(s_arr, t_arr, zt, nm, em, tf, float(g["scale"]), noise=noise, return_parts=True)
+    for k in ("eps", "grad_raw", "zs"):
+        v = out[k].view(reps, b0, N, -1)
+        assert torch.equal(v, v[:1].expand_as(v)), f"{k}: copies differ"
+        assert maxabs(v[0], g[f"{k}_{t}"]) <= TOL, k
+    runtime.release_workspaces()
+    torch.cuda.empty_cache()
