@@ -279,3 +279,27 @@ def test_tensor_core_wgrad_matches_fp64():
         _lib.check(L.gb_wgrad(K, M, N, training._ptr(G), Gf.stride(0), training._ptr(X), Xf.stride(0), training._ptr(Cf), N, 0,
                               training._ptr(scratch), nbytes, training._stream()))
         assert torch.equal(Cf, results[0])                 # the two-phase path is bit-reproducible
+
+
+def test_fit_loop_checkpoints_the_best_validation_epoch(tmp_path):
+    """train_edm.main's loop (train_epoch / val_epoch / best-val checkpoint) on a tiny synthetic loader."""
+    from gaudi_b200 import train_utils as TU
+    dev = _dev()
+    args, model = _train_model("cata", dev, hidden=(64, 64), layers=(2, 2))
+    torch.manual_seed(9)
+
+    def make_batch(sizes):
+        nm, em = gb.build_masks(torch.tensor(sizes), 11, False)
+        B, N = nm.shape[:2]
+        x = torch.randn(B, N, 3) * 2.0 * nm
+        return x, nm.squeeze(2), em.view(B, N, N), torch.ones(B, N, 1) * nm, torch.zeros(B)
+    train = [make_batch([11, 10, 9, 8]), make_batch([11, 11, 7, 5])]
+    val = [make_batch([10, 9, 11, 6])]
+    torch.manual_seed(10)
+    out = TU.fit(model, train, val, dev, num_epochs=3, lr=1e-3, exp_dir=str(tmp_path))
+    assert len(out["history"]) == 3 and all(np.isfinite(h["train_loss"]) and np.isfinite(h["val_loss"]) for h in out["history"])
+    assert (tmp_path / "model.pt").exists()
+    best = min(out["history"], key=lambda h: h["val_loss"])
+    assert out["best_epoch"] == best["epoch"] and abs(out["best_val_loss"] - best["val_loss"]) < 1e-9
+    sd = torch.load(str(tmp_path / "model.pt"))
+    assert all(torch.equal(v.cpu(), model.state_dict()[k].cpu()) for k, v in sd.items())      # best weights restored
