@@ -253,6 +253,36 @@ def test_sharded_sampling_gathers_full_batch_world_size_2(tmp_path, ds):
     assert res.stdout.count("ok") == 2
 
 
+_GRAD_WORKER = r"""
+import os, sys, torch, torch.distributed as tdist
+sys.path.insert(0, os.environ["GB_ROOT"])
+from gaudi_b200 import dist
+tdist.init_process_group("gloo")
+rank, ws = tdist.get_rank(), tdist.get_world_size()
+torch.manual_seed(0)
+lin = torch.nn.Linear(5, 3)
+frozen = torch.nn.Parameter(torch.zeros(2), requires_grad=False)
+lin.weight.grad = torch.full((3, 5), float(rank + 1))
+lin.bias.grad = torch.arange(3.0) * (rank + 1)
+n = dist.average_gradients(list(lin.parameters()) + [frozen])
+assert n == 18
+assert torch.allclose(lin.weight.grad, torch.full((3, 5), 1.5)) and torch.allclose(lin.bias.grad, torch.arange(3.0) * 1.5)
+tdist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_gradient_averaging_world_size_2(tmp_path):
+    script = tmp_path / "gworker.py"
+    script.write_text(_GRAD_WORKER)
+    env = dict(os.environ, GB_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29535")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29535", str(script)],
+                         env=env, capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert res.stdout.count("ok") == 2
+
+
 def test_training_loop_utilities(tmp_path):
     """Queue / gradient_clipping (edm/utils.py:31-70) and the experiment-args loaders (utils/helpers.py:204-224)."""
     import json
