@@ -1,16 +1,22 @@
 // Tensor-core (tcgen05, 3xTF32) version of the node-level fused Linear kernel -- same contract as lin_kernel.cu.
 //
-// Warp roles (one persistent CTA per SM, 576 threads):
-//   warp 0      TMA producer: streams the pre-swizzled hi/lo weight K-atoms (one 1-D bulk copy per atom)
-//   warp 1      MMA issuer: 3 tcgen05.mma (lo*hi, hi*lo, hi*hi) per 8-wide K step, accumulator [128 x NP] fp32 in TMEM
-//   warps 2-17  workers, thread = tile row (four parts of 4 warps, each part covers all 128 TMEM lanes; part p owns the
-//               16-column chunks ch == p mod 4): build the A K-atoms (global row -> hi/lo split -> 128B-swizzled smem),
-//               then run the epilogue on their chunks read back with tcgen05.ld.
+// Warp roles (one persistent CTA per SM, 576 threads), chosen from a clock64 timeline of the first version (thread = row for
+// everything, one accumulator): per 128-row tile the MMAs take 4.7 us but the tile took 13.7 us, because the same threads
+// first waited for their A rows (2.3 us), then for the MMAs, then ran a 7 us epilogue whose 16-byte-per-row accesses cost
+// 32 L1 tag lookups per warp instruction.  Now the three phases overlap:
+//   warp 0       TMA producer: streams the pre-swizzled hi/lo weight K-atoms (one 1-D bulk copy per atom)
+//   warp 1       MMA issuer: 3 tcgen05.mma (lo*hi, hi*lo, hi*hi) per 8-wide K step into one of TWO [128 x NP] fp32 accumulators
+//   warps 2-9    A builders: 8 consecutive lanes read the 128 bytes of one row of a K-atom (4 full lines per warp load), split
+//                hi/lo and store to the 128B-swizzled image; the loads of the next two atoms (also across tiles) are in flight
+//                while the current one is stored, so the builders run ahead of the MMA warp, throttled only by the ring
+//   warps 10-17  epilogue: two parts of 4 warps (a part covers the 128 TMEM lanes; part p owns the 16-column chunks
+//                ch == p mod 2).  tcgen05.ld gives thread = row; the chunk is transposed through a per-warp shared-memory
+//                block so that bias / side input / output accesses are 8 rows x 64 contiguous bytes per warp instruction.
+//                The epilogue of tile t runs while the MMAs of tile t+1 fill the other accumulator.
 #include "tc_common.cuh"
 #include "kernels.h"
 
-#ifndef GB_LIN_NPARTS
-#define GB_LIN_NPARTS 4     // worker parts of 4 warps
+#ifndef GB_LIN_S
 #define GB_LIN_S 2          // operand ring stages
 #define GB_LIN_CTAS 1       // CTAs per SM
 #endif
@@ -24,11 +30,16 @@ struct TcLinCfg {
     static constexpr int A_BYTES = 128 * ATOM_ROW_BYTES;
     static constexpr int W_BYTES = NP * ATOM_ROW_BYTES;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-    static constexpr int SMEM = S * STAGE_BYTES + 1024 + 256;
-    static constexpr int TMEM_COLS = 256;
-    static constexpr int NPARTS = GB_LIN_NPARTS;                          // worker parts of 4 warps; part p owns 16-column chunks ch == p (mod 4)
-    static constexpr int NWORK = 128 * NPARTS;
-    static constexpr int THREADS = 64 + NWORK;
+    static constexpr int TMEM_COLS = 512;                 // two accumulators at columns 0 and 256
+    static constexpr int NBUILD = 256;                    // warps 2-9
+    static constexpr int EPARTS = 2;                      // warps 10-17
+    static constexpr int NEPI = 128 * EPARTS;
+    static constexpr int THREADS = 64 + NBUILD + NEPI;
+    static constexpr int STG_PITCH = 20;                  // floats per staged row: conflict-free float4 writes by row
+    static constexpr int STG_WARP_BYTES = 32 * STG_PITCH * 4;
+    static constexpr int BAR_BYTES = 1024 + 256;
+    static constexpr int SMEM = S * STAGE_BYTES + BAR_BYTES + (NEPI / 32) * STG_WARP_BYTES + NP * 4;
+    static_assert(SMEM <= 232448, "shared memory budget");
 };
 
 template <int NP>
@@ -38,23 +49,26 @@ __global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, GB_LIN_CTAS) tc_lin_ker
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::S * CF::STAGE_BYTES);
     uint64_t* full_a = bars; uint64_t* full_w = bars + CF::S; uint64_t* empty = bars + 2 * CF::S;
-    uint64_t* d_full = bars + 3 * CF::S; uint64_t* d_empty = d_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 1);
+    uint64_t* d_full = bars + 3 * CF::S; uint64_t* d_empty = d_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+    float* stg_all = reinterpret_cast<float*>(base + CF::S * CF::STAGE_BYTES + CF::BAR_BYTES);
+    float* bias_s = stg_all + (CF::NEPI / 32) * (CF::STG_WARP_BYTES / 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cb = blockIdx.y;
     if (tid == 0) {
-        for (int s = 0; s < CF::S; ++s) { mbar_init(&full_a[s], 256); mbar_init(&full_w[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(d_full, 1); mbar_init(d_empty, CF::NWORK);
+        for (int s = 0; s < CF::S; ++s) { mbar_init(&full_a[s], CF::NBUILD); mbar_init(&full_w[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&d_full[b], 1); mbar_init(&d_empty[b], CF::NEPI); }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<CF::TMEM_COLS>(tmem_slot);
+    for (int i = tid; i < NP; i += blockDim.x) bias_s[i] = (a.bias && i < H) ? a.bias[(size_t)cb * H + i] : 0.f;
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
     const int n_tiles = (a.M + 127) / 128;
-    const int cb = blockIdx.y;
     const int na1 = (a.K1 + ATOM_K - 1) / ATOM_K, na2 = (a.K2 + ATOM_K - 1) / ATOM_K, na = na1 + na2;
     const size_t atom_floats = (size_t)2 * NP * ATOM_K;
     const float* wcb = wimg + (size_t)cb * na * atom_floats;
@@ -75,8 +89,10 @@ __global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, GB_LIN_CTAS) tc_lin_ker
         if (lane == 0) {
             uint32_t it = 0, tcnt = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcnt) {
-                if (tcnt > 0) mbar_wait(d_empty, (tcnt - 1) & 1);
+                const uint32_t buf = tcnt & 1, use = tcnt >> 1;
+                if (use > 0) mbar_wait(&d_empty[buf], (use - 1) & 1);
                 fence_after_sync();
+                const uint32_t d_tmem = tmem_base + buf * 256;
                 for (int j = 0; j < na; ++j, ++it) {
                     const uint32_t s = it % CF::S, r = it / CF::S;
                     const int kvalid = (j < na1 ? a.K1 - j * ATOM_K : a.K2 - (j - na1) * ATOM_K);
@@ -88,86 +104,115 @@ __global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, GB_LIN_CTAS) tc_lin_ker
                     const uint32_t w_hi = a_hi + 2 * CF::A_BYTES, w_lo = w_hi + CF::W_BYTES;
                     for (int kk = 0; kk < ksteps; ++kk) {
                         const uint32_t ko = kk * 32;
-                        mma_tf32(tmem_base, smem_desc(a_lo + ko), smem_desc(w_hi + ko), idesc, (j | kk) != 0);
-                        mma_tf32(tmem_base, smem_desc(a_hi + ko), smem_desc(w_lo + ko), idesc, 1);
-                        mma_tf32(tmem_base, smem_desc(a_hi + ko), smem_desc(w_hi + ko), idesc, 1);
+                        mma_tf32(d_tmem, smem_desc(a_lo + ko), smem_desc(w_hi + ko), idesc, (j | kk) != 0);
+                        mma_tf32(d_tmem, smem_desc(a_hi + ko), smem_desc(w_lo + ko), idesc, 1);
+                        mma_tf32(d_tmem, smem_desc(a_hi + ko), smem_desc(w_hi + ko), idesc, 1);
                     }
                     mma_commit(&empty[s]);
                 }
-                mma_commit(d_full);
+                mma_commit(&d_full[buf]);
             }
         }
+    } else if (warp < 2 + CF::NBUILD / 32) {
+        // ---- A builders: float4 f = bt + 256 i covers row f/8, 16-byte chunk f%8 of the atom; the loads of the next TWO atoms
+        //      (across tiles too) are in flight while one atom is split and stored: ~32 KB of reads in flight per SM ----
+        const int bt = tid - 64;
+        const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+        const uint32_t total = (uint32_t)my_tiles * na;
+        auto load_atom = [&](uint32_t q, float4 (&x)[4]) {
+            if (q >= total) return;
+            const int tile = blockIdx.x + (q / na) * gridDim.x, j = q % na;
+            const bool first = j < na1;
+            const int kvalid = first ? a.K1 - j * ATOM_K : a.K2 - (j - na1) * ATOM_K;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int f = bt + 256 * i, kc = (f & 7) << 2;
+                const int grow = tile * 128 + (f >> 3);
+                x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (grow < a.M && kc < kvalid) {
+                    const float* src = first ? a.A1 + (size_t)grow * a.lda1 + j * ATOM_K : a.A2 + (size_t)grow * a.lda2 + (j - na1) * ATOM_K;
+                    x[i] = __ldg(reinterpret_cast<const float4*>(src + kc));
+                }
+            }
+        };
+        auto store_atom = [&](uint32_t q, float4 (&x)[4]) {
+            if (q >= total) return;
+            const uint32_t s = q % CF::S, rr = q / CF::S;
+            if (a.rowscale) {
+                const int tile = blockIdx.x + (q / na) * gridDim.x;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int grow = tile * 128 + ((bt + 256 * i) >> 3);
+                    const float rs = grow < a.M ? __ldg(a.rowscale + grow) : 0.f;
+                    x[i].x *= rs; x[i].y *= rs; x[i].z *= rs; x[i].w *= rs;
+                }
+            }
+            if (rr > 0) mbar_wait(&empty[s], (rr - 1) & 1);
+            unsigned char* a_hi = base + s * CF::STAGE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const int f = bt + 256 * i; store_split(a_hi, a_hi + CF::A_BYTES, f >> 3, f & 7, x[i]); }
+            fence_proxy_async();
+            mbar_arrive(&full_a[s]);
+        };
+        float4 xa[4], xb[4], xc[4];
+        load_atom(0, xa);
+        load_atom(1, xb);
+        for (uint32_t q = 0; q < total; q += 3) {
+            load_atom(q + 2, xc); store_atom(q, xa);
+            load_atom(q + 3, xa); store_atom(q + 1, xb);
+            load_atom(q + 4, xb); store_atom(q + 2, xc);
+        }
     } else {
-        const int group = warp & 3, part = (warp - 2) >> 2, half = part & 1;
-        const int r = group * 32 + lane;
+        // ---- epilogue warps ----
+        const int group = warp & 3, part = (warp - 2 - CF::NBUILD / 32) >> 2;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(group * 32) << 16);
         const int nchunks = (H + 15) / 16;
+        float* stg = stg_all + (warp - 2 - CF::NBUILD / 32) * (CF::STG_WARP_BYTES / 4);
+        const int piece = lane & 3, rsub = lane >> 2;
+        const bool use_res = a.epi == EPI_RES_MASK || (a.epi == EPI_ADD_RES && (a.res_cb < 0 || cb == a.res_cb));
         uint32_t tcnt = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcnt) {
-            const int row = tile * 128 + r;
-            const bool rvalid = row < a.M;
-            const float rs = (rvalid && a.rowscale) ? __ldg(a.rowscale + row) : 1.f;
-            // ---- build the A atoms owned by this half ----
-            for (int j = part >> 1; j < na; j += CF::NPARTS / 2) {
-                const uint32_t it = tcnt * na + j;
-                const uint32_t s = it % CF::S, rr = it / CF::S;
-                const bool first = j < na1;
-                const float* src = first ? a.A1 + (size_t)row * a.lda1 + j * ATOM_K : a.A2 + (size_t)row * a.lda2 + (j - na1) * ATOM_K;
-                const int kvalid = first ? a.K1 - j * ATOM_K : a.K2 - (j - na1) * ATOM_K;
-                float4 x[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int kc = 16 * half + 4 * c;
-                    x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rvalid && kc < kvalid) {
-                        x[c] = __ldg(reinterpret_cast<const float4*>(src + kc));
-                        x[c].x *= rs; x[c].y *= rs; x[c].z *= rs; x[c].w *= rs;
-                    }
-                }
-                if (rr > 0) mbar_wait(&empty[s], (rr - 1) & 1);
-                unsigned char* a_hi = base + s * CF::STAGE_BYTES;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) store_split(a_hi, a_hi + CF::A_BYTES, r, 4 * half + c, x[c]);
-                fence_proxy_async();
-                mbar_arrive(&full_a[s]);
-            }
-            // ---- epilogue on alternating 16-column chunks ----
-            mbar_wait(d_full, tcnt & 1);
+            const uint32_t buf = tcnt & 1;
+            mbar_wait(&d_full[buf], (tcnt >> 1) & 1);
             fence_after_sync();
-            float mk = 1.f;
-            if (rvalid && (a.epi == EPI_RES_MASK || (a.epi == EPI_ADD_RES && a.mask))) mk = __ldg(a.mask + row);
-            const bool use_res = a.epi == EPI_RES_MASK || (a.epi == EPI_ADD_RES && (a.res_cb < 0 || cb == a.res_cb));
-            for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
+            for (int ch = part; ch < nchunks; ch += CF::EPARTS) {
                 float v[16];
-                tmem_ld16(lane_addr + ch * 16, v);
-                if (!rvalid) continue;
-                const int c0 = ch * 16;
-                const size_t col0 = (size_t)cb * H + c0;         // column blocks are H wide in the node tensors
+                tmem_ld16(lane_addr + buf * 256 + ch * 16, v);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (c0 + 4 * q >= H) break;
-                    float o[4] = {v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]};
-                    if (a.bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col0 + 4 * q));
-                        o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
-                    }
-                    if (a.epi == EPI_SILU) {
-                        if (a.out2) *reinterpret_cast<float4*>(a.out2 + (size_t)row * a.ldo2 + col0 + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<float4*>(stg + lane * CF::STG_PITCH + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                __syncwarp();
+                const int c0 = ch * 16 + 4 * piece;
+                if (c0 < H) {
+                    const size_t col = (size_t)cb * H + c0;      // column blocks are H wide in the node tensors
+                    const float4 b = *reinterpret_cast<const float4*>(bias_s + c0);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) o[e] = silu_f(o[e]);
-                    } else if (a.epi == EPI_MUL_DSILU) {
-                        const float4 p = __ldg(reinterpret_cast<const float4*>(a.aux + (size_t)row * a.ldaux + col0 + 4 * q));
-                        o[0] *= dsilu_f(p.x); o[1] *= dsilu_f(p.y); o[2] *= dsilu_f(p.z); o[3] *= dsilu_f(p.w);
-                    } else if (use_res) {
-                        const float4 rsd = __ldg(reinterpret_cast<const float4*>(a.res + (size_t)row * a.ldr + col0 + 4 * q));
-                        if (a.epi == EPI_RES_MASK) { o[0] = (rsd.x + o[0]) * mk; o[1] = (rsd.y + o[1]) * mk; o[2] = (rsd.z + o[2]) * mk; o[3] = (rsd.w + o[3]) * mk; }
-                        else { o[0] += rsd.x * mk; o[1] += rsd.y * mk; o[2] += rsd.z * mk; o[3] += rsd.w * mk; }
+                    for (int i = 0; i < 4; ++i) {
+                        const int rl = rsub + 8 * i;
+                        const int row = tile * 128 + group * 32 + rl;
+                        if (row >= a.M) continue;
+                        const float4 acc = *reinterpret_cast<const float4*>(stg + rl * CF::STG_PITCH + 4 * piece);
+                        float o[4] = {acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w};
+                        if (a.epi == EPI_SILU) {
+                            if (a.out2) *reinterpret_cast<float4*>(a.out2 + (size_t)row * a.ldo2 + col) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) o[e] = silu_f(o[e]);
+                        } else if (a.epi == EPI_MUL_DSILU) {
+                            const float4 p = __ldg(reinterpret_cast<const float4*>(a.aux + (size_t)row * a.ldaux + col));
+                            o[0] *= dsilu_f(p.x); o[1] *= dsilu_f(p.y); o[2] *= dsilu_f(p.z); o[3] *= dsilu_f(p.w);
+                        } else if (use_res) {
+                            const float4 rsd = __ldg(reinterpret_cast<const float4*>(a.res + (size_t)row * a.ldr + col));
+                            const float mk = (a.epi == EPI_RES_MASK || a.mask) ? __ldg(a.mask + row) : 1.f;
+                            if (a.epi == EPI_RES_MASK) { o[0] = (rsd.x + o[0]) * mk; o[1] = (rsd.y + o[1]) * mk; o[2] = (rsd.z + o[2]) * mk; o[3] = (rsd.w + o[3]) * mk; }
+                            else { o[0] += rsd.x * mk; o[1] += rsd.y * mk; o[2] += rsd.z * mk; o[3] += rsd.w * mk; }
+                        }
+                        *reinterpret_cast<float4*>(a.out + (size_t)row * a.ldo + col) = make_float4(o[0], o[1], o[2], o[3]);
                     }
-                    *reinterpret_cast<float4*>(a.out + (size_t)row * a.ldo + col0 + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
                 }
+                __syncwarp();
             }
             fence_before_sync();
-            mbar_arrive(d_empty);
+            mbar_arrive(&d_empty[buf]);
         }
     }
     fence_before_sync();

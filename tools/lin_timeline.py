@@ -1,0 +1,25 @@
+import sys, ctypes as C, numpy as np, torch
+sys.path.insert(0, '/root/repo')
+from gaudi_b200 import _lib, training
+dev = torch.device('cuda:0')
+M, K, N = 100000, 192, 192
+A = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev); b = torch.randn(N, device=dev)
+for _ in range(3):
+    y = training._linear(A, W, K, N, b, epi=1)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); y = training._linear(A, W, K, N, b, epi=1); e1.record(); torch.cuda.synchronize()
+print("ms incl pack", e0.elapsed_time(e1))
+buf = np.zeros((3, 1024), dtype=np.uint64)
+lib = _lib.lib(); lib.gb_debug_timeline.argtypes = [C.c_void_p]; lib.gb_debug_timeline.restype = C.c_int
+print("rc", lib.gb_debug_timeline(buf.ctypes.data_as(C.c_void_p)))
+ev = []
+for role in range(3):
+    for i in range(512):
+        code, clk = int(buf[role, 2 * i]), int(buf[role, 2 * i + 1])
+        if clk: ev.append((clk, role, code))
+ev.sort()
+t0 = ev[0][0]
+names = {0: "BLD ", 1: "MMA ", 2: "EPI "}
+for clk, role, code in ev[:140]:
+    print(f"{(clk - t0) / 1.9e3:9.2f} us  {names[role]} {code}")
