@@ -175,21 +175,40 @@ __global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, GB_LIN_CTAS) tc_lin_ker
             const uint32_t buf = tcnt & 1;
             mbar_wait(&d_full[buf], (tcnt >> 1) & 1);
             fence_after_sync();
+            // the TMEM read of the next chunk is in flight while this one is processed
+            uint32_t vr[16];
+            if (part < nchunks) tmem_ld16_issue(lane_addr + buf * 256 + part * 16, vr);
             for (int ch = part; ch < nchunks; ch += CF::EPARTS) {
-                float v[16];
-                tmem_ld16(lane_addr + buf * 256 + ch * 16, v);
+                tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<float4*>(stg + lane * CF::STG_PITCH + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    *reinterpret_cast<uint4*>(stg + lane * CF::STG_PITCH + 4 * q) = make_uint4(vr[4 * q], vr[4 * q + 1], vr[4 * q + 2], vr[4 * q + 3]);
                 __syncwarp();
+                if (ch + CF::EPARTS < nchunks) tmem_ld16_issue(lane_addr + buf * 256 + (ch + CF::EPARTS) * 16, vr);
                 const int c0 = ch * 16 + 4 * piece;
                 if (c0 < H) {
                     const size_t col = (size_t)cb * H + c0;      // column blocks are H wide in the node tensors
                     const float4 b = *reinterpret_cast<const float4*>(bias_s + c0);
+                    const int row0 = tile * 128 + group * 32 + rsub;
+                    float4 sd[4];
+                    float mk[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {                 // side inputs first: four independent loads in flight
+                        const int row = row0 + 8 * i;
+                        sd[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        mk[i] = 1.f;
+                        if (row < a.M) {
+                            if (a.epi == EPI_MUL_DSILU) sd[i] = __ldg(reinterpret_cast<const float4*>(a.aux + (size_t)row * a.ldaux + col));
+                            else if (use_res) {
+                                sd[i] = __ldg(reinterpret_cast<const float4*>(a.res + (size_t)row * a.ldr + col));
+                                if (a.epi == EPI_RES_MASK || a.mask) mk[i] = __ldg(a.mask + row);
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int rl = rsub + 8 * i;
-                        const int row = tile * 128 + group * 32 + rl;
+                        const int row = row0 + 8 * i;
                         if (row >= a.M) continue;
                         const float4 acc = *reinterpret_cast<const float4*>(stg + rl * CF::STG_PITCH + 4 * piece);
                         float o[4] = {acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w};
@@ -198,13 +217,10 @@ __global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, GB_LIN_CTAS) tc_lin_ker
 #pragma unroll
                             for (int e = 0; e < 4; ++e) o[e] = silu_f(o[e]);
                         } else if (a.epi == EPI_MUL_DSILU) {
-                            const float4 p = __ldg(reinterpret_cast<const float4*>(a.aux + (size_t)row * a.ldaux + col));
-                            o[0] *= dsilu_f(p.x); o[1] *= dsilu_f(p.y); o[2] *= dsilu_f(p.z); o[3] *= dsilu_f(p.w);
+                            o[0] *= dsilu_f(sd[i].x); o[1] *= dsilu_f(sd[i].y); o[2] *= dsilu_f(sd[i].z); o[3] *= dsilu_f(sd[i].w);
                         } else if (use_res) {
-                            const float4 rsd = __ldg(reinterpret_cast<const float4*>(a.res + (size_t)row * a.ldr + col));
-                            const float mk = (a.epi == EPI_RES_MASK || a.mask) ? __ldg(a.mask + row) : 1.f;
-                            if (a.epi == EPI_RES_MASK) { o[0] = (rsd.x + o[0]) * mk; o[1] = (rsd.y + o[1]) * mk; o[2] = (rsd.z + o[2]) * mk; o[3] = (rsd.w + o[3]) * mk; }
-                            else { o[0] += rsd.x * mk; o[1] += rsd.y * mk; o[2] += rsd.z * mk; o[3] += rsd.w * mk; }
+                            if (a.epi == EPI_RES_MASK) { o[0] = (sd[i].x + o[0]) * mk[i]; o[1] = (sd[i].y + o[1]) * mk[i]; o[2] = (sd[i].z + o[2]) * mk[i]; o[3] = (sd[i].w + o[3]) * mk[i]; }
+                            else { o[0] += sd[i].x * mk[i]; o[1] += sd[i].y * mk[i]; o[2] += sd[i].z * mk[i]; o[3] += sd[i].w * mk[i]; }
                         }
                         *reinterpret_cast<float4*>(a.out + (size_t)row * a.ldo + col) = make_float4(o[0], o[1], o[2], o[3]);
                     }
