@@ -519,7 +519,12 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::BWD_THREADS, 1) tc_pred_edge_bw
             mbar_wait(d2_full, tcnt & 1);
             fence_after_sync();
             float pr = 0.f, pa = 0.f;
-            float* gp_row = a.g_pre1 + (size_t)(e_lo + r) * H;
+            // g_pre1 rows are written through a per-warp transpose block: thread = row is what TMEM gives, but 16 bytes of 32
+            // different rows per store instruction cost 32 L1 tag lookups; transposed, one instruction covers 8 rows x 64 bytes.
+            // The block lives in the A half of the operand ring, which is idle between the last MMA of GEMM 2 (d2_full) and the
+            // next tile's first operand store (after the barriers below).
+            float* stg = reinterpret_cast<float*>(base + ((warp - 2) >> 3) * CF::STAGE_BYTES) + ((warp - 2) & 7) * (32 * 20);
+            const int piece = lane & 3, rsub = lane >> 2;
 #pragma unroll 1
             for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
                 float v[16];
@@ -528,17 +533,28 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::BWD_THREADS, 1) tc_pred_edge_bw
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
                     const int c0 = ch * 16 + 4 * c4;
+                    float4 gp = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (c0 < H) {
                         const float4 d1 = d1p[c4 * 128];
-                        const float4 gp = make_float4(v[4 * c4] * d1.x, v[4 * c4 + 1] * d1.y, v[4 * c4 + 2] * d1.z, v[4 * c4 + 3] * d1.w);
+                        gp = make_float4(v[4 * c4] * d1.x, v[4 * c4 + 1] * d1.y, v[4 * c4 + 2] * d1.z, v[4 * c4 + 3] * d1.w);
                         const float4 wr = *reinterpret_cast<const float4*>(vec_s + c0);
                         const float4 wa = *reinterpret_cast<const float4*>(vec_s + NP + c0);
                         pr += wr.x * gp.x + wr.y * gp.y + wr.z * gp.z + wr.w * gp.w;
                         pa += wa.x * gp.x + wa.y * gp.y + wa.z * gp.z + wa.w * gp.w;
-                        if (valid) *reinterpret_cast<float4*>(gp_row + c0) = gp;
                     }
+                    *reinterpret_cast<float4*>(stg + lane * 20 + 4 * c4) = gp;
                 }
                 sv_release(sv, q0 + 3 * nchunks + ch);
+                __syncwarp();
+                const int c = ch * 16 + 4 * piece;
+                if (c < H) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rl = group * 32 + rsub + 8 * i;
+                        if (rl < ne) *reinterpret_cast<float4*>(a.g_pre1 + (size_t)(e_lo + rl) * H + c) = *reinterpret_cast<const float4*>(stg + (rsub + 8 * i) * 20 + 4 * piece);
+                    }
+                }
+                __syncwarp();
             }
             fence_before_sync();
             mbar_arrive(d_empty);
