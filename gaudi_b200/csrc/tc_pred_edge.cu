@@ -451,9 +451,25 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::BWD_THREADS, 1) tc_pred_edge_bw
             // ---- epilogue 1: g_ef = coordinate branch + aggregation branch; attention backward ----
             mbar_wait(d1_full, tcnt & 1);
             fence_after_sync();
+            // the tile's rows of g_agg (one per row node, shared by its ~9 edges) are copied once, coalesced, into the A half of
+            // the operand ring (idle between GEMM 1 and the first operand store of GEMM 2) instead of being gathered from L2
+            // with four dependent 16-byte loads per chunk and thread
+            constexpr int GA_ROWS = CF::A_BYTES * 2 / (NP * 4);            // rows per ring stage (A hi + A lo)
+            const bool ga_staged = nn <= 2 * GA_ROWS;
+            if (ga_staged) {
+                const int h4 = H >> 2;
+                for (int idx = (warp - 2) * 32 + lane; idx < nn * h4; idx += CF::NWORK) {
+                    const int nl = idx / h4, k4 = idx - nl * h4;
+                    float* dst = reinterpret_cast<float*>(base + (nl / GA_ROWS) * CF::STAGE_BYTES) + (nl % GA_ROWS) * NP + 4 * k4;
+                    *reinterpret_cast<float4*>(dst) = __ldg(reinterpret_cast<const float4*>(a.g_agg + (size_t)(node_lo + nl) * a.ld_gagg + 4 * k4));
+                }
+                nbar(1, CF::NWORK);
+            }
             float gef[CF::MYCH][16];
             float plog = 0.f, pdot = 0.f;
-            const float* ga_row = a.g_agg + (size_t)rown * a.ld_gagg;
+            const int rloc = valid ? rown - node_lo : 0;
+            const float* ga_row = ga_staged ? reinterpret_cast<const float*>(base + (rloc / GA_ROWS) * CF::STAGE_BYTES) + (rloc % GA_ROWS) * NP
+                                            : a.g_agg + (size_t)rown * a.ld_gagg;
 #pragma unroll
             for (int ci = 0; ci < CF::MYCH; ++ci) {
                 const int ch = part + CF::NPARTS * ci;
@@ -464,7 +480,7 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::BWD_THREADS, 1) tc_pred_edge_bw
                     for (int c4 = 0; c4 < 4; ++c4) {
                         const int c0 = ch * 16 + 4 * c4;
                         if (c0 < H) {
-                            const float4 ga = __ldg(reinterpret_cast<const float4*>(ga_row + c0));
+                            const float4 ga = *reinterpret_cast<const float4*>(ga_row + c0);
                             const float4 p2 = p2p[c4 * 128];
                             const float gadd[4] = {ga.x, ga.y, ga.z, ga.w};
                             const float pv[4] = {p2.x, p2.y, p2.z, p2.w};
