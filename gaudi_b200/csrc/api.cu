@@ -322,18 +322,35 @@ extern "C" int gb_tile_pack(const int32_t* rowptr, int n_nodes, int32_t* tile_pt
     return 0;
 }
 
+__global__ void tile_info_kernel(const int* __restrict__ tile_ptr, const int* __restrict__ rowptr, int n_tiles, int4* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const int lo = tile_ptr[t], hi = tile_ptr[t + 1];
+    const int e_lo = rowptr[lo];
+    out[t] = make_int4(lo, hi - lo, e_lo, rowptr[hi] - e_lo);
+}
+
 extern "C" int gb_graph_create(gb_graph** out, int B, int N, int n_edges, int n_tiles, int n_tc, const int32_t* rowptr,
                                const int32_t* erow, const int32_t* ecol, const int32_t* tile_ptr, const int32_t* tc_ptr,
                                const int32_t* tc_node, const int32_t* tc_start, const int32_t* cperm,
                                const int32_t* colptr, const int32_t* cedge, const float* node_mask) {
     (void)n_tc;
     if (!out) return fail("null argument");
+    int4* tinfo = nullptr;                       // the only memory a graph owns: 16 bytes per tile, derived from the caller's arrays
+    if (n_tiles > 0) {
+        GB_CUDA(cudaMalloc(&tinfo, (size_t)n_tiles * sizeof(int4)));
+        tile_info_kernel<<<(n_tiles + 255) / 256, 256>>>(tile_ptr, rowptr, n_tiles, tinfo);
+        GB_CUDA(cudaDeviceSynchronize());        // not a hot-path call: graphs are created once per mask pair
+    }
     gb_graph* g = new gb_graph();
-    g->g = Graph{B * N, n_edges, n_tiles, B, N, rowptr, erow, ecol, tile_ptr, tc_ptr, tc_node, tc_start, cperm, colptr, cedge, node_mask};
+    g->g = Graph{B * N, n_edges, n_tiles, B, N, rowptr, erow, ecol, tile_ptr, tc_ptr, tc_node, tc_start, cperm, colptr, cedge, node_mask, tinfo};
     *out = g;
     return 0;
 }
-extern "C" int gb_graph_destroy(gb_graph* g) { delete g; return 0; }
+extern "C" int gb_graph_destroy(gb_graph* g) {
+    if (g) { if (g->g.tile_info) cudaFree((void*)g->g.tile_info); delete g; }
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------------
 // workspace carving

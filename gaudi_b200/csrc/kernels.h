@@ -28,6 +28,7 @@ struct Graph {
     const int* colptr;    // [n_nodes+1] CSC pointer
     const int* cedge;     // [n_edges] edge ids grouped by column node
     const float* node_mask;  // [n_nodes]
+    const int4* tile_info;   // [n_tiles] (node_lo, n_nodes, e_lo, n_edges) of every tile: one load instead of a dependent chain
 };
 
 enum LinEpi { EPI_BIAS = 0, EPI_SILU = 1, EPI_RES_MASK = 2, EPI_MUL_DSILU = 3, EPI_ADD_RES = 4 };

@@ -174,9 +174,8 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
         float* my_ef = ef_s + part * 128 * CF::EF_STRIDE;
         uint32_t tcnt = 0;
         for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
-            const int node_lo = g.tile_ptr[tile], node_hi = g.tile_ptr[tile + 1];
-            const int nn = node_hi - node_lo;
-            const int e_lo = g.rowptr[node_lo], ne = g.rowptr[node_hi] - e_lo;
+            const int4 ti = __ldg(g.tile_info + tile);
+            const int node_lo = ti.x, nn = ti.y, e_lo = ti.z, ne = ti.w;
             const bool valid = r < ne;
             int rown = 0, coln = 0; float rad = 0.f, a0 = 0.f, ux = 0.f, uy = 0.f, uz = 0.f;
             if (valid) {
@@ -407,7 +406,7 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::BWD_THREADS, 1) tc_pred_edge_bw
         uint32_t tcnt = 0;
         for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
             const uint32_t q0 = tcnt * 4 * nchunks;                 // first saved-activation chunk of this tile
-            const int node_lo = g.tile_ptr[tile], node_hi = g.tile_ptr[tile + 1];
+            const int node_lo = g.tile_ptr[tile], node_hi = g.tile_ptr[tile + 1];     // (tile_info costs registers here: slower)
             const int nn = node_hi - node_lo;
             const int e_lo = g.rowptr[node_lo], ne = g.rowptr[node_hi] - e_lo;
             const bool valid = r < ne;
