@@ -24,6 +24,14 @@
 namespace gb {
 using namespace tc;
 
+// Optional per-tile timeline (make EXTRA=-DGB_TIMELINE; tools/lin_timeline.py): clock64 marks of CTA 0 per role.
+#ifdef GB_TIMELINE
+__device__ unsigned long long gb_tl[3][1024];
+#define TL(role, idx, code) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (idx) < 512) { gb_tl[role][2 * (idx)] = (code); gb_tl[role][2 * (idx) + 1] = clock64(); } } while (0)
+#else
+#define TL(role, idx, code) do {} while (0)
+#endif
+
 template <int NP>
 struct TcLinCfg {
     static constexpr int S = GB_LIN_S;
@@ -98,7 +106,9 @@ __global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, GB_LIN_CTAS) tc_lin_ker
                     const int kvalid = (j < na1 ? a.K1 - j * ATOM_K : a.K2 - (j - na1) * ATOM_K);
                     const int ksteps = kvalid >= ATOM_K ? 4 : (kvalid + 7) / 8;
                     mbar_wait(&full_a[s], r & 1);
+                    TL(1, 2 * it, 1000 + it);
                     mbar_wait(&full_w[s], r & 1);
+                    TL(1, 2 * it + 1, 2000 + it);
                     fence_after_sync();
                     const uint32_t a_hi = smem_u32(base + s * CF::STAGE_BYTES), a_lo = a_hi + CF::A_BYTES;
                     const uint32_t w_hi = a_hi + 2 * CF::A_BYTES, w_lo = w_hi + CF::W_BYTES;
@@ -153,6 +163,7 @@ __global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, GB_LIN_CTAS) tc_lin_ker
             for (int i = 0; i < 4; ++i) { const int f = bt + 256 * i; store_split(a_hi, a_hi + CF::A_BYTES, f >> 3, f & 7, x[i]); }
             fence_proxy_async();
             mbar_arrive(&full_a[s]);
+            if (tid == 64) TL(0, q, 200 + q);
         };
         float4 xa[4], xb[4], xc[4];
         load_atom(0, xa);
@@ -174,6 +185,7 @@ __global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, GB_LIN_CTAS) tc_lin_ker
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcnt) {
             const uint32_t buf = tcnt & 1;
             mbar_wait(&d_full[buf], (tcnt >> 1) & 1);
+            if (tid == 320) TL(2, 2 * tcnt, 300 + tcnt);
             fence_after_sync();
             // the TMEM read of the next chunk is in flight while this one is processed
             uint32_t vr[16];
@@ -229,12 +241,17 @@ __global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, GB_LIN_CTAS) tc_lin_ker
             }
             fence_before_sync();
             mbar_arrive(&d_empty[buf]);
+            if (tid == 320) TL(2, 2 * tcnt + 1, 400 + tcnt);
         }
     }
     fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc<CF::TMEM_COLS>(tmem_base);
 }
+
+#ifdef GB_TIMELINE
+extern "C" int gb_debug_timeline(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, gb_tl, sizeof(gb_tl)); }
+#endif
 
 template <int NP>
 static void launch_t(const LinArgs& a, const float* wimg, int H, cudaStream_t s) {
