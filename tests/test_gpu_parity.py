@@ -248,3 +248,25 @@ def test_full_size_batch_replicas_are_identical_and_match_golden(dataset, reps):
         assert maxabs(v[0], g[f"{k}_{t}"]) <= TOL, k
     runtime.release_workspaces()
     torch.cuda.empty_cache()
+
+
+def test_tiles_with_many_tiny_molecules_match_oracle():
+    """Hundreds of 2- and 3-ring molecules: a 128-edge tile then spans ~100 nodes, which takes the backward kernel's un-staged
+    g_agg path (more rows than fit the idle operand ring) and packs many row segments into one tile."""
+    dev = _dev()
+    args, model, pred, prop = build_models("cata", dev)
+    wd, wp = cpu_weights(model, pred)
+    dcfg, pcfg = oracle_cfgs("cata")
+    nx = torch.tensor([2, 3] * 150 + [2] * 60)
+    nm, em = gb.build_masks(nx, 11, False, device=dev)
+    B, N = nm.shape[:2]
+    gen = torch.Generator().manual_seed(5)
+    zt = O.draw_noise(B, N, 4, nm.cpu(), generator=gen)
+    noise = O.draw_noise(B, N, 4, nm.cpu(), generator=gen)
+    s = 300
+    ref = O.guided_step(wd, dcfg, wp, pcfg, O.gamma_table(dcfg), s, zt, noise, nm.cpu(), em.cpu(), O.target_max_gap, 0.6)
+    s_arr = torch.full((B, 1), s, device=dev) / model.T
+    out = model.sample_p_zs_given_zt_guidance(s_arr, s_arr + 1.0 / model.T, zt.to(dev), nm, em, gb.AffineTarget.max_gap(pred), 0.6,
+                                              noise=noise.to(dev), return_parts=True)
+    for k in ("eps", "zs_pre", "grad_raw", "zs"):
+        assert maxabs(out[k], ref[k]) <= TOL, (k, maxabs(out[k], ref[k]))
