@@ -307,3 +307,17 @@ def test_training_loop_utilities(tmp_path):
     TU.save_model(lin, str(tmp_path / "m.pt"))
     lin2 = TU.load_model(torch.nn.Linear(4, 4), str(tmp_path / "m.pt"))
     assert torch.equal(lin2.weight, lin.weight) and not lin2.training
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints ONE JSON line with the contract's keys."""
+    import json
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--cpu-batch", "8"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "molecules/s" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] in ("port", "reference")
