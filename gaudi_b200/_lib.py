@@ -55,7 +55,7 @@ SIGNATURES = {
     "gb_linear_scratch_bytes": (_SZ, [_I, _I, _I]),
     "gb_linear": (_I, [_I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "gb_wgrad_scratch_bytes": (_SZ, [_I, _I]),
-    "gb_wgrad": (_I, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _I, _P, _SZ, _P]),
+    "gb_wgrad": (_I, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _I, _P, _P, _SZ, _P]),
     "gb_gemm": (_I, [_I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P]),
     "gb_colsum": (_I, [_P, _I, _I, _I, _P, _P, _I, _P]),
     "gb_rowdot": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),

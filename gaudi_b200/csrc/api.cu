@@ -944,15 +944,20 @@ extern "C" int gb_linear(int M, int N, int K1, int K2, const float* A1, int lda1
 
 extern "C" size_t gb_wgrad_scratch_bytes(int M, int N) { return wgrad_tc_scratch_bytes(M, N); }
 extern "C" int gb_wgrad(int K, int M, int N, const float* G, int ldg, const float* X, int ldx, float* C, int ldc, int accumulate,
-                        void* scratch, size_t scratch_bytes, void* stream) {
+                        float* colsum, void* scratch, size_t scratch_bytes, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (M <= 0 || N <= 0) return 0;
     if (M > 256 || N > 256 || (M & 3) || (N & 3) || (ldg & 3) || (ldx & 3) || ((uintptr_t)G & 15) || ((uintptr_t)X & 15))
         return fail("gb_wgrad: needs M, N <= 256, multiples of 4, and 16-byte aligned rows (got M=%d N=%d ldg=%d ldx=%d)", M, N, ldg, ldx);
     float* sc = (scratch && scratch_bytes >= wgrad_tc_scratch_bytes(M, N) && ((uintptr_t)scratch & 15) == 0) ? (float*)scratch : nullptr;
-    if (K <= 0) { if (!accumulate) GB_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, s)); return 0; }
+    if (colsum && (!sc || N >= 256)) return fail("gb_wgrad: the fused column sum needs the scratch (two-phase) path and N < 256");
+    if (K <= 0) {
+        if (!accumulate) GB_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, s));
+        if (colsum) GB_CUDA(cudaMemsetAsync(colsum, 0, (size_t)M * 4, s));
+        return 0;
+    }
     if (!sc && !accumulate) GB_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, s));
-    launch_wgrad_tc(K, M, N, G, ldg, X, ldx, C, ldc, accumulate, sc, s);
+    launch_wgrad_tc(K, M, N, G, ldg, X, ldx, C, ldc, accumulate, sc, colsum, s);
     GB_LAUNCHED(sc ? 2 : 1);
     return check_launch("gb_wgrad");
 }

@@ -55,7 +55,7 @@ void launch_lin_tc(int H, const LinArgs& a, const float* wimg, cudaStream_t s);
 int tc_np(int H);
 // C[m][n] += sum_e G[e][m] X[e][n] on tcgen05 (both operands MN-major, 3xTF32); C must be zeroed / hold the value to add to
 void launch_wgrad_tc(int K, int M, int N, const float* G, int ldg, const float* X, int ldx, float* C, int ldc, int accumulate,
-                     float* scratch, cudaStream_t s);
+                     float* scratch, float* colsum, cudaStream_t s);
 size_t wgrad_tc_scratch_bytes(int M, int N);
 void launch_pack_tc(float* dst, const float* src, int ld, int k_off, int n_off, int Kv, int Nv, int NP, int atoms, int transpose, cudaStream_t s);
 

@@ -40,7 +40,7 @@ __device__ __forceinline__ uint32_t idesc_tf32_mn(int N) {      // TF32 x TF32 -
 
 __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(int K, int M, int N, const float* __restrict__ G, int ldg,
                                                                 const float* __restrict__ X, int ldx, float* __restrict__ C, int ldc,
-                                                                int kt_per_cta, float* __restrict__ partial) {
+                                                                int kt_per_cta, float* __restrict__ partial, int with_colsum) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(base + WG_STAGES * WG_STAGE);
@@ -63,7 +63,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(int K, int M, i
     const uint32_t tmem_base = *tmem_slot;
     const int n_kt = (K + WG_KT - 1) / WG_KT;
     const int kt_lo = blockIdx.x * kt_per_cta, kt_hi = min(n_kt, kt_lo + kt_per_cta);
-    const int NP = (N + 15) & ~15, n_mblk = (M + 127) / 128;
+    // with_colsum: a column of ones is appended to X (column N of the operand image), so accumulator column N = sum_e G[e][m],
+    // the bias gradient of the same Linear, for free (two-phase path only)
+    const int NP = (N + (with_colsum ? 1 : 0) + 15) & ~15, n_mblk = (M + 127) / 128;
 
     if (warp == 1) {
         if (lane == 0 && kt_lo < kt_hi) {
@@ -110,6 +112,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(int K, int M, i
                 *reinterpret_cast<float4*>(op + off) = h;
                 *reinterpret_cast<float4*>(op + WG_OP + off) = l;
             }
+            if (with_colsum && w < WG_KT) {                       // hi = 1, lo = 0 (pre-zeroed) for the rows that exist
+                const int k = w, col = N;
+                const float one = (kt * WG_KT + k < K) ? 1.f : 0.f;
+                const uint32_t off = (uint32_t)((col >> 5) * WG_BLK + (k >> 2) * 512 + (k & 3) * 128 + ((((col & 31) >> 3) ^ (k & 3)) << 5) + ((col & 7) << 2));
+                *reinterpret_cast<float*>(st + 2 * WG_OP + off) = one;
+            }
             fence_proxy_async();
             mbar_arrive(&full[s]);
         }
@@ -146,11 +154,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(int K, int M, i
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-// C[m][n] = (accumulate ? C : 0) + sum over the CTA slabs, fixed order
+// C[m][n] = (accumulate ? C : 0) + sum over the CTA slabs, fixed order; column N of the slabs (if present) -> colsum[m]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_slabs, int M, int N, int NP, float* __restrict__ C, int ldc,
-                                    int accumulate) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M * N; i += gridDim.x * blockDim.x) {
-        const int m = i / N, n = i - m * N;
+                                    int accumulate, float* __restrict__ colsum) {
+    const int ncol = N + (colsum ? 1 : 0);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M * ncol; i += gridDim.x * blockDim.x) {
+        const int m = i / ncol, n = i - m * ncol;
         float s0 = 0.f, s1 = 0.f;
         int g = 0;
         for (; g + 1 < n_slabs; g += 2) {
@@ -158,17 +167,18 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_sla
             s1 += partial[((size_t)(g + 1) * M + m) * NP + n];
         }
         if (g < n_slabs) s0 += partial[((size_t)g * M + m) * NP + n];
+        if (n == N) { colsum[m] = s0 + s1; continue; }
         float* c = C + (size_t)m * ldc + n;
         *c = (accumulate ? *c : 0.f) + (s0 + s1);
     }
 }
 
-size_t wgrad_tc_scratch_bytes(int M, int N) { return (size_t)148 * M * ((N + 15) & ~15) * sizeof(float); }
+size_t wgrad_tc_scratch_bytes(int M, int N) { return (size_t)148 * M * ((N + 1 + 15) & ~15) * sizeof(float); }
 
 // scratch (>= wgrad_tc_scratch_bytes) selects the deterministic two-phase reduction; without it C must hold the value to add
 // to (zero or the accumulation target) and the CTAs add their partial sums with fp32 atomics
 void launch_wgrad_tc(int K, int M, int N, const float* G, int ldg, const float* X, int ldx, float* C, int ldc, int accumulate,
-                     float* scratch, cudaStream_t s) {
+                     float* scratch, float* colsum, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
@@ -180,10 +190,11 @@ void launch_wgrad_tc(int K, int M, int N, const float* G, int ldg, const float* 
     if (grid > 148) grid = 148;
     const int per = (n_kt + grid - 1) / grid;
     grid = (n_kt + per - 1) / per;
-    tc_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM, s>>>(K, M, N, G, ldg, X, ldx, C, ldc, per, scratch);
+    const int wc = (scratch && colsum && N < 256) ? 1 : 0;
+    tc_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM, s>>>(K, M, N, G, ldg, X, ldx, C, ldc, per, scratch, wc);
     if (scratch) {
-        const int total = M * N;
-        wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(scratch, grid, M, N, (N + 15) & ~15, C, ldc, accumulate);
+        const int total = M * (N + wc);
+        wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(scratch, grid, M, N, (N + wc + 15) & ~15, C, ldc, accumulate, wc ? colsum : nullptr);
     }
 }
 

@@ -36,17 +36,21 @@ def _gemm(mode: int, M: int, N: int, K: int, A, lda, B, ldb, Cm, ldc, bias=None,
     _call("gb_gemm", mode, M, N, K, _ptr(A), lda, _ptr(B), ldb, _ptr(Cm), ldc, _ptr(bias), int(acc))
 
 
-def _wgrad(G, X, out, M: int, N: int, K: int) -> None:
-    """out[M,N] (a view into a weight-gradient tensor, row stride out.stride(0)) = G[K,M]^T X[K,N]."""
-    if (_TC and M <= 256 and N <= 256 and M % 4 == 0 and N % 4 == 0 and G.stride(0) % 4 == 0 and X.stride(0) % 4 == 0
+def _wgrad(G, X, out, M: int, N: int, K: int, colsum: bool = False):
+    """out[M,N] (a view into a weight-gradient tensor, row stride out.stride(0)) = G[K,M]^T X[K,N]; with ``colsum`` also
+    returns sum_k G[k,:] (the bias gradient of the same Linear; fused into the tensor-core kernel as a column of ones)."""
+    if (_TC and M <= 256 and N < 256 and M % 4 == 0 and N % 4 == 0 and G.stride(0) % 4 == 0 and X.stride(0) % 4 == 0
             and G.data_ptr() % 16 == 0 and X.data_ptr() % 16 == 0):
         nbytes = _lib.lib().gb_wgrad_scratch_bytes(M, N)
         key = ("wgrad", G.device.index)
         if key not in _scratch or _scratch[key].numel() < nbytes:
             _scratch[key] = torch.empty(nbytes, dtype=torch.uint8, device=G.device)
-        _call("gb_wgrad", K, M, N, _ptr(G), G.stride(0), _ptr(X), X.stride(0), _ptr(out), out.stride(0), 0, _ptr(_scratch[key]), nbytes)
-    else:
-        _gemm(2, M, N, K, G, G.stride(0), X, X.stride(0), out, out.stride(0))
+        cs = torch.empty(M, dtype=torch.float32, device=G.device) if colsum else None
+        _call("gb_wgrad", K, M, N, _ptr(G), G.stride(0), _ptr(X), X.stride(0), _ptr(out), out.stride(0), 0, _ptr(cs),
+              _ptr(_scratch[key]), nbytes)
+        return cs
+    _gemm(2, M, N, K, G, G.stride(0), X, X.stride(0), out, out.stride(0))
+    return _colsum(G, K, M) if colsum else None
 
 
 def _colsum(X, M: int, N: int, w=None) -> torch.Tensor:
@@ -135,8 +139,7 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = _linear(gy, W, N, K, transpose=True)
         gW = _new(gy, N, K)
-        _wgrad(gy, x, gW, N, K, M)
-        gb = _colsum(gy, M, N) if ctx.has_bias else None
+        gb = _wgrad(gy, x, gW, N, K, M, colsum=ctx.has_bias)
         return gx, gW, gb, None, None
 
 
@@ -195,18 +198,16 @@ class _EdgeMLP(torch.autograd.Function):
         s1 = _new(h, E, H)
         _call("gb_silu_fwd", _ptr(pre1), _ptr(s1), E * H)
         gW2 = _new(h, H, H)
-        _wgrad(G2, s1, gW2, H, H, E)
-        gb2 = _colsum(G2, E, H)
+        gb2 = _wgrad(G2, s1, gW2, H, H, E, colsum=True)
         del s1
         G1 = _linear(G2, W2, H, H, transpose=True, epi=EPI_MUL_DSILU, aux=pre1)
         gPa, gPb = _new(h, n, H), _new(h, n, H)
         _call("gb_rowcol_reduce", g.handle, _ptr(G1), H, _F(1.0), _ptr(gPa), _ptr(gPb))
         gW1 = _new(h, H, ld1)
-        _wgrad(gPa, h, gW1, H, H, n)
+        gb1 = _wgrad(gPa, h, gW1, H, H, n, colsum=True)
         _wgrad(gPb, h, gW1[:, H:], H, H, n)
         gW1[:, 2 * H].copy_(_colsum(G1, E, H, r))
         gW1[:, 2 * H + 1].copy_(_colsum(G1, E, H, d0))
-        gb1 = _colsum(gPa, n, H)
         gh = _linear(gPa, W1, H, H, transpose=True)
         gh = _linear(gPb, W1[:, H:], H, H, transpose=True, epi=EPI_ADD, aux=gh)
         g_r = _new(h, E)
@@ -341,13 +342,11 @@ class _NodeMLP(torch.autograd.Function):
         gt = _new(h, n, H)
         _call("gb_resmask", _ptr(_c(g_out)), None, _ptr(mask), n, H, _ptr(gt))
         gW4 = _new(h, H, H)
-        _wgrad(gt, sn, gW4, H, H, n)
-        gb4 = _colsum(gt, n, H)
+        gb4 = _wgrad(gt, sn, gW4, H, H, n, colsum=True)
         gpre = _linear(gt, W4, H, H, transpose=True, epi=EPI_MUL_DSILU, aux=pre)
         gW3 = _new(h, H, 2 * H)
-        _wgrad(gpre, h, gW3, H, H, n)
+        gb3 = _wgrad(gpre, h, gW3, H, H, n, colsum=True)
         _wgrad(gpre, agg, gW3[:, H:], H, H, n)
-        gb3 = _colsum(gpre, n, H)
         gh = _linear(gpre, W3, H, H, transpose=True, epi=EPI_ADD, aux=gt)      # residual branch + gpre W3[:, :H]
         gagg = _linear(gpre, W3[:, H:], H, H, transpose=True)
         return gh, gagg, gW3, gb3, gW4, gb4, None

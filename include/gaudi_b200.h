@@ -178,11 +178,12 @@ int gb_linear(int M, int N, int K1, int K2, const float* A1, int lda1, const flo
               const float* mask, void* wimg, size_t wimg_bytes, void* stream);
  /* gb_wgrad: C[M,N] (+)= G[K,M]^T X[K,N] on tcgen05 (3xTF32, both operands read row-major = MN-major, reduction split
   * across CTAs).  With `scratch` (gb_wgrad_scratch_bytes) the per-CTA slabs are summed by a second kernel in a fixed order
-  * (bit-reproducible); without it they meet in C through fp32 atomics.  M, N <= 256 and multiples of 4; ldg, ldx multiples
-  * of 4; 16-byte aligned G, X. */
+  * (bit-reproducible); without it they meet in C through fp32 atomics.  colsum (optional, scratch path, N < 256): also
+  * returns colsum[m] = sum_k G[k][m] -- the bias gradient of the same Linear -- through a column of ones appended to X.
+  * M, N <= 256 and multiples of 4; ldg, ldx multiples of 4; 16-byte aligned G, X. */
 size_t gb_wgrad_scratch_bytes(int M, int N);
 int gb_wgrad(int K, int M, int N, const float* G, int ldg, const float* X, int ldx, float* C, int ldc, int accumulate,
-             void* scratch, size_t scratch_bytes, void* stream);
+             float* colsum, void* scratch, size_t scratch_bytes, void* stream);
 int gb_gemm(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
             const float* bias, int accumulate, void* stream);
 int gb_colsum(const float* X, int ld, int M, int N, const float* w, float* out, int accumulate, void* stream);

@@ -269,15 +269,18 @@ def test_tensor_core_wgrad_matches_fp64():
             Cf = torch.full((M, N + 6), 7.0, device=dev)
             C = Cf[:, 2:2 + N]
             args = (K, M, N, training._ptr(G), Gf.stride(0), training._ptr(X), Xf.stride(0), training._ptr(C), Cf.stride(0))
-            _lib.check(L.gb_wgrad(*args, 0, training._ptr(sc), sb, training._stream()))
+            cs = torch.full((M,), 3.0, device=dev) if (sc is not None and N < 256) else None
+            _lib.check(L.gb_wgrad(*args, 0, training._ptr(cs), training._ptr(sc), sb, training._stream()))
+            if cs is not None:                      # fused bias gradient: column sums of G through a column of ones
+                assert maxabs(cs, G.double().sum(0)) <= 3e-6 * max(1.0, float(G.double().sum(0).abs().max())) * max(1.0, (K / 1000) ** 0.5)
             assert maxabs(C, ref) <= tol, (K, M, N, sc is None, maxabs(C, ref))
             assert float((Cf[:, :2] - 7).abs().max()) == 0 and float((Cf[:, 2 + N:] - 7).abs().max()) == 0     # nothing outside the view
             results.append(C.clone())
-            _lib.check(L.gb_wgrad(*args, 1, training._ptr(sc), sb, training._stream()))
+            _lib.check(L.gb_wgrad(*args, 1, None, training._ptr(sc), sb, training._stream()))
             assert maxabs(C, 2 * ref) <= 2 * tol
         Cf = torch.empty(M, N, device=dev)
         _lib.check(L.gb_wgrad(K, M, N, training._ptr(G), Gf.stride(0), training._ptr(X), Xf.stride(0), training._ptr(Cf), N, 0,
-                              training._ptr(scratch), nbytes, training._stream()))
+                              None, training._ptr(scratch), nbytes, training._stream()))
         assert torch.equal(Cf, results[0])                 # the two-phase path is bit-reproducible
 
 
