@@ -389,7 +389,8 @@ class _DenFinish(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_fin, h3, x_in, mask, B, N, F):
         eps = _new(x_fin, B, N, 3 + F)
-        _call("gb_den_finish_fwd", _ptr(_c(x_fin)), _ptr(x_in), _ptr(_c(h3)), _ptr(mask), B, N, F, _ptr(eps))
+        x_fin, h3 = _c(x_fin), _c(h3)          # locals keep possible contiguous copies alive until the launch is enqueued
+        _call("gb_den_finish_fwd", _ptr(x_fin), _ptr(x_in), _ptr(h3), _ptr(mask), B, N, F, _ptr(eps))
         ctx.save_for_backward(mask)
         ctx.dims = (B, N, F)
         return eps
@@ -490,7 +491,8 @@ def training_loss(model, x, h, node_mask, edge_mask, t_int: Optional[torch.Tenso
     eps = _c(eps.to(torch.float32))
     gamma = model.gamma.gamma.detach().to(torch.float32).contiguous()
     xh, zt, gamma_t = _new(eps, B, N, 3 + F), _new(eps, B, N, 3 + F), _new(eps, B)
-    _call("gb_make_zt", _ptr(_c(x.to(torch.float32))), _ptr(_c(h_cat.to(torch.float32))), _ptr(mask), _ptr(eps), _ptr(gamma), _ptr(t_f),
+    xs, hs = _c(x.to(torch.float32)), _c(h_cat.to(torch.float32))     # two temporaries in one call must not share a freed block
+    _call("gb_make_zt", _ptr(xs), _ptr(hs), _ptr(mask), _ptr(eps), _ptr(gamma), _ptr(t_f),
           _F(model.norm_values[0]), _F(model.norm_values[1]), _F(model.norm_biases[1]), B, N, F, _ptr(xh), _ptr(zt), _ptr(gamma_t))
     net = denoiser_forward_train(model.dynamics, t_f / model.T, zt, node_mask, edge_mask)
     return _TrainLoss.apply(net, eps, zt, xh, mask, t_f, gamma_t, model._gamma_T(), float(model.norm_values[1]),
@@ -548,7 +550,8 @@ def sample_edm_t(x, h, edm_model, t, node_mask, eps: Optional[torch.Tensor] = No
     t_idx = torch.round(t.reshape(B).to(torch.float32) * edm_model.T).contiguous()       # PredefinedNoiseSchedule.forward
     gamma = edm_model.gamma.gamma.detach().to(torch.float32).contiguous()
     xh, zt, gamma_t = _new(eps, B, N, 3 + F), _new(eps, B, N, 3 + F), _new(eps, B)
-    _call("gb_make_zt", _ptr(_c(x.to(torch.float32))), _ptr(_c(h.to(torch.float32))), _ptr(mask), _ptr(eps), _ptr(gamma), _ptr(t_idx),
+    xs, hs = _c(x.to(torch.float32)), _c(h.to(torch.float32))
+    _call("gb_make_zt", _ptr(xs), _ptr(hs), _ptr(mask), _ptr(eps), _ptr(gamma), _ptr(t_idx),
           _F(edm_model.norm_values[0]), _F(edm_model.norm_values[1]), _F(edm_model.norm_biases[1]), B, N, F, _ptr(xh), _ptr(zt),
           _ptr(gamma_t))
     return zt

@@ -160,6 +160,10 @@ def test_optimizer_steps_reduce_the_loss():
     h = torch.ones(B, N, 1, device=dev) * nm
     t_int = torch.randint(1, 1001, (B, 1), device=dev)
     eps = model.sample_combined_position_feature_noise(B, N, nm)
+    hd = {"categorical": h, "integer": torch.zeros(0, device=dev)}
+    l32 = model(x, hd, nm, em, t_int=t_int, eps=eps).detach()
+    l64 = model(x.double(), {"categorical": h.double(), "integer": torch.zeros(0, device=dev)}, nm, em, t_int=t_int, eps=eps.double()).detach()
+    assert torch.equal(l32, l64)                              # non-fp32 inputs are converted once, result unchanged
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3, amsgrad=True, weight_decay=1e-12)
     losses = []
     for _ in range(30):
