@@ -270,3 +270,23 @@ def test_tiles_with_many_tiny_molecules_match_oracle():
                                               noise=noise.to(dev), return_parts=True)
     for k in ("eps", "zs_pre", "grad_raw", "zs"):
         assert maxabs(out[k], ref[k]) <= TOL, (k, maxabs(out[k], ref[k]))
+
+
+def test_hidden_256_matches_oracle():
+    """BASELINE config 4 sweeps hidden 256: node Linears on tcgen05 (NP = 256), edge kernels on the FP32 engine."""
+    dev = _dev()
+    args, model, pred, prop = build_models("cata", dev, hidden=(256, 256), layers=(2, 3))
+    wd, wp = cpu_weights(model, pred)
+    dcfg, pcfg = oracle_cfgs("cata", hidden=(256, 256), layers=(2, 3))
+    nx = torch.tensor([11, 4, 10, 9, 2, 7] * 40)
+    nm, em = gb.build_masks(nx, 11, False, device=dev)
+    B, N = nm.shape[:2]
+    gen = torch.Generator().manual_seed(21)
+    z = O.draw_noise(B, N, 4, nm.cpu(), generator=gen)
+    t = torch.full((B, 1), 640) / 1000
+    eps = model.phi(z.to(dev), t.to(dev), nm, em, None)
+    assert maxabs(eps, O.denoiser_forward(wd, dcfg, z, t, nm.cpu(), em.cpu())) <= TOL
+    w = torch.tensor([0.3, -1.0, 0.2, 0.0, 0.5])
+    pr, gr = runtime.predictor_value_and_grad(pred, z.to(dev), nm, em, t.to(dev), w.to(dev))
+    rp, rg = O.predictor_input_grad(wp, pcfg, z, nm.cpu(), em.cpu(), t, lambda p: (p * w).sum(1), 1.0)
+    assert maxabs(pr, rp) <= TOL and maxabs(gr, rg) <= TOL
