@@ -25,8 +25,15 @@ namespace gb {
 // ----------------------------------------------------------------------------------------------
 // math
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+// sigmoid(x) = 1 / (1 + 2^(-x log2 e)): one MUFU.EX2 and one MUFU.RCP.  The denominator lies in [1, inf], so the bare
+// rcp.approx (1 ulp, like __fdividef) needs none of __fdividef's range checks and fix-ups (an FSETP and predicated
+// multiplies per element, which showed up in the SASS of every edge kernel).
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float exp_neg(float x) {          // e^-x; flush-to-zero ex2 (no denormal scaling code around the MUFU)
+    float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * -1.4426950408889634f)); return r;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_approx(1.f + exp_neg(x)); }
+__device__ __forceinline__ float silu_f(float x) { return x * rcp_approx(1.f + exp_neg(x)); }
 // d/dx [x * sigmoid(x)]
 __device__ __forceinline__ float dsilu_f(float x) {
     float s = sigmoid_f(x);
