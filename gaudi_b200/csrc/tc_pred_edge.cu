@@ -119,7 +119,9 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
                                                                    const float* __restrict__ wcimg, int H) {
     using CF = TcPredCfg<NP>;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array: the compiler keeps the address space (LDS / STS
+    // instead of generic LD / ST for every staging and operand access)
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::S * CF::STAGE_BYTES);
     TcPipe p{base, bars, bars + CF::S, bars + 2 * CF::S, CF::STAGE_BYTES, CF::S};
     uint64_t* d1_full = bars + 3 * CF::S; uint64_t* d2_full = d1_full + 1; uint64_t* d_empty = d2_full + 1;
@@ -329,7 +331,9 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::BWD_THREADS, 1) tc_pred_edge_bw
                                                                    const float* __restrict__ w2img_nt, int H) {
     using CF = TcPredCfg<NP>;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array: the compiler keeps the address space (LDS / STS
+    // instead of generic LD / ST for every staging and operand access)
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::S * CF::STAGE_BYTES);
     TcPipe p{base, bars, bars + CF::S, bars + 2 * CF::S, CF::STAGE_BYTES, CF::S};
     uint64_t* d1_full = bars + 3 * CF::S; uint64_t* d2_full = d1_full + 1; uint64_t* d_empty = d2_full + 1;

@@ -42,7 +42,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(int K, int M, i
                                                                 const float* __restrict__ X, int ldx, float* __restrict__ C, int ldc,
                                                                 int kt_per_cta, float* __restrict__ partial, int with_colsum) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array: the compiler keeps the address space (LDS / STS
+    // instead of generic LD / ST for every staging and operand access)
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(base + WG_STAGES * WG_STAGE);
     uint64_t* empty = full + WG_STAGES;
     uint64_t* d_full = empty + WG_STAGES;
