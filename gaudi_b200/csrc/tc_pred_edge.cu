@@ -343,6 +343,7 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::BWD_THREADS, 1) tc_pred_edge_bw
     float* red_s = vec_s + 6 * NP;                                                       // [4][128]
     float* ef_s = red_s + 4 * CF::NPARTS * 128;                                          // saved-activation ring (4 x 8 KB)
     int* seg_s = reinterpret_cast<int*>(ef_s + CF::NPARTS * 128 * CF::EF_STRIDE);
+    float* geo_s = reinterpret_cast<float*>(seg_s + 132);                                // [6][128] dx, dy, dz, g_u of every tile edge
     const SvRing sv{reinterpret_cast<unsigned char*>(ef_s), sv_full, sv_empty};
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -415,19 +416,27 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::BWD_THREADS, 1) tc_pred_edge_bw
             const int e_lo = g.rowptr[node_lo], ne = g.rowptr[node_hi] - e_lo;
             const bool valid = r < ne;
             int rown = 0, coln = 0;
-            float gphi = 0.f, nrm = 1.f, dx = 0.f, dy = 0.f, dz = 0.f, gux = 0.f, guy = 0.f, guz = 0.f;
-            if (valid) {
-                const int e = e_lo + r;
-                rown = g.erow[e]; coln = g.ecol[e];
-                dx = a.x[3 * rown] - a.x[3 * coln]; dy = a.x[3 * rown + 1] - a.x[3 * coln + 1]; dz = a.x[3 * rown + 2] - a.x[3 * coln + 2];
-                nrm = sqrtf(dx * dx + dy * dy + dz * dz + 1e-8f);
-                const float inv = 1.f / (nrm + 1.f);
-                const float mk = g.node_mask[rown];
-                const float gx = a.g_xout[3 * rown] * mk, gy = a.g_xout[3 * rown + 1] * mk, gz = a.g_xout[3 * rown + 2] * mk;
-                const float tau = a.sv_tau[e];
-                const float gdotu = (gx * dx + gy * dy + gz * dz) * inv;
-                if (a.use_tanh) { gphi = gdotu * a.coords_range * (1.f - tau * tau); const float sc = tau * a.coords_range; gux = gx * sc; guy = gy * sc; guz = gz * sc; }
-                else { gphi = gdotu; gux = gx * tau; guy = gy * tau; guz = gz * tau; }
+            float gphi = 0.f;
+            {   // the edge geometry is needed again only at the very end (dL/d(x_i - x_j), part 0): it waits in shared memory
+                // instead of occupying seven registers of every worker across both GEMMs
+                float dx = 0.f, dy = 0.f, dz = 0.f, gux = 0.f, guy = 0.f, guz = 0.f;
+                if (valid) {
+                    const int e = e_lo + r;
+                    rown = g.erow[e]; coln = g.ecol[e];
+                    dx = a.x[3 * rown] - a.x[3 * coln]; dy = a.x[3 * rown + 1] - a.x[3 * coln + 1]; dz = a.x[3 * rown + 2] - a.x[3 * coln + 2];
+                    const float nrm = sqrtf(dx * dx + dy * dy + dz * dz + 1e-8f);
+                    const float inv = 1.f / (nrm + 1.f);
+                    const float mk = g.node_mask[rown];
+                    const float gx = a.g_xout[3 * rown] * mk, gy = a.g_xout[3 * rown + 1] * mk, gz = a.g_xout[3 * rown + 2] * mk;
+                    const float tau = a.sv_tau[e];
+                    const float gdotu = (gx * dx + gy * dy + gz * dz) * inv;
+                    if (a.use_tanh) { gphi = gdotu * a.coords_range * (1.f - tau * tau); const float sc = tau * a.coords_range; gux = gx * sc; guy = gy * sc; guz = gz * sc; }
+                    else { gphi = gdotu; gux = gx * tau; guy = gy * tau; guz = gz * tau; }
+                }
+                if (part == 0) {
+                    geo_s[r] = dx; geo_s[128 + r] = dy; geo_s[256 + r] = dz;
+                    geo_s[384 + r] = gux; geo_s[512 + r] = guy; geo_s[640 + r] = guz;
+                }
             }
             if (part == 0) for (int i = r; i <= nn; i += 128) seg_s[i] = g.rowptr[node_lo + i] - e_lo;
             const uint32_t it0 = tcnt * 2 * na;
@@ -584,6 +593,9 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::BWD_THREADS, 1) tc_pred_edge_bw
                 const float g_r = psum_parts<CF::NPARTS>(red_s + 2 * CF::NPARTS * 128, r);
                 const float g_a = psum_parts<CF::NPARTS>(red_s + 3 * CF::NPARTS * 128, r);
                 a.g_attr[e_lo + r] += g_a;
+                const float dx = geo_s[r], dy = geo_s[128 + r], dz = geo_s[256 + r];
+                const float gux = geo_s[384 + r], guy = geo_s[512 + r], guz = geo_s[640 + r];
+                const float nrm = sqrtf(dx * dx + dy * dy + dz * dz + 1e-8f);
                 const float inv = 1.f / (nrm + 1.f);
                 const float k2 = (gux * dx + guy * dy + guz * dz) * inv * inv / nrm;
                 float* gd = a.g_d + (size_t)(e_lo + r) * 3;
