@@ -179,17 +179,22 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
             const int4 ti = __ldg(g.tile_info + tile);
             const int node_lo = ti.x, nn = ti.y, e_lo = ti.z, ne = ti.w;
             const bool valid = r < ne;
-            int rown = 0, coln = 0; float rad = 0.f, a0 = 0.f, ux = 0.f, uy = 0.f, uz = 0.f;
-            if (valid) {
-                const int e = e_lo + r;
-                rown = g.erow[e]; coln = g.ecol[e];
-                const float dx = a.x[3 * rown] - a.x[3 * coln], dy = a.x[3 * rown + 1] - a.x[3 * coln + 1], dz = a.x[3 * rown + 2] - a.x[3 * coln + 2];
-                rad = dx * dx + dy * dy + dz * dz;
-                const float inv = 1.f / (sqrtf(rad + 1e-8f) + 1.f);
-                ux = dx * inv; uy = dy * inv; uz = dz * inv;
-                const float ex = a.x0[3 * rown] - a.x0[3 * coln], ey = a.x0[3 * rown + 1] - a.x0[3 * coln + 1], ez = a.x0[3 * rown + 2] - a.x0[3 * coln + 2];
-                a0 = ex * ex + ey * ey + ez * ez;
-                if (a.a_edge) a0 = a.a_edge[e];
+            int rown = 0, coln = 0; float rad = 0.f, a0 = 0.f;
+            {   // the unit difference vector is needed again only for the coordinate update at the end of the tile (part 0):
+                // it waits in tr_s instead of in three registers of every worker
+                float ux = 0.f, uy = 0.f, uz = 0.f;
+                if (valid) {
+                    const int e = e_lo + r;
+                    rown = g.erow[e]; coln = g.ecol[e];
+                    const float dx = a.x[3 * rown] - a.x[3 * coln], dy = a.x[3 * rown + 1] - a.x[3 * coln + 1], dz = a.x[3 * rown + 2] - a.x[3 * coln + 2];
+                    rad = dx * dx + dy * dy + dz * dz;
+                    const float inv = 1.f / (sqrtf(rad + 1e-8f) + 1.f);
+                    ux = dx * inv; uy = dy * inv; uz = dz * inv;
+                    const float ex = a.x0[3 * rown] - a.x0[3 * coln], ey = a.x0[3 * rown + 1] - a.x0[3 * coln + 1], ez = a.x0[3 * rown + 2] - a.x0[3 * coln + 2];
+                    a0 = ex * ex + ey * ey + ez * ez;
+                    if (a.a_edge) a0 = a.a_edge[e];
+                }
+                if (part == 0) { tr_s[3 * r] = ux; tr_s[3 * r + 1] = uy; tr_s[3 * r + 2] = uz; }
             }
             if (part == 0) for (int i = r; i <= nn; i += 128) seg_s[i] = g.rowptr[node_lo + i] - e_lo;
             const uint32_t it0 = tcnt * 2 * na;
@@ -304,6 +309,7 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
                 const float phi = psum_parts<CF::NPARTS>(red_s + CF::NPARTS * 128, r);
                 const float tau = a.use_tanh ? tanhf(phi) : phi;
                 if (SAVE && valid) a.sv_tau[e_lo + r] = tau;
+                const float ux = tr_s[3 * r], uy = tr_s[3 * r + 1], uz = tr_s[3 * r + 2];
                 if (a.use_tanh) { tr_s[3 * r] = ux * tau * a.coords_range; tr_s[3 * r + 1] = uy * tau * a.coords_range; tr_s[3 * r + 2] = uz * tau * a.coords_range; }
                 else { tr_s[3 * r] = ux * tau; tr_s[3 * r + 1] = uy * tau; tr_s[3 * r + 2] = uz * tau; }
             }
