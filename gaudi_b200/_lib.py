@@ -6,6 +6,8 @@ ImportError is raised when that is impossible.  All compute entry points need a 
 from __future__ import annotations
 
 import ctypes as C
+import glob
+import hashlib
 import os
 import shutil
 import subprocess
@@ -84,6 +86,34 @@ SIGNATURES = {
 }
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def source_hash() -> str:
+    """sha256 over the CUDA sources, headers and Makefile the library is built from (content, not mtime: the tree is
+    copied between machines)."""
+    files = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+                   glob.glob(os.path.join(CSRC, "*.h")) + [os.path.join(CSRC, "Makefile"),
+                                                            os.path.join(_HERE, "..", "include", "gaudi_b200.h")])
+    h = hashlib.sha256()
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def is_stale() -> bool:
+    """True when libgaudi_b200.so is missing or was built from other sources than the ones in the tree."""
+    if not os.path.exists(LIB_PATH):
+        return True
+    try:
+        with open(HASH_PATH) as fh:
+            return fh.read().strip() != source_hash()
+    except OSError:
+        return True
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA sources for sm_100a into ``csrc/libgaudi_b200.so`` (nvcc cross-compiles without a GPU)."""
     if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
@@ -99,6 +129,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise ImportError("gaudi_b200: building libgaudi_b200.so failed:\n" + res.stdout[-4000:] + res.stderr[-4000:])
     if verbose:
         print(res.stdout)
+    with open(HASH_PATH, "w") as fh:
+        fh.write(source_hash() + "\n")
     return LIB_PATH
 
 
@@ -108,7 +140,7 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        if is_stale():                          # missing, or built from older sources (ABI / behaviour mismatch after a pull)
             build()
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .runtime import _ptr, _stream, _need_cuda
+from .runtime import _ptr, _stream, _need_cuda, _on_device
 
 FLAG_NAMES = ("orientation_nodes", "dist_stable", "connected", "angels3", "angels4")
 _MAXRANGE = 4
@@ -92,6 +92,7 @@ def _ring_index(ring_type: torch.Tensor) -> torch.Tensor:
     return ring_type.to(torch.int32).contiguous()
 
 
+@_on_device
 def positions2adj(x: torch.Tensor, ring_type: torch.Tensor, tol: float = 0.1, dataset: str = "cata"):
     """(dist [B,N,N], adj [B,N,N]) -- utils/helpers.py:172-196.  ``ring_type`` [B,N] indices or [B,N,F] one-hot."""
     _need_cuda(x, "x")
@@ -107,6 +108,7 @@ def positions2adj(x: torch.Tensor, ring_type: torch.Tensor, tol: float = 0.1, da
     return dist, adj
 
 
+@_on_device
 def check_stability_batch(x: torch.Tensor, ring_type: torch.Tensor, node_mask: torch.Tensor, tol: float = 0.1,
                           dataset: str = "cata") -> torch.Tensor:
     """flags uint8 [B,8] for a padded batch: columns 0-4 = ``FLAG_NAMES``, 5 = molecule stable (all five), 6 = error bits,

@@ -14,7 +14,10 @@ What is different by design
   * a target function that is affine in the predictor outputs (``AffineTarget``; both closures of
     generation_guidance.py:200-211 are) runs the whole T-step loop inside ``gb_sample_loop`` (optionally as a
     replayed CUDA graph); any other Python callable goes through autograd with the hand-written backward.
-Out of scope (raise NotImplementedError): learned schedule, training loss (``forward``), ``sample_chain``.
+  * with ``self.seed`` set (``dist`` sets ``seed + rank``) EVERY draw of a sampler call -- z_T, the per-step noise and the
+    p(x|z0) noise -- comes from the in-kernel Philox stream of that seed (draw indices 0, 1..T, T+1), so a seed
+    reproduces a run and ranks never share noise; with ``seed is None`` torch's generator is used as in the reference.
+Out of scope (raise NotImplementedError): learned schedule, context conditioning, ``include_charges``.
 """
 from __future__ import annotations
 
@@ -333,20 +336,47 @@ class EnVariationalDiffusion(torch.nn.Module):
             runtime.cog_fix(x, nm, self._last_cog)
         return x, h
 
-    def _initial_z(self, n_samples, n_nodes, node_mask, fix_noise, std, noise):
+    def set_seed(self, seed: Optional[int]) -> None:
+        """Fix the Philox base seed of the samplers and restart its call counter (same seed -> same molecules)."""
+        self.seed = None if seed is None else int(seed)
+        self.__dict__["_seed_base"], self.__dict__["_loop_calls"] = self.seed, 0
+
+    def _call_seed(self) -> Optional[int]:
+        """Philox seed of one sampler call: a function of the fixed base seed (e.g. seed + rank) and of how many calls /
+        batch chunks were sampled under it so far, or None when ``self.seed`` is unset (torch's generator is used)."""
+        if self.seed is None:
+            return None
+        if self.__dict__.get("_seed_base") != int(self.seed):          # a new seed restarts the stream
+            self.__dict__["_seed_base"], self.__dict__["_loop_calls"] = int(self.seed), 0
+        calls = self.__dict__.get("_loop_calls", 0)
+        self.__dict__["_loop_calls"] = calls + 1
+        return (int(self.seed) * 0x9E3779B1 + calls) & ((1 << 62) - 1)
+
+    def _seeded_noise(self, n_samples, n_nodes, node_mask, std, seed: int, draw: int):
+        """Same distribution as sample_combined_position_feature_noise, drawn by the Philox kernel (gb_noise)."""
+        return runtime.noise(self._flat_mask(node_mask), n_samples, n_nodes, self.n_dims + self.in_node_nf, std, seed, draw)
+
+    def _initial_z(self, n_samples, n_nodes, node_mask, fix_noise, std, noise, seed=None):
         if noise is not None:
             return noise[0].to(torch.float32).contiguous().clone()
+        if seed is not None:
+            return self._seeded_noise(n_samples, n_nodes, node_mask, std, seed, 0)
         bs = 1 if fix_noise else n_samples
         z = self.sample_combined_position_feature_noise(bs, n_nodes, node_mask, std)
         return z.expand(n_samples, -1, -1).contiguous()
 
-    def _fused_loop(self, z, node_mask, edge_mask, predictor, target_w, noise, stats):
+    def _last_noise(self, n_samples, n_nodes, node_mask, fix_noise, noise, seed=None):
+        if noise is not None:
+            return noise[self.T + 1]
+        if fix_noise:
+            return None                                  # _step_noise draws the shared sample
+        if seed is not None:
+            return self._seeded_noise(n_samples, n_nodes, node_mask, 1.0, seed, self.T + 1)
+        return self.sample_combined_position_feature_noise(n_samples, n_nodes, node_mask)
+
+    def _fused_loop(self, z, node_mask, edge_mask, predictor, target_w, noise, stats, seed=None):
         sched, tvals, _ = self._tables(z.device)
-        if self.seed is not None:      # fixed base seed (e.g. seed + rank): every loop call / batch chunk gets its own stream
-            calls = self.__dict__.get("_loop_calls", 0)
-            self.__dict__["_loop_calls"] = calls + 1
-            seed = (int(self.seed) * 0x9E3779B1 + calls) & ((1 << 62) - 1)
-        else:
+        if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         nz = None if noise is None else noise.to(torch.float32).contiguous()
         runtime.sample_loop(self.dynamics, predictor, node_mask, edge_mask, z, self.T, self.T, 0, sched, tvals,
@@ -364,18 +394,17 @@ class EnVariationalDiffusion(torch.nn.Module):
                                 n_samples, node_mask, edge_mask, noise, None)
             if out is not None:
                 return out
-        z = self._initial_z(n_samples, n_nodes, node_mask, fix_noise, std, noise)
+        # fix_noise (one shared draw for the whole batch, a visualisation mode) keeps torch's generator
+        seed = None if (noise is not None or fix_noise) else self._call_seed()
+        z = self._initial_z(n_samples, n_nodes, node_mask, fix_noise, std, noise, seed)
         stats = torch.zeros(self.T, 8, dtype=torch.float32, device=z.device)
         if fix_noise:
             for s in reversed(range(self.T)):
                 s_arr = torch.full((n_samples, 1), fill_value=s, device=z.device) / self.T
                 z = self.sample_p_zs_given_zt(s_arr, s_arr, z, node_mask, edge_mask, None, True, None, stats[s])
-            last = None
         else:
-            self._fused_loop(z, node_mask, edge_mask, None, None, noise, stats)
-            last = None if noise is None else noise[self.T + 1]
-            if noise is None:
-                last = self.sample_combined_position_feature_noise(n_samples, n_nodes, node_mask)
+            self._fused_loop(z, node_mask, edge_mask, None, None, noise, stats, seed)
+        last = self._last_noise(n_samples, n_nodes, node_mask, fix_noise, noise, seed)
         self.last_stats = stats
         self._check_stats(stats)
         return self._finish(z, node_mask, edge_mask, fix_noise, last)
@@ -428,42 +457,47 @@ class EnVariationalDiffusion(torch.nn.Module):
             if out is not None:
                 return out
         n_nodes = node_mask.size(1)
-        z = self._initial_z(n_samples, n_nodes, node_mask, fix_noise, std, noise)
+        seed = None if (noise is not None or fix_noise) else self._call_seed()
+        z = self._initial_z(n_samples, n_nodes, node_mask, fix_noise, std, noise, seed)
         stats = torch.zeros(self.T, 8, dtype=torch.float32, device=z.device)
         if isinstance(target_function, AffineTarget) and not fix_noise:
             w = (target_function.weights * float(scale)).to(z.device).contiguous()
-            self._fused_loop(z, node_mask, edge_mask, target_function.predictor, w, noise, stats)
+            self._fused_loop(z, node_mask, edge_mask, target_function.predictor, w, noise, stats, seed)
         else:
             for s in reversed(range(self.T)):
                 s_arr = torch.full((n_samples, 1), fill_value=s, device=z.device) / self.T
                 t_arr = torch.full((n_samples, 1), fill_value=s + 1, device=z.device) / self.T
                 nz = None if noise is None else noise[self.T - s]
+                if nz is None and seed is not None:
+                    nz = self._seeded_noise(n_samples, n_nodes, node_mask, 1.0, seed, self.T - s)
                 z = self.sample_p_zs_given_zt_guidance(s_arr, t_arr, z, node_mask, edge_mask, target_function, scale,
                                                        fix_noise, nz, stats[s])
         self.last_stats = stats
         self._check_stats(stats)
-        last = None if noise is None else noise[self.T + 1]
-        if last is None and not fix_noise:
-            last = self.sample_combined_position_feature_noise(n_samples, n_nodes, node_mask)
+        last = self._last_noise(n_samples, n_nodes, node_mask, fix_noise, noise, seed)
         return self._finish(z, node_mask, edge_mask, fix_noise, last)
 
     @torch.no_grad()
     def sample_chain(self, n_samples, n_nodes, node_mask, edge_mask, context=None, keep_frames=None, std=1.0, noise=None):
         """Unguided sampling that keeps intermediate states (en_diffusion.py:1118-1174): returns the un-normalised frames
         flattened to [n_samples * keep_frames, N, D]; frame 0 is the final (x, h).  Runs the eager per-step path."""
-        z = self._initial_z(n_samples, n_nodes, node_mask, False, std, noise)
+        seed = None if noise is not None else self._call_seed()
+        z = self._initial_z(n_samples, n_nodes, node_mask, False, std, noise, seed)
         keep_frames = self.T if keep_frames is None else keep_frames
         assert keep_frames <= self.T
         chain = torch.zeros((keep_frames,) + z.size(), device=z.device)
         stats = torch.zeros(self.T, 8, dtype=torch.float32, device=z.device)
         for s in reversed(range(self.T)):
             s_arr = torch.full((n_samples, 1), fill_value=s, device=z.device) / self.T
-            z = self.sample_p_zs_given_zt(s_arr, s_arr + 1.0 / self.T, z, node_mask, edge_mask, context,
-                                          noise=None if noise is None else noise[self.T - s], stats=stats[s])
+            nz = None if noise is None else noise[self.T - s]
+            if nz is None and seed is not None:
+                nz = self._seeded_noise(n_samples, n_nodes, node_mask, 1.0, seed, self.T - s)
+            z = self.sample_p_zs_given_zt(s_arr, s_arr + 1.0 / self.T, z, node_mask, edge_mask, context, noise=nz,
+                                          stats=stats[s])
             x, h_cat, _ = self.unnormalize(z[:, :, :self.n_dims], z[:, :, self.n_dims:], z[:, :, :0], node_mask)
             chain[(s * keep_frames) // self.T] = torch.cat([x, h_cat], dim=2)
         self._check_stats(stats)
-        last = noise[self.T + 1] if noise is not None else self.sample_combined_position_feature_noise(n_samples, n_nodes, node_mask)
+        last = self._last_noise(n_samples, n_nodes, node_mask, False, noise, seed)
         x, h = self._finish(z, node_mask, edge_mask, False, last)
         chain[0] = torch.cat([x, h["categorical"], h["integer"]], dim=2)
         return chain.view(n_samples * keep_frames, *z.size()[1:])

@@ -62,13 +62,17 @@ def sample_guidance_sharded(args, model, target_function, nodesxsample: torch.Te
     fn = sampler or sampling.sample_guidance
     if hi > lo:
         inner = getattr(model, "module", model)
-        if noise is None:
-            inner.seed = int(seed) + rank
-        local_noise = None
-        if noise is not None:                         # padded to the local max the same way the masks are
-            nloc = int(local.max().item())
-            local_noise = noise[:, lo:hi, :nloc].contiguous()
-        x, one_hot, node_mask, _ = fn(args, model, target_function, local, scale=scale, std=std, noise=local_noise)
+        if noise is None:                              # per-rank Philox stream for z_T, every step and the final decode
+            if hasattr(inner, "set_seed"):
+                inner.set_seed(int(seed) + rank)
+            else:
+                inner.seed = int(seed) + rank
+        # every shard pads to the ring count of the WHOLE batch (sampling_edm.py:177): the predictor's mean pooling runs over
+        # the padded nodes (egnn_predictor/models.py:456-457), so local padding would rescale the guidance gradient by
+        # nmax_global / nmax_local (1.10x for a shard whose largest molecule has 10 of 11 rings)
+        local_noise = None if noise is None else noise[:, lo:hi].contiguous()
+        x, one_hot, node_mask, _ = fn(args, model, target_function, local, scale=scale, std=std, noise=local_noise,
+                                      max_nodes=nmax_global)
     else:
         dev = args.device
         x = torch.zeros(0, 1, 3, device=dev); one_hot = torch.zeros(0, 1, 1, device=dev); node_mask = torch.zeros(0, 1, 1, device=dev)

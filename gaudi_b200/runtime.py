@@ -7,6 +7,7 @@ There is deliberately no CPU / eager fallback: a non-CUDA tensor raises.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import weakref
 from typing import Dict, List, Optional, Tuple
 
@@ -24,6 +25,39 @@ def _ptr(t: Optional[torch.Tensor]) -> _VP:
 
 def _stream() -> _VP:
     return _VP(torch.cuda.current_stream().cuda_stream)
+
+
+def _cuda_device_of(args, kwargs) -> Optional[torch.device]:
+    """Device of the first CUDA tensor / module parameter among the arguments; all CUDA tensor arguments must share it."""
+    dev = None
+    for a in list(args) + list(kwargs.values()):
+        d = None
+        if isinstance(a, torch.Tensor):
+            d = a.device if a.is_cuda else None
+        elif isinstance(a, torch.nn.Module):
+            p = next(a.parameters(), None)
+            d = p.device if p is not None and p.is_cuda else None
+        if d is None:
+            continue
+        if dev is None:
+            dev = d
+        elif d != dev:
+            raise RuntimeError(f"gaudi_b200: arguments live on different CUDA devices ({dev} and {d})")
+    return dev
+
+
+def _on_device(fn):
+    """Run a C-ABI entry point with the arguments' device current: the library launches on the current device's stream
+    and allocates with cudaMalloc, so tensors on cuda:1 while cuda:0 is current (``args.device='cuda:1'`` without
+    ``torch.cuda.set_device``, legal in the reference) would otherwise meet kernels of the wrong device."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = _cuda_device_of(args, kwargs)
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
 
 
 def _need_cuda(t: torch.Tensor, what: str) -> None:
@@ -84,6 +118,7 @@ def _versions(ps: List[torch.Tensor]) -> Tuple:
     return tuple((p.data_ptr(), p._version) for p in ps)
 
 
+@_on_device
 def denoiser_handle(dyn) -> NetHandle:
     """Packed-weights handle of an ``EGNN_dynamics`` (re-packed when parameters were reloaded / moved)."""
     ps = _param_list_denoiser(dyn.egnn)
@@ -104,6 +139,7 @@ def denoiser_handle(dyn) -> NetHandle:
     return h
 
 
+@_on_device
 def predictor_handle(pred) -> NetHandle:
     ps = _param_list_predictor(pred.egnn)
     _need_cuda(ps[0], "predictor parameters")
@@ -129,6 +165,9 @@ class GraphHandle:
     def __init__(self, topo: Topology):
         self.topo = topo
         out = _VP(0)
+        # gb_graph_create launches its tile-table kernel on the legacy stream and synchronises the device; under a
+        # non-blocking side stream the int32 conversions of build_topology must have finished before it reads them
+        torch.cuda.current_stream(topo.rowptr.device).synchronize()
         _lib.check(_lib.lib().gb_graph_create(
             C.byref(out), topo.B, topo.N, topo.n_edges, topo.n_tiles, topo.n_tc, _ptr(topo.rowptr), _ptr(topo.erow),
             _ptr(topo.ecol), _ptr(topo.tile_ptr), _ptr(topo.tc_ptr), _ptr(topo.tc_node), _ptr(topo.tc_start),
@@ -146,6 +185,7 @@ _graph_cache: Dict[Tuple, GraphHandle] = {}
 _GRAPH_CACHE_MAX = 8
 
 
+@_on_device
 def graph_for(node_mask: torch.Tensor, edge_mask: torch.Tensor, B: int, N: int) -> GraphHandle:
     _need_cuda(node_mask, "node_mask")
     _need_cuda(edge_mask, "edge_mask")
@@ -203,6 +243,7 @@ def _time_tensor(t, B: int, device) -> Tuple[torch.Tensor, int]:
     return t.reshape(B).contiguous(), 1
 
 
+@_on_device
 def denoiser_forward(dyn, t, xh: torch.Tensor, node_mask: torch.Tensor, edge_mask: torch.Tensor,
                      scrub_all: bool = False, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """EGNN_dynamics._forward (edm/egnn/models.py:83-152)."""
@@ -251,19 +292,22 @@ class _PredictorFn(torch.autograd.Function):
                                "call backward before running the predictor again")
         B, N, D = ctx.shape
         gp = _f32c(g_pred)
-        gz = torch.empty(B, N, D, dtype=torch.float32, device=gp.device)
-        ws = wsp.buf
-        _lib.check(_lib.lib().gb_predictor_input_grad(ctx.net.handle, ctx.g.handle, _ptr(gp), 0, _ptr(gz), _ptr(ws),
-                                                      ws.numel(), _stream()))
+        with torch.cuda.device(gp.device):
+            gz = torch.empty(B, N, D, dtype=torch.float32, device=gp.device)
+            ws = wsp.buf
+            _lib.check(_lib.lib().gb_predictor_input_grad(ctx.net.handle, ctx.g.handle, _ptr(gp), 0, _ptr(gz), _ptr(ws),
+                                                          ws.numel(), _stream()))
         return gz, None, None, None, None
 
 
+@_on_device
 def predictor_forward(pred_module, xh, node_mask, edge_mask, t) -> torch.Tensor:
     """EGNN_predictor.forward (edm/egnn_predictor/models.py:433-457), differentiable w.r.t. ``xh``."""
     _need_cuda(xh, "xh")
     return _PredictorFn.apply(xh, pred_module, node_mask, edge_mask, t)
 
 
+@_on_device
 def predictor_value_and_grad(pred_module, xh, node_mask, edge_mask, t, g_pred_row: torch.Tensor):
     """(pred, d<g_pred_row, sum_b pred_b>/dxh) without autograd: the affine-target fast path."""
     _need_cuda(xh, "xh")
@@ -287,6 +331,7 @@ def predictor_value_and_grad(pred_module, xh, node_mask, edge_mask, t, g_pred_ro
 
 
 # ---- step pieces -------------------------------------------------------------------------------------
+@_on_device
 def step_sample(zt, eps, noise, coef, node_mask_flat, project: bool, seed: int = 0, draw: int = 0) -> torch.Tensor:
     B, N, D = zt.shape
     zs = torch.empty_like(zt)
@@ -295,6 +340,7 @@ def step_sample(zt, eps, noise, coef, node_mask_flat, project: bool, seed: int =
     return zs
 
 
+@_on_device
 def step_guide(zs_pre, grad, coef, node_mask_flat, max_norm: float = 10.0) -> torch.Tensor:
     B, N, D = zs_pre.shape
     zs = torch.empty_like(zs_pre)
@@ -303,6 +349,7 @@ def step_guide(zs_pre, grad, coef, node_mask_flat, max_norm: float = 10.0) -> to
     return zs
 
 
+@_on_device
 def decode(z0, eps, noise, coef, node_mask_flat, norm_x, norm_h, bias_h, seed: int = 0, draw: int = 0):
     B, N, D = z0.shape
     x = torch.empty(B, N, 3, dtype=torch.float32, device=z0.device)
@@ -314,17 +361,20 @@ def decode(z0, eps, noise, coef, node_mask_flat, norm_x, norm_h, bias_h, seed: i
     return x, one_hot, cog
 
 
+@_on_device
 def cog_fix(x, node_mask_flat, cog, thresh: float = 5e-2) -> None:
     B, N, _ = x.shape
     _lib.check(_lib.lib().gb_cog_fix(_ptr(x), _ptr(node_mask_flat), _ptr(cog), float(thresh), B, N, _stream()))
 
 
+@_on_device
 def noise(node_mask_flat, B: int, N: int, D: int, std: float, seed: int, draw: int) -> torch.Tensor:
     out = torch.empty(B, N, D, dtype=torch.float32, device=node_mask_flat.device)
     _lib.check(_lib.lib().gb_noise(_ptr(out), _ptr(node_mask_flat), B, N, D, float(std), seed, draw, _stream()))
     return out
 
 
+@_on_device
 def sample_loop(dyn, pred_module, node_mask, edge_mask, z, T: int, s_hi: int, s_lo: int, sched, tvals,
                 target_w: Optional[torch.Tensor], noise_all: Optional[torch.Tensor], seed: int,
                 stats: Optional[torch.Tensor], use_graph: bool) -> None:
@@ -411,6 +461,7 @@ def _edge_gather(t, g, width):
     return _f32c(t.reshape(-1, width)[g.topo.dense_idx])
 
 
+@_on_device
 def gcl_forward(mod, h, edge_index, edge_attr, node_mask, edge_mask):
     g, B, n = _flat_graph(h, edge_index, node_mask, edge_mask)
     H = mod.node_mlp[2].out_features
@@ -427,6 +478,7 @@ def gcl_forward(mod, h, edge_index, edge_attr, node_mask, edge_mask):
     return out
 
 
+@_on_device
 def equiv_update_forward(mod, h, coord, edge_index, coord_diff, edge_attr, node_mask, edge_mask):
     g, B, n = _flat_graph(h, edge_index, node_mask, edge_mask)
     H = mod.coord_mlp[2].out_features
@@ -450,6 +502,7 @@ def _block_params(blk):
     return ps + _equiv_params(blk.gcl_equiv)
 
 
+@_on_device
 def equiv_block_forward(mod, h, x, edge_index, node_mask, edge_mask, edge_attr):
     g, B, n = _flat_graph(h, edge_index, node_mask, edge_mask)
     H = mod.hidden_nf
@@ -465,6 +518,7 @@ def equiv_block_forward(mod, h, x, edge_index, node_mask, edge_mask, edge_attr):
     return hout, xout
 
 
+@_on_device
 def egnn_forward(mod, h, x, edge_index, node_mask, edge_mask):
     g, B, n = _flat_graph(h, edge_index, node_mask, edge_mask)
     ps = _param_list_denoiser(mod)
@@ -504,6 +558,7 @@ def _pred_ws(net, g, device):
     return workspace("pred", device).get(nbytes, device)
 
 
+@_on_device
 def e_gcl_forward(mod, h, edge_index, coord, edge_attr, node_mask, edge_mask):
     g, B, n = _flat_graph(h, edge_index, node_mask, edge_mask)
     H = mod.node_mlp[2].out_features
@@ -519,6 +574,7 @@ def e_gcl_forward(mod, h, edge_index, coord, edge_attr, node_mask, edge_mask):
     return hout, xout
 
 
+@_on_device
 def pred_egnn_forward(mod, h, x, edges, edge_attr, node_mask, edge_mask):
     g, B, n = _flat_graph(h, edges, node_mask, edge_mask)
     ps = _param_list_predictor(mod)

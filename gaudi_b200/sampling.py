@@ -89,6 +89,18 @@ class MyDataParallel(nn.DataParallel):
     Sampling resolves through ``__getattr__`` to the bare module, i.e. one device per process; multi-GPU runs
     shard the batch across processes instead (``gaudi_b200.dist``)."""
 
+    def __init__(self, module, device_ids=None, output_device=None, dim=0):
+        if device_ids is None:
+            # one device per process: nn.DataParallel would otherwise replicate over every visible GPU in forward(), and
+            # the C library keeps per-process state (packed-weight handles, workspaces) that threads must not share
+            p = next(module.parameters(), None)
+            if p is not None and p.is_cuda:
+                device_ids = [p.device.index if p.device.index is not None else torch.cuda.current_device()]
+        super().__init__(module, device_ids=device_ids, output_device=output_device, dim=dim)
+
+    def forward(self, *inputs, **kwargs):
+        return self.module(*inputs, **kwargs)          # no scatter / replicate: multi-GPU runs shard across processes
+
     def __getattr__(self, name):
         if name == "module":
             return super().__getattr__("module")
@@ -171,9 +183,19 @@ def sample_pos_edm(args, model, nodesxsample, std=0.7, noise=None):
     return x, h["categorical"], node_mask, edge_mask
 
 
-def sample_guidance(args, model, target_function, nodesxsample, scale=1, std=1.0, noise=None):
-    """Guided sampling helper (sampling_edm.py:172-224); pads to nodesxsample.max()."""
-    node_mask, edge_mask = _masks(args, nodesxsample, int(torch.as_tensor(nodesxsample).max().item()))
+def sample_guidance(args, model, target_function, nodesxsample, scale=1, std=1.0, noise=None, max_nodes=None):
+    """Guided sampling helper (sampling_edm.py:172-224); pads to nodesxsample.max() as the reference does (:177).
+
+    ``max_nodes`` overrides the padded ring count.  The predictor pools with ``mean`` over the PADDED node count
+    (edm/egnn_predictor/models.py:456-457), so the guidance gradient depends on the padding: a shard of a larger batch
+    must pad to the whole batch's maximum (``dist.sample_guidance_sharded`` passes it) to reproduce the single-process
+    result."""
+    nmax = int(torch.as_tensor(nodesxsample).max().item())
+    if max_nodes is not None:
+        if int(max_nodes) < nmax:
+            raise ValueError(f"max_nodes={max_nodes} is smaller than the largest molecule ({nmax} rings)")
+        nmax = int(max_nodes)
+    node_mask, edge_mask = _masks(args, nodesxsample, nmax)
     x, h = model.sample_guidance(len(nodesxsample), target_function, node_mask, edge_mask, scale, fix_noise=False,
                                  std=std, noise=noise)
     _post_asserts(x, node_mask)

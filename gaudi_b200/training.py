@@ -19,6 +19,7 @@ from typing import Optional
 import torch
 
 from . import _lib
+from . import runtime
 from .runtime import _ptr, _stream, _need_cuda, graph_for
 
 _F = C.c_float
@@ -426,6 +427,7 @@ class _TrainLoss(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+@runtime._on_device
 def denoiser_forward_train(dyn, t: torch.Tensor, xh: torch.Tensor, node_mask: torch.Tensor, edge_mask: torch.Tensor) -> torch.Tensor:
     """Differentiable (w.r.t. the parameters) ``EGNN_dynamics._forward`` (edm/egnn/models.py:76-152)."""
     _need_cuda(xh, "xh")
@@ -468,6 +470,7 @@ def denoiser_forward_train(dyn, t: torch.Tensor, xh: torch.Tensor, node_mask: to
     return _DenFinish.apply(x, h3, x_in, mask, B, N, F)
 
 
+@runtime._on_device
 def training_loss(model, x, h, node_mask, edge_mask, t_int: Optional[torch.Tensor] = None,
                   eps: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``EnVariationalDiffusion.forward`` in train mode with loss_type 'l2' and include_charges False: loss [B].
@@ -502,6 +505,7 @@ def training_loss(model, x, h, node_mask, edge_mask, t_int: Optional[torch.Tenso
 # ------------------------------------------------------------------------------------------------------------------
 # property predictor: cond_prediction/train_cond_predictor.py:47-81
 # ------------------------------------------------------------------------------------------------------------------
+@runtime._on_device
 def predictor_forward_train(pred_module, xh: torch.Tensor, node_mask: torch.Tensor, edge_mask: torch.Tensor, t) -> torch.Tensor:
     """``EGNN_predictor.forward`` (edm/egnn_predictor/models.py:433-457, 543-560; gcl.py:225-316), differentiable w.r.t. the
     PARAMETERS (the guidance path, differentiable w.r.t. the input, is runtime.predictor_forward)."""
@@ -538,6 +542,7 @@ def predictor_forward_train(pred_module, xh: torch.Tensor, node_mask: torch.Tens
     return _PoolMean.apply(hout, B, N)
 
 
+@runtime._on_device
 def sample_edm_t(x, h, edm_model, t, node_mask, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
     """z_t ~ q(z_t | x, h) at the per-sample times ``t`` [B,1] in [0,1] (cond_prediction/train_cond_predictor.py:47-62)."""
     _need_cuda(x, "x")
@@ -557,6 +562,7 @@ def sample_edm_t(x, h, edm_model, t, node_mask, eps: Optional[torch.Tensor] = No
     return zt
 
 
+@runtime._on_device
 def vlb_loss(model, x, h, node_mask, edge_mask, t_int: Optional[torch.Tensor] = None, eps: Optional[torch.Tensor] = None,
              eps0: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``EnVariationalDiffusion.forward`` in eval mode: the -log p(x,h) estimator compute_loss(t0_always=True) [B]

@@ -31,12 +31,29 @@ x, oh, m = dist.sample_guidance_sharded(args, model, tf, nx, scale=0.6, noise=no
 assert x.shape == (6, 11, 3) and oh.shape == (6, 11, 1) and torch.equal(m.cpu(), nm)
 # single-process reference on this rank
 xr, ohr, _, _ = gb.sample_guidance(args, model, tf, nx, scale=0.6, noise=noise)
-err = float((x - xr).abs().max()) / max(1.0, float(xr.abs().max()))
-assert err < 1e-3, err
+# rank 0 holds [10, 9, 11], rank 1 holds [4, 7, 10]: rank 1's local maximum (10) is below the batch maximum (11), the case
+# where local padding would rescale the guidance gradient by 1.10.  The kernels are tile-offset invariant, so the sharded
+# result must be BIT-identical to the single-process one (SURVEY.md 8e)
+err = float((x - xr).abs().max())
+assert torch.equal(x, xr), err
 assert torch.equal(oh, ohr)
-# Philox mode: different ranks draw different noise, results are finite and masked
-x2, oh2, m2 = dist.sample_guidance_sharded(args, model, tf, nx, scale=0.6, seed=5)
+# Philox mode: different ranks draw different noise (both ranks were seeded identically by torch, so only the per-rank
+# Philox seed can make the shards differ), results are finite and masked, and a fixed seed reproduces the run
+nx2 = torch.tensor([10, 10, 10, 10])
+x2, oh2, m2 = dist.sample_guidance_sharded(args, model, tf, nx2, scale=0.6, seed=5)
 assert torch.isfinite(x2).all() and float((x2 * (1 - m2)).abs().max()) == 0.0
+assert not torch.equal(x2[:2], x2[2:]), "ranks must not share their initial / decode noise"
+x3, _, _ = dist.sample_guidance_sharded(args, model, tf, nx2, scale=0.6, seed=5)
+assert torch.equal(x2, x3), "a fixed seed must reproduce the sharded run"
+# hetro layout (rings | orientation nodes): ragged shards, injected noise, bit-identical to the single-process run
+argsh, modelh, predh, proph = build_models("hetro", dev, hidden=(64, 64), layers=(2, 2), timesteps=20)
+nxh = torch.tensor([10, 8, 3, 9])
+nmh, emh = O.build_masks(nxh, 10, True)
+noiseh = torch.stack([O.draw_noise(len(nxh), 20, 15, nmh, generator=gen) for _ in range(modelh.T + 2)]).to(dev)
+tfh = gb.AffineTarget.opv(predh, proph)
+xh, ohh, mh = dist.sample_guidance_sharded(argsh, modelh, tfh, nxh, scale=0.6, noise=noiseh)
+xhr, ohhr, _, _ = gb.sample_guidance(argsh, modelh, tfh, nxh, scale=0.6, noise=noiseh)
+assert torch.equal(mh.cpu(), nmh) and torch.equal(xh, xhr) and torch.equal(ohh, ohhr)
 tdist.destroy_process_group()
 print("multi ok", rank, err)
 """

@@ -218,8 +218,9 @@ rank, ws = tdist.get_rank(), tdist.get_world_size()
 args = gb.args_edm(device="cpu", dataset=os.environ["GB_DS"])
 nx = torch.tensor([3, 2, 4, 1, 2])
 calls = []
-def fake_sampler(args, model, tf, local, scale=1, std=1.0, noise=None):
-    nm, em = gb.build_masks(local, int(local.max()), args.dataset != "cata")
+def fake_sampler(args, model, tf, local, scale=1, std=1.0, noise=None, max_nodes=None):
+    assert max_nodes == 4, "every shard must pad to the ring count of the whole batch (sampling_edm.py:177)"
+    nm, em = gb.build_masks(local, max_nodes, args.dataset != "cata")
     x = nm.repeat(1, 1, 3) * (100.0 * rank + local.view(-1, 1, 1).float())
     oh = nm.repeat(1, 1, 2)
     calls.append(len(local))
@@ -251,6 +252,32 @@ def test_sharded_sampling_gathers_full_batch_world_size_2(tmp_path, ds):
                          env=env, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
     assert res.stdout.count("ok") == 2
+
+
+def test_shard_padding_changes_the_guidance_gradient_by_the_padding_ratio():
+    """Why dist.sample_guidance_sharded pads every shard to the GLOBAL ring count: the predictor pools with mean over the
+    padded nodes (edm/egnn_predictor/models.py:456-457), so the same molecules padded to 10 instead of 11 nodes get a
+    guidance gradient exactly 11/10 times larger (the 1.10x effect the round-1 review measured)."""
+    from helpers import cpu_weights, oracle_cfgs
+    args, model, pred, prop = build_models("cata", "cpu", hidden=(32, 32), layers=(1, 2), timesteps=20)
+    _, wp = cpu_weights(model, pred)
+    _, pcfg = oracle_cfgs("cata", hidden=(32, 32), layers=(1, 2))
+    nx = torch.tensor([10, 9, 4])
+    grads = {}
+    for n_pad in (10, 11):
+        nm, em = O.build_masks(nx, n_pad, False)
+        gen = torch.Generator().manual_seed(3)
+        z = O.draw_noise(3, 10, 4, O.build_masks(nx, 10, False)[0], generator=gen)
+        z = torch.nn.functional.pad(z, (0, 0, 0, n_pad - 10)).requires_grad_()
+        t = torch.full((3, 1), 0.5)
+        out = O.predictor_forward(wp, pcfg, z, nm, em, t)
+        (-out[:, 1]).sum().backward()
+        grads[n_pad] = z.grad[:, :10].clone()
+    assert float(grads[11].abs().max()) > 0
+    assert torch.allclose(grads[10], grads[11] * (11.0 / 10.0), rtol=2e-5, atol=1e-9)
+    # and the product helper refuses a padding below the largest molecule
+    with pytest.raises(ValueError):
+        gb.sample_guidance(gb.args_edm(device="cpu"), None, None, nx, max_nodes=9)
 
 
 _GRAD_WORKER = r"""
