@@ -15,6 +15,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libgaudi_b200.so")
+# development aid (tools/kernel_lab.py): load an alternative build of the same sources, e.g. compiled with other -D flags
+_LIB_OVERRIDE = os.environ.get("GAUDI_B200_LIB")
 
 _P = C.c_void_p
 _I = C.c_int
@@ -32,6 +34,8 @@ SIGNATURES = {
     "gb_net_destroy": (_I, [_P]),
     "gb_net_hidden_padded": (_I, [_P]),
     "gb_tile_pack": (_I, [_P, _I, _P, C.POINTER(_I)]),
+    "gb_tile_pack_graphs": (_I, [_P, _I, _I, _P, C.POINTER(_I)]),
+    "gb_stage_rows": (_I, []),
     "gb_graph_create": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gb_graph_destroy": (_I, [_P]),
     "gb_denoiser_workspace_bytes": (_SZ, [_P, _P]),
@@ -140,9 +144,13 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if is_stale():                          # missing, or built from older sources (ABI / behaviour mismatch after a pull)
-            build()
-        handle = C.CDLL(LIB_PATH)
+        if _LIB_OVERRIDE:
+            path = _LIB_OVERRIDE
+        else:
+            if is_stale():                      # missing, or built from older sources (ABI / behaviour mismatch after a pull)
+                build()
+            path = LIB_PATH
+        handle = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError here = header/library mismatch: fail loudly
             fn.restype = res

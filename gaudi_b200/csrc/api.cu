@@ -322,12 +322,39 @@ extern "C" int gb_tile_pack(const int32_t* rowptr, int n_nodes, int32_t* tile_pt
     return 0;
 }
 
-__global__ void tile_info_kernel(const int* __restrict__ tile_ptr, const int* __restrict__ rowptr, int n_tiles, int4* __restrict__ out) {
+extern "C" int gb_stage_rows(void) { return GB_PS_ROWS_HOST; }
+extern "C" int gb_tile_pack_graphs(const int32_t* rowptr, int n_nodes, int N, int32_t* tile_ptr, int* n_tiles_out) {
+    if (N <= 0) return gb_tile_pack(rowptr, n_nodes, tile_ptr, n_tiles_out);
+    int nt = 0, start = 0;
+    if (tile_ptr) tile_ptr[0] = 0;
+    while (start < n_nodes) {
+        int end = start;
+        while (end < n_nodes && (end - start) < GB_TM_HOST && rowptr[end + 1] - rowptr[start] <= GB_TM_HOST &&
+               (end + 1 - start) + (end / N - start / N + 1) * N <= GB_PS_ROWS_HOST) ++end;
+        if (end == start) {
+            if (rowptr[start + 1] - rowptr[start] > GB_TM_HOST)
+                return fail("node %d has %d edges (> %d per tile)", start, rowptr[start + 1] - rowptr[start], GB_TM_HOST);
+            return fail("graphs of %d padded nodes do not fit the %d staged rows of the edge kernels", N, GB_PS_ROWS_HOST);
+        }
+        ++nt;
+        if (tile_ptr) tile_ptr[nt] = end;
+        start = end;
+    }
+    *n_tiles_out = nt;
+    return 0;
+}
+
+__global__ void tile_info_kernel(const int* __restrict__ tile_ptr, const int* __restrict__ rowptr, int n_tiles, int N, int4* __restrict__ out,
+                                 int* __restrict__ bad) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
     const int lo = tile_ptr[t], hi = tile_ptr[t + 1];
     const int e_lo = rowptr[lo];
     out[t] = make_int4(lo, hi - lo, e_lo, rowptr[hi] - e_lo);
+    // contract of the edge kernels: <= 128 edges / nodes per tile, and the staged node-projection rows fit (gb_tile_pack_graphs)
+    const int rows = (hi - lo) + ((hi - 1) / N - lo / N + 1) * N;
+    if (hi <= lo || hi - lo > GB_TM_HOST || rowptr[hi] - e_lo > GB_TM_HOST || rows > GB_PS_ROWS_HOST) atomicOr(bad, 1);
+    atomicMax(bad + 1, rows);
 }
 
 extern "C" int gb_graph_create(gb_graph** out, int B, int N, int n_edges, int n_tiles, int n_tc, const int32_t* rowptr,
@@ -336,14 +363,22 @@ extern "C" int gb_graph_create(gb_graph** out, int B, int N, int n_edges, int n_
                                const int32_t* colptr, const int32_t* cedge, const float* node_mask) {
     (void)n_tc;
     if (!out) return fail("null argument");
+    int ps_rows = 0;
     int4* tinfo = nullptr;                       // the only memory a graph owns: 16 bytes per tile, derived from the caller's arrays
     if (n_tiles > 0) {
-        GB_CUDA(cudaMalloc(&tinfo, (size_t)n_tiles * sizeof(int4)));
-        tile_info_kernel<<<(n_tiles + 255) / 256, 256>>>(tile_ptr, rowptr, n_tiles, tinfo);
+        if (N <= 0) return fail("gb_graph_create: N must be positive");
+        GB_CUDA(cudaMalloc(&tinfo, ((size_t)n_tiles + 1) * sizeof(int4)));
+        int* bad = reinterpret_cast<int*>(tinfo + n_tiles);
+        GB_CUDA(cudaMemset(bad, 0, 2 * sizeof(int)));
+        tile_info_kernel<<<(n_tiles + 255) / 256, 256>>>(tile_ptr, rowptr, n_tiles, N, tinfo, bad);
         GB_CUDA(cudaDeviceSynchronize());        // not a hot-path call: graphs are created once per mask pair
+        int bad_h[2] = {0, 0};
+        GB_CUDA(cudaMemcpy(bad_h, bad, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+        ps_rows = bad_h[1];
+        if (bad_h[0]) { cudaFree(tinfo); return fail("gb_graph_create: tile_ptr violates the tile contract (pack it with gb_tile_pack_graphs)"); }
     }
     gb_graph* g = new gb_graph();
-    g->g = Graph{B * N, n_edges, n_tiles, B, N, rowptr, erow, ecol, tile_ptr, tc_ptr, tc_node, tc_start, cperm, colptr, cedge, node_mask, tinfo};
+    g->g = Graph{B * N, n_edges, n_tiles, B, N, rowptr, erow, ecol, tile_ptr, tc_ptr, tc_node, tc_start, cperm, colptr, cedge, node_mask, tinfo, ps_rows};
     *out = g;
     return 0;
 }

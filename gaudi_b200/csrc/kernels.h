@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #define GB_TM_HOST 128   // rows per tile (== GB_TM of common.cuh)
+#define GB_PS_ROWS_HOST 96   // node-projection rows staged per K-atom by the tcgen05 edge kernels (== tc::PS_ROWS)
 
 namespace gb {
 
@@ -29,6 +30,7 @@ struct Graph {
     const int* cedge;     // [n_edges] edge ids grouped by column node
     const float* node_mask;  // [n_nodes]
     const int4* tile_info;   // [n_tiles] (node_lo, n_nodes, e_lo, n_edges) of every tile: one load instead of a dependent chain
+    int ps_rows;             // max over tiles of (row nodes + nodes of the touched graphs): node-projection rows staged per K-atom
 };
 
 enum LinEpi { EPI_BIAS = 0, EPI_SILU = 1, EPI_RES_MASK = 2, EPI_MUL_DSILU = 3, EPI_ADD_RES = 4 };

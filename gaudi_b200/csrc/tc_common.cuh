@@ -10,6 +10,7 @@
 //   a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi   (dropped term ~2^-22 relative), accumulated in FP32 in TMEM.
 #pragma once
 #include "common.cuh"
+#include "kernels.h"
 
 namespace gb {
 namespace tc {
@@ -124,6 +125,168 @@ __device__ __forceinline__ void store_split(unsigned char* atom_hi, unsigned cha
     const uint32_t off = swz_offset(r, c);
     *reinterpret_cast<float4*>(atom_hi + off) = h;
     *reinterpret_cast<float4*>(atom_lo + off) = l;
+}
+
+// named barriers of the worker warps: ids 1-4 = the four warps sharing a TMEM lane quadrant (one per part; they exchange
+// per-row partial sums), 5-12 = the four warps of one part (they cover the 128 rows of a chunk), 13 = all workers
+__device__ __forceinline__ void bar_named(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+constexpr int BAR_QUAD = 1, BAR_PART = 5, BAR_WORKERS = 13;
+
+// Per-tile edge geometry is produced ONE TILE AHEAD by a dedicated warp into a double-buffered shared-memory block
+// (the dependent global-load chain tile_info -> erow/ecol -> coordinates used to stall all 16 worker warps at every tile
+// start: ~15 % of the stall samples of the round-1 kernels).  Layout of one block, in 32-bit words:
+//   [0,4) node_lo, n_nodes, e_lo, n_edges   [4,136) row-segment starts (tile-local)   then NF arrays of 128 (one per tile row)
+constexpr int GEO_HDR = 136;
+__host__ __device__ constexpr int geo_words(int nf) { return GEO_HDR + 128 * nf; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Operand rings of the edge kernels.  The activation (A) ring holds SA stages of [A hi | A lo] K-atoms written by the worker
+// warps; the weight (W) ring holds SW slots of ONE half-atom image each (hi or lo, NP x 128 B) streamed by the TMA warp in
+// the order the packed image stores them: hi(0), lo(0), hi(1), lo(1), ...  Per K-atom the MMA warp issues the two products
+// that read w_hi first, releases that slot, then the product that reads w_lo: three slots (instead of two stages of hi+lo)
+// keep one half-atom in flight ahead of the tensor pipe and free NP x 128 B of shared memory for the staged P rows.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NP>
+struct Rings {
+    static constexpr int SA = 2, SW = 3;
+    static constexpr int A_BYTES = 128 * ATOM_ROW_BYTES;     // one hi or lo image of a [128 x 32] activation atom
+    static constexpr int A_STAGE = 2 * A_BYTES;
+    static constexpr int W_BYTES = NP * ATOM_ROW_BYTES;      // one hi or lo image of a [NP x 32] weight atom
+    static constexpr int BYTES = SA * A_STAGE + SW * W_BYTES;
+    static constexpr int NBARS = 2 * SA + 2 * SW;
+    unsigned char* a_base; unsigned char* w_base;
+    uint64_t *full_a, *empty_a, *full_w, *empty_w;
+    __device__ __forceinline__ void carve(unsigned char* base, uint64_t* bars) {
+        a_base = base; w_base = base + SA * A_STAGE;
+        full_a = bars; empty_a = bars + SA; full_w = bars + 2 * SA; empty_w = full_w + SW;
+    }
+    __device__ __forceinline__ void init(int a_arrivals) {   // one thread
+        for (int s = 0; s < SA; ++s) { mbar_init(&full_a[s], a_arrivals); mbar_init(&empty_a[s], 1); }
+        for (int s = 0; s < SW; ++s) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], 1); }
+    }
+    // TMA warp (one lane): the 2*na half-atoms of one GEMM; wq = running half-atom counter of this CTA
+    __device__ __forceinline__ void tma_gemm(uint32_t& wq, int na, const float* wimg) const {
+        for (int h = 0; h < 2 * na; ++h, ++wq) {
+            const uint32_t s = wq % SW, r = wq / SW;
+            if (r > 0) mbar_wait(&empty_w[s], (r - 1) & 1);
+            mbar_arrive_expect_tx(&full_w[s], W_BYTES);
+            bulk_g2s(w_base + s * W_BYTES, wimg + (size_t)h * NP * ATOM_K, W_BYTES, &full_w[s]);
+        }
+    }
+    // MMA warp (one lane): na atoms of K (H columns) into accumulator d_tmem; it = running atom counter, wq as above
+    __device__ __forceinline__ void mma_gemm(uint32_t& it, uint32_t& wq, int na, int H, uint32_t d_tmem) const {
+        constexpr uint32_t idesc = instr_desc_tf32(NP);
+        for (int j = 0; j < na; ++j, ++it) {
+            const uint32_t sa = it % SA, ra = it / SA;
+            const int kvalid = H - j * ATOM_K;
+            const int ksteps = kvalid >= ATOM_K ? 4 : (kvalid + 7) / 8;
+            const uint32_t a_hi = smem_u32(a_base + sa * A_STAGE), a_lo = a_hi + A_BYTES;
+            mbar_wait(&full_a[sa], ra & 1);
+            {
+                const uint32_t s = wq % SW, r = wq / SW;
+                mbar_wait(&full_w[s], r & 1);
+                fence_after_sync();
+                const uint32_t w_hi = smem_u32(w_base + s * W_BYTES);
+                for (int kk = 0; kk < ksteps; ++kk) {
+                    const uint32_t ko = kk * 32;
+                    mma_tf32(d_tmem, smem_desc(a_lo + ko), smem_desc(w_hi + ko), idesc, (j | kk) != 0);
+                    mma_tf32(d_tmem, smem_desc(a_hi + ko), smem_desc(w_hi + ko), idesc, 1);
+                }
+                mma_commit(&empty_w[s]);
+                ++wq;
+            }
+            {
+                const uint32_t s = wq % SW, r = wq / SW;
+                mbar_wait(&full_w[s], r & 1);
+                fence_after_sync();
+                const uint32_t w_lo = smem_u32(w_base + s * W_BYTES);
+                for (int kk = 0; kk < ksteps; ++kk) mma_tf32(d_tmem, smem_desc(a_hi + kk * 32), smem_desc(w_lo + kk * 32), idesc, 1);
+                mma_commit(&empty_w[s]);
+                ++wq;
+            }
+            mma_commit(&empty_a[sa]);
+        }
+    }
+    // worker: publish this thread's 16 columns (4 x float4) of atom `it`; half h writes the 16-byte chunks 4h..4h+3 of its row
+    __device__ __forceinline__ void put_chunk(uint32_t it, int r, int half, const float4 (&x)[4]) const {
+        const uint32_t s = it % SA, rr = it / SA;
+        if (rr > 0) mbar_wait(&empty_a[s], (rr - 1) & 1);
+        unsigned char* a_hi = a_base + s * A_STAGE;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) store_split(a_hi, a_hi + A_BYTES, r, 4 * half + c, x[c]);
+        fence_proxy_async();
+        mbar_arrive(&full_a[s]);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Staged node projections.  The first edge Linear is factorised per node (P = h [W_a | W_b] + b, kernels.h), so the operand
+// build needs Pa[row] + Pb[col] per edge: ~10 edges share every row.  Instead of 2 x 16-byte L2 gathers per edge and
+// 4 columns (5x the unique bytes, on the same L2->SM path that streams the weights), two loader warps copy the 32-column
+// slice of the tile's row nodes (Pa) and of its molecules' nodes (Pb) once per K-atom into a two-stage ring with a
+// 36-float pitch (conflict-free float4 reads for consecutive nodes).  PS_ROWS bounds rows(Pa) + rows(Pb); the tile packer
+// (gb_tile_pack_graphs) guarantees it.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int PS_ROWS = 96;                                 // == GB_PS_ROWS_HOST (kernels.h), enforced by gb_tile_pack_graphs
+constexpr int PS_PITCH = 36;
+constexpr int PS_FLOATS = 2 * PS_ROWS * PS_PITCH;           // the whole ring: 2 stages of 96 rows or 4 stages of 48 rows
+constexpr int PS_BYTES = PS_FLOATS * 4;
+
+struct PStage {
+    float* buf; uint64_t* full; uint64_t* empty;            // [4] each; full: 1 arrival (loader lane 0), empty: 256 (two parts)
+    int lg;                                                 // log2(stages): 2 when every tile of the launch needs <= 48 rows, else 1
+    __device__ __forceinline__ void init() const { for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 256); } }
+    __device__ __forceinline__ uint32_t stage(uint32_t it) const { return it & ((1u << lg) - 1u); }
+    __device__ __forceinline__ uint32_t round(uint32_t it) const { return it >> lg; }
+    __device__ __forceinline__ float* ptr(uint32_t s) const { return buf + s * (PS_FLOATS >> lg); }
+    // worker side
+    __device__ __forceinline__ const float* acquire(uint32_t it) const { mbar_wait(&full[stage(it)], round(it) & 1); return ptr(stage(it)); }
+    __device__ __forceinline__ void release(uint32_t it) const { mbar_arrive(&empty[stage(it)]); }
+};
+
+// One loader warp (ldw = 0 / 1 handles the even / odd atoms of the CTA's running atom sequence): atom j of a tile.
+// P is [n_nodes][2H]; cn_lo/ncn = first node / node count of the molecules the tile's rows belong to.
+__device__ __forceinline__ void pstage_load_atom(const PStage& ps, uint32_t it, int j, int H, const float* __restrict__ P,
+                                                 int node_lo, int nn, int cn_lo, int ncn, int lane) {
+    const int rows = nn + ncn;
+    const uint32_t s = ps.stage(it), rr = ps.round(it);
+    if (rr > 0) mbar_wait(&ps.empty[s], (rr - 1) & 1);
+    float* dst = ps.ptr(s);
+    const int kbase = j * ATOM_K;
+    for (int i0 = 0; i0 < rows * 8; i0 += 384) {          // 12 independent 16-byte loads in flight per lane (48 rows per pass)
+        float4 v[12];
+#pragma unroll
+        for (int u = 0; u < 12; ++u) {
+            const int i = i0 + 32 * u + lane, row = i >> 3, kc = (i & 7) << 2;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < rows && kbase + kc < H) {
+                const float* src = row < nn ? P + (size_t)(node_lo + row) * (2 * H) : P + (size_t)(cn_lo + row - nn) * (2 * H) + H;
+                v[u] = __ldg(reinterpret_cast<const float4*>(src + kbase + kc));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 12; ++u) {
+            const int i = i0 + 32 * u + lane, row = i >> 3, kc = (i & 7) << 2;
+            if (row < rows) *reinterpret_cast<float4*>(dst + row * PS_PITCH + kc) = v[u];
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ps.full[s]);
+}
+
+// Edge list of one tile as the auxiliary warp keeps it in registers one tile ahead (lane l owns tile rows l, l+32, l+64, l+96)
+struct TileMeta { int node_lo, nn, e_lo, ne, cn_lo, ncn; int row[4], col[4]; };
+__device__ __forceinline__ void tile_meta_load(TileMeta& m, const Graph& g, int tile, int lane, bool with_edges) {
+    const int4 ti = __ldg(g.tile_info + tile);
+    m.node_lo = ti.x; m.nn = ti.y; m.e_lo = ti.z; m.ne = ti.w;
+    m.cn_lo = (ti.x / g.N) * g.N;
+    m.ncn = min(((ti.x + ti.y - 1) / g.N + 1) * g.N, g.n_nodes) - m.cn_lo;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int r = lane + 32 * q;
+        m.row[q] = 0; m.col[q] = 0;
+        if (with_edges && r < ti.w) { m.row[q] = __ldg(g.erow + ti.z + r); m.col[q] = __ldg(g.ecol + ti.z + r); }
+    }
 }
 
 }  // namespace tc

@@ -12,24 +12,39 @@
 namespace gb {
 using namespace tc;
 
+// Optional clock64 timeline of CTA 0 (make EXTRA=-DGB_TIMELINE; tools/edge_timeline.py): role 0 = worker part 0 / lane 0,
+// 1 = worker part 2 / lane 0, 2 = MMA lane, 3 = aux warp 0, 4 = aux warp 1.  Each record = (code, clock).
+#ifdef GB_TIMELINE
+__device__ unsigned long long gb_tl_den[5][2048];
+__device__ unsigned int gb_tl_den_n[5];
+#define TLD(role, code) do { if (blockIdx.x == 0) { unsigned int i_ = gb_tl_den_n[role]; if (i_ < 1023) { gb_tl_den[role][2 * i_] = (code); gb_tl_den[role][2 * i_ + 1] = clock64(); gb_tl_den_n[role] = i_ + 1; } } } while (0)
+#else
+#define TLD(role, code) do {} while (0)
+#endif
+
 template <int NP>
 struct TcEdgeCfg {
-    static constexpr int S = 2;
-    static constexpr int A_BYTES = 128 * ATOM_ROW_BYTES;
-    static constexpr int W_BYTES = NP * ATOM_ROW_BYTES;
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+    using R = Rings<NP>;
     static constexpr int NPARTS = 4;                         // worker parts of 4 warps; part p owns 16-column chunks ch == p (mod 4)
     static constexpr int NWORK = 128 * NPARTS;
-    static constexpr int THREADS = 64 + NWORK;
+    // two auxiliary warps stage the P rows of every K-atom (even / odd atoms); the first one also prepares the edge geometry
+    // of its next tile before that tile's first atom, i.e. while the workers are still in the previous tile's epilogue.
+    // (20 warps: register allocation is per 4 warps, a 21st warp would cap every thread at 80 registers)
+    static constexpr int AUX_WARP = 2 + NWORK / 32;
+    static constexpr int THREADS = 64 + NWORK + 64;
     static constexpr int MAXCH = (NP + 15) / 16;             // 16-column chunks
     static constexpr int MYCH = (MAXCH + NPARTS - 1) / NPARTS;
     static constexpr int EF_STRIDE = 17;
-    static constexpr int SCRATCH = 6 * NP * 4 + NPARTS * 128 * 4 + NPARTS * 128 * EF_STRIDE * 4 + 129 * 4 + 128 * 3 * 4 + 64;
-    static constexpr int SMEM = S * STAGE_BYTES + 1024 + 256 + SCRATCH;
-    static constexpr int TMEM_COLS = NP <= 64 ? 64 : 256;
+    static constexpr int GEO_NF = 7;                         // P-stage row of the row node / of the col node, radial, d0, unit vector (3)
+    static constexpr int GEO_WORDS = geo_words(GEO_NF);
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int NGEO = 3;                           // tile k builds while tile k-1 is in its epilogue and k+1 is being prepared
+    static constexpr int SCRATCH = 4 * NP * 4 + 2 * NPARTS * 128 * 4 + NPARTS * 128 * EF_STRIDE * 4 + NGEO * GEO_WORDS * 4 + 2 * 128 * 3 * 4 + PS_BYTES + 64;
+    static constexpr int SMEM = R::BYTES + 1024 + BAR_BYTES + SCRATCH;
+    static constexpr int ACC_STRIDE = NP <= 64 ? 64 : 256;   // two accumulators: the MMAs of tile k+1 run during the epilogue of tile k
+    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+    static_assert(NP > 208 || SMEM <= 232448, "shared memory budget");   // NP = 256 is instantiated but never launched (api.cu)
 };
-
-__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 template <int NP, int MODE>
 __global__ void __launch_bounds__(TcEdgeCfg<NP>::THREADS, 1) tc_den_edge_kernel(DenEdgeArgs a, const float* __restrict__ wimg, int H) {
@@ -38,20 +53,25 @@ __global__ void __launch_bounds__(TcEdgeCfg<NP>::THREADS, 1) tc_den_edge_kernel(
     // 1024-byte alignment by pointer arithmetic on the __shared__ array: the compiler keeps the address space (LDS / STS
     // instead of generic LD / ST for every staging and operand access)
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::S * CF::STAGE_BYTES);
-    uint64_t* full_a = bars; uint64_t* full_w = bars + CF::S; uint64_t* empty = bars + 2 * CF::S;
-    uint64_t* d_full = bars + 3 * CF::S; uint64_t* d_empty = d_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 1);
-    float* vec_s = reinterpret_cast<float*>(base + CF::S * CF::STAGE_BYTES + 256);    // [4][NP]: w_r, w_d, b2, vecw
-    float* red_s = vec_s + 6 * NP;                                                       // [2][128]
-    float* ef_s = red_s + CF::NPARTS * 128;                                              // [NPARTS][128][17]
-    int* seg_s = reinterpret_cast<int*>(ef_s + CF::NPARTS * 128 * CF::EF_STRIDE);        // [129]
-    float* tr_s = reinterpret_cast<float*>(seg_s + 129);                                 // [128][3]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::R::BYTES);
+    Rings<NP> rg; rg.carve(base, bars);
+    uint64_t* d_full = bars + CF::R::NBARS; uint64_t* d_empty = d_full + 2;
+    uint64_t* geo_full = d_empty + 2; uint64_t* geo_empty = geo_full + CF::NGEO;
+    uint64_t* ps_full = geo_empty + CF::NGEO; uint64_t* ps_empty = ps_full + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ps_empty + 4);
+    float* vec_s = reinterpret_cast<float*>(base + CF::R::BYTES + CF::BAR_BYTES);     // [4][NP]: w_r, w_d, b2, vecw
+    float* red_s = vec_s + 4 * NP;                                                       // [2][NPARTS][128] (tile parity)
+    float* ef_s = red_s + 2 * CF::NPARTS * 128;                                          // [NPARTS][128][17]
+    int* geo_s = reinterpret_cast<int*>(ef_s + CF::NPARTS * 128 * CF::EF_STRIDE);        // [NGEO][GEO_WORDS]
+    float* tr_s = reinterpret_cast<float*>(geo_s + CF::NGEO * CF::GEO_WORDS);            // [2][128][3] (tile parity)
+    const PStage ps{tr_s + 2 * 128 * 3, ps_full, ps_empty, a.g.ps_rows <= PS_ROWS / 2 ? 2 : 1};  // 4 x 48 or 2 x 96 rows of 36 floats
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < CF::S; ++s) { mbar_init(&full_a[s], 256); mbar_init(&full_w[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(d_full, 1); mbar_init(d_empty, CF::NWORK);
+        rg.init(256);
+        for (int b = 0; b < 2; ++b) { mbar_init(&d_full[b], 1); mbar_init(&d_empty[b], CF::NWORK); }
+        for (int b = 0; b < CF::NGEO; ++b) { mbar_init(&geo_full[b], 1); mbar_init(&geo_empty[b], CF::NWORK); }
+        ps.init();
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<CF::TMEM_COLS>(tmem_slot);
@@ -66,88 +86,112 @@ __global__ void __launch_bounds__(TcEdgeCfg<NP>::THREADS, 1) tc_den_edge_kernel(
     const uint32_t tmem_base = *tmem_slot;
     const Graph& g = a.g;
     const int na = (H + ATOM_K - 1) / ATOM_K;
-    const size_t atom_floats = (size_t)2 * NP * ATOM_K;
-    constexpr uint32_t idesc = instr_desc_tf32(NP);
 
     if (warp == 0) {
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x)
-                for (int j = 0; j < na; ++j, ++it) {
-                    const uint32_t s = it % CF::S, r = it / CF::S;
-                    if (r > 0) mbar_wait(&empty[s], (r - 1) & 1);
-                    mbar_arrive_expect_tx(&full_w[s], 2 * CF::W_BYTES);
-                    bulk_g2s(base + s * CF::STAGE_BYTES + 2 * CF::A_BYTES, wimg + (size_t)j * atom_floats, 2 * CF::W_BYTES, &full_w[s]);
-                }
+            uint32_t wq = 0;
+            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) rg.tma_gemm(wq, na, wimg);
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            uint32_t it = 0, tcnt = 0;
+            uint32_t it = 0, wq = 0, tcnt = 0;
             for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
-                if (tcnt > 0) mbar_wait(d_empty, (tcnt - 1) & 1);
+                const uint32_t ab = tcnt & 1, use = tcnt >> 1;
+                if (use > 0) mbar_wait(&d_empty[ab], (use - 1) & 1);
                 fence_after_sync();
-                for (int j = 0; j < na; ++j, ++it) {
-                    const uint32_t s = it % CF::S, r = it / CF::S;
-                    const int kvalid = H - j * ATOM_K;
-                    const int ksteps = kvalid >= ATOM_K ? 4 : (kvalid + 7) / 8;
-                    mbar_wait(&full_a[s], r & 1);
-                    mbar_wait(&full_w[s], r & 1);
-                    fence_after_sync();
-                    const uint32_t a_hi = smem_u32(base + s * CF::STAGE_BYTES), a_lo = a_hi + CF::A_BYTES;
-                    const uint32_t w_hi = a_hi + 2 * CF::A_BYTES, w_lo = w_hi + CF::W_BYTES;
-                    for (int kk = 0; kk < ksteps; ++kk) {
-                        const uint32_t ko = kk * 32;
-                        mma_tf32(tmem_base, smem_desc(a_lo + ko), smem_desc(w_hi + ko), idesc, (j | kk) != 0);
-                        mma_tf32(tmem_base, smem_desc(a_hi + ko), smem_desc(w_lo + ko), idesc, 1);
-                        mma_tf32(tmem_base, smem_desc(a_hi + ko), smem_desc(w_hi + ko), idesc, 1);
+                TLD(2, 1);
+                rg.mma_gemm(it, wq, na, H, tmem_base + ab * CF::ACC_STRIDE);
+                mma_commit(&d_full[ab]);
+                TLD(2, 2);
+            }
+        }
+    } else if (warp >= CF::AUX_WARP) {
+        // ---- auxiliary warps.  Both stage P rows (warp 0: even atoms, warp 1: odd atoms of the CTA's atom sequence); warp 1 also
+        //      keeps the NEXT tile's edge list in registers while this tile's atoms are loaded and writes that tile's geometry block
+        //      (header, row-segment table, per-edge P-stage rows / radial / d0 / unit vector) before the workers get there ----
+        const int ldw = warp - CF::AUX_WARP;
+        auto geo_emit = [&](const TileMeta& m, uint32_t tc) {
+            const uint32_t gb_ = tc % CF::NGEO, use = tc / CF::NGEO;
+            if (use > 0) mbar_wait(&geo_empty[gb_], (use - 1) & 1);
+            int* gi = geo_s + gb_ * CF::GEO_WORDS;
+            float* gf = reinterpret_cast<float*>(gi);
+            if (lane == 0) { gi[0] = m.node_lo; gi[1] = m.nn; gi[2] = m.e_lo; gi[3] = m.ne; }
+            for (int i = lane; i <= m.nn; i += 32) gi[4 + i] = __ldg(g.rowptr + m.node_lo + i) - m.e_lo;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = lane + 32 * q;
+                int prow = 0, pcol = 0; float rad = 0.f, d0 = 0.f, ux = 0.f, uy = 0.f, uz = 0.f;
+                if (r < m.ne) {
+                    const int e = m.e_lo + r, rown = m.row[q], coln = m.col[q];
+                    prow = rown - m.node_lo; pcol = m.nn + coln - m.cn_lo;
+                    if (a.eattr) { rad = a.eattr[2 * e]; d0 = a.eattr[2 * e + 1]; }
+                    else {
+                        const float dx = a.x[3 * rown] - a.x[3 * coln], dy = a.x[3 * rown + 1] - a.x[3 * coln + 1], dz = a.x[3 * rown + 2] - a.x[3 * coln + 2];
+                        rad = dx * dx + dy * dy + dz * dz;
+                        const float ex = a.x0[3 * rown] - a.x0[3 * coln], ey = a.x0[3 * rown + 1] - a.x0[3 * coln + 1], ez = a.x0[3 * rown + 2] - a.x0[3 * coln + 2];
+                        d0 = ex * ex + ey * ey + ez * ez;
+                        if (a.d0_edge) d0 = a.d0_edge[e];
+                        if (MODE == 1) { const float inv = 1.f / (sqrtf(rad + 1e-8f) + a.norm_constant); ux = dx * inv; uy = dy * inv; uz = dz * inv; }
                     }
-                    mma_commit(&empty[s]);
+                    if (MODE == 1 && a.cdiff) { ux = a.cdiff[3 * e]; uy = a.cdiff[3 * e + 1]; uz = a.cdiff[3 * e + 2]; }
                 }
-                mma_commit(d_full);
+                gi[GEO_HDR + r] = prow; gi[GEO_HDR + 128 + r] = pcol;
+                gf[GEO_HDR + 256 + r] = rad; gf[GEO_HDR + 384 + r] = d0;
+                if (MODE == 1) { gf[GEO_HDR + 512 + r] = ux; gf[GEO_HDR + 640 + r] = uy; gf[GEO_HDR + 768 + r] = uz; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&geo_full[gb_]);
+        };
+        TileMeta cur, nxt;
+        int tile = blockIdx.x;
+        if (tile < g.n_tiles) {
+            tile_meta_load(cur, g, tile, lane, ldw == 1);
+            if (ldw == 1) geo_emit(cur, 0);
+        }
+        for (uint32_t tcnt = 0; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
+            const int ntile = tile + gridDim.x;
+            if (ntile < g.n_tiles) tile_meta_load(nxt, g, ntile, lane, ldw == 1);
+            for (int j = 0; j < na; ++j) {
+                const uint32_t it = tcnt * na + j;
+                if ((int)(it & 1) == ldw) { pstage_load_atom(ps, it, j, H, a.P, cur.node_lo, cur.nn, cur.cn_lo, cur.ncn, lane); if (lane == 0) TLD(3 + ldw, 20 + j); }
+            }
+            if (ntile < g.n_tiles) {
+                if (ldw == 1) { geo_emit(nxt, tcnt + 1); if (lane == 0) TLD(4, 70); }
+                cur = nxt;
             }
         }
     } else {
         const int group = warp & 3, part = (warp - 2) >> 2, half = part & 1;
         const int r = group * 32 + lane;                       // tile row == TMEM lane
-        const int ht = r;                                      // thread index inside this half (0..127)
+        const int ht = r;                                      // thread index inside this part (0..127)
         const uint32_t lane_addr = tmem_base + ((uint32_t)(group * 32) << 16);
         const int nchunks = (H + 15) / 16;
         float* my_ef = ef_s + part * 128 * CF::EF_STRIDE;
-        uint32_t tcnt = 0;
-        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
-            const int4 ti = __ldg(g.tile_info + tile);
-            const int node_lo = ti.x, nn = ti.y, e_lo = ti.z, ne = ti.w;
-            const bool valid = r < ne;
-            int rown = 0, coln = 0; float rad = 0.f, d0 = 0.f, ux = 0.f, uy = 0.f, uz = 0.f;
-            if (valid) {
-                const int e = e_lo + r;
-                rown = g.erow[e]; coln = g.ecol[e];
-                if (a.eattr) { rad = a.eattr[2 * e]; d0 = a.eattr[2 * e + 1]; }
-                else {
-                    const float dx = a.x[3 * rown] - a.x[3 * coln], dy = a.x[3 * rown + 1] - a.x[3 * coln + 1], dz = a.x[3 * rown + 2] - a.x[3 * coln + 2];
-                    rad = dx * dx + dy * dy + dz * dz;
-                    const float ex = a.x0[3 * rown] - a.x0[3 * coln], ey = a.x0[3 * rown + 1] - a.x0[3 * coln + 1], ez = a.x0[3 * rown + 2] - a.x0[3 * coln + 2];
-                    d0 = ex * ex + ey * ey + ez * ez;
-                    if (a.d0_edge) d0 = a.d0_edge[e];
-                    if (MODE == 1) { const float inv = 1.f / (sqrtf(rad + 1e-8f) + a.norm_constant); ux = dx * inv; uy = dy * inv; uz = dz * inv; }
-                }
-                if (MODE == 1 && a.cdiff) { ux = a.cdiff[3 * e]; uy = a.cdiff[3 * e + 1]; uz = a.cdiff[3 * e + 2]; }
-            }
-            if (part == 0) for (int i = ht; i <= nn; i += 128) seg_s[i] = g.rowptr[node_lo + i] - e_lo;
-            // ---- build activation atoms ----
-            const float* pa_row = a.P + (size_t)rown * (2 * H);
-            const float* pb_row = a.P + (size_t)coln * (2 * H) + H;
+        const int tlr = (lane == 0 && group == 0) ? (part == 0 ? 0 : (part == 2 ? 1 : -1)) : -1;
+        (void)tlr;
+        // ---- operand build of tile number k (the CTA's k-th tile): SiLU(Pa[row] + Pb[col] + w_r r + w_d d0) as hi/lo atoms ----
+        auto build = [&](uint32_t k) {
+            const uint32_t gb_ = k % CF::NGEO;
+            if (tlr >= 0) TLD(tlr, 10);
+            mbar_wait(&geo_full[gb_], (k / CF::NGEO) & 1);
+            if (tlr >= 0) TLD(tlr, 11);
+            const int* gi = geo_s + gb_ * CF::GEO_WORDS;
+            const float* gf = reinterpret_cast<const float*>(gi);
+            const bool valid = r < gi[3];
+            const int pa_off = gi[GEO_HDR + r] * PS_PITCH + 16 * half, pb_off = gi[GEO_HDR + 128 + r] * PS_PITCH + 16 * half;
+            const float rad = gf[GEO_HDR + 256 + r], d0 = gf[GEO_HDR + 384 + r];
             for (int j = part >> 1; j < na; j += 2) {
-                const uint32_t it = tcnt * na + j;
-                const uint32_t s = it % CF::S, rr = it / CF::S;
+                const uint32_t it = k * na + j;
+                const float* pst = ps.acquire(it);
+                if (tlr >= 0) TLD(tlr, 20 + j);
                 float4 x[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int k0 = j * ATOM_K + 16 * half + 4 * c;
                     x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (valid && k0 < H) {
-                        const float4 pa = __ldg(reinterpret_cast<const float4*>(pa_row + k0));
-                        const float4 pb = __ldg(reinterpret_cast<const float4*>(pb_row + k0));
+                        const float4 pa = *reinterpret_cast<const float4*>(pst + pa_off + 4 * c);
+                        const float4 pb = *reinterpret_cast<const float4*>(pst + pb_off + 4 * c);
                         const float4 wr = *reinterpret_cast<const float4*>(vec_s + k0);
                         const float4 wd = *reinterpret_cast<const float4*>(vec_s + NP + k0);
                         x[c].x = silu_f(pa.x + pb.x + wr.x * rad + wd.x * d0);
@@ -156,15 +200,28 @@ __global__ void __launch_bounds__(TcEdgeCfg<NP>::THREADS, 1) tc_den_edge_kernel(
                         x[c].w = silu_f(pa.w + pb.w + wr.w * rad + wd.w * d0);
                     }
                 }
-                if (rr > 0) mbar_wait(&empty[s], (rr - 1) & 1);
-                unsigned char* a_hi = base + s * CF::STAGE_BYTES;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) store_split(a_hi, a_hi + CF::A_BYTES, r, 4 * half + c, x[c]);
-                fence_proxy_async();
-                mbar_arrive(&full_a[s]);
+                ps.release(it);                                  // P slice consumed (the loads above fed the arithmetic)
+                if (tlr >= 0) TLD(tlr, 30 + j);
+                rg.put_chunk(it, r, half, x);
+                if (tlr >= 0) TLD(tlr, 40 + j);
             }
-            // ---- epilogue ----
-            mbar_wait(d_full, tcnt & 1);
+        };
+        // Software pipeline over the CTA's tiles: build(0); then per tile k: build(k+1), epilogue(k) -- the tensor pipe works on
+        // tile k+1 (second accumulator) while the workers run the epilogue of tile k.
+        uint32_t k = 0;
+        int tile = blockIdx.x;
+        if (tile < g.n_tiles) build(0);
+        for (; tile < g.n_tiles; tile += gridDim.x, ++k) {
+            if (tile + (int)gridDim.x < g.n_tiles) build(k + 1);
+            // ---- epilogue of tile k ----
+            const uint32_t gb_ = k % CF::NGEO, ab = k & 1;
+            const int* gi = geo_s + gb_ * CF::GEO_WORDS;
+            const float* gf = reinterpret_cast<const float*>(gi);
+            const int* seg_s = gi + 4;
+            const int node_lo = gi[0], nn = gi[1];
+            float* red = red_s + ab * CF::NPARTS * 128;
+            mbar_wait(&d_full[ab], (k >> 1) & 1);
+            if (tlr >= 0) TLD(tlr, 50);
             fence_after_sync();
             float m[CF::MYCH][16];
             float psum = 0.f;
@@ -172,7 +229,7 @@ __global__ void __launch_bounds__(TcEdgeCfg<NP>::THREADS, 1) tc_den_edge_kernel(
             for (int ci = 0; ci < CF::MYCH; ++ci) {
                 const int ch = part + CF::NPARTS * ci;
                 if (ch < nchunks) {
-                    tmem_ld16(lane_addr + ch * 16, m[ci]);
+                    tmem_ld16(lane_addr + ab * CF::ACC_STRIDE + ch * 16, m[ci]);
 #pragma unroll
                     for (int q = 0; q < 16; ++q) {
                         const int c = ch * 16 + q;
@@ -183,56 +240,65 @@ __global__ void __launch_bounds__(TcEdgeCfg<NP>::THREADS, 1) tc_den_edge_kernel(
                 }
             }
             fence_before_sync();
-            mbar_arrive(d_empty);                               // accumulator is in registers: the next tile's MMAs may start
-            red_s[part * 128 + r] = psum;
-            named_bar(1, CF::NWORK);
-            const float dot = red_s[r] + red_s[128 + r] + red_s[256 + r] + red_s[384 + r];
+            mbar_arrive(&d_empty[ab]);                          // accumulator is in registers: the MMAs of tile k+2 may overwrite it
+            // red / tr are double-buffered by tile parity: a warp can be one tile ahead of another one (it passed the barriers of
+            // tile k with it), never two, because it needs that warp's arrival at the barriers of tile k+1
+            red[part * 128 + r] = psum;
+            if (tlr >= 0) TLD(tlr, 51);
+            bar_named(BAR_QUAD + group, 128);                   // the four warps of this TMEM lane quadrant, one per part
+            if (tlr >= 0) TLD(tlr, 52);
+            const float dot = red[r] + red[128 + r] + red[256 + r] + red[384 + r];
             if (MODE == 0) {
                 const float gate = a.attention ? sigmoid_f(dot + a.att_b) : 1.f;
 #pragma unroll
                 for (int ci = 0; ci < CF::MYCH; ++ci) {
                     const int ch = part + CF::NPARTS * ci;
-                    if (ch < nchunks) {                          // uniform across the half
+                    if (ch < nchunks) {                          // uniform across the part
 #pragma unroll
                         for (int q = 0; q < 16; ++q) my_ef[r * CF::EF_STRIDE + q] = m[ci][q] * gate;
-                        named_bar(2 + part, 128);
+                        bar_named(BAR_PART + part, 128);
                         for (int nl = ht >> 4; nl < nn; nl += 8) {
                             const int col = ht & 15, c = ch * 16 + col;
                             float sum = 0.f;
                             for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += my_ef[mm * CF::EF_STRIDE + col];
                             if (c < H) a.agg[(size_t)(node_lo + nl) * H + c] = sum / a.normf;
                         }
-                        named_bar(2 + part, 128);
+                        bar_named(BAR_PART + part, 128);
                     }
                 }
             } else {
+                float* tr = tr_s + ab * 128 * 3;
                 if (part == 0) {
-                    float sc;
-                    if (a.use_tanh) {
-                        const float th = tanhf(dot);
-                        tr_s[3 * r] = ux * th * a.coords_range; tr_s[3 * r + 1] = uy * th * a.coords_range; tr_s[3 * r + 2] = uz * th * a.coords_range;
-                    } else {
-                        sc = dot;
-                        tr_s[3 * r] = ux * sc; tr_s[3 * r + 1] = uy * sc; tr_s[3 * r + 2] = uz * sc;
-                    }
+                    const float ux = gf[GEO_HDR + 512 + r], uy = gf[GEO_HDR + 640 + r], uz = gf[GEO_HDR + 768 + r];
+                    const float sc = a.use_tanh ? tanhf(dot) * a.coords_range : dot;
+                    tr[3 * r] = ux * sc; tr[3 * r + 1] = uy * sc; tr[3 * r + 2] = uz * sc;
                 }
-                named_bar(1, CF::NWORK);
+                bar_named(BAR_WORKERS, CF::NWORK);
                 const int wt = part * 128 + ht;
                 for (int idx = wt; idx < nn * 3; idx += CF::NWORK) {
                     const int nl = idx / 3, d = idx - 3 * nl;
                     float sum = 0.f;
-                    for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += tr_s[3 * mm + d];
+                    for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += tr[3 * mm + d];
                     const int node = node_lo + nl;
                     a.x_out[3 * node + d] = (a.x[3 * node + d] + sum / a.normf) * g.node_mask[node];
                 }
             }
-            named_bar(1, CF::NWORK);                                  // scratch (seg_s, red_s, tr_s) free for the next tile
+            mbar_arrive(&geo_empty[gb_]);                        // header / segment table of tile k no longer needed
+            if (tlr >= 0) TLD(tlr, 60);
         }
     }
     fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc<CF::TMEM_COLS>(tmem_base);
 }
+
+#ifdef GB_TIMELINE
+extern "C" int gb_debug_timeline_den(unsigned long long* out, unsigned int* n, int reset) {
+    if (reset) { unsigned int z[5] = {0, 0, 0, 0, 0}; return (int)cudaMemcpyToSymbol(gb_tl_den_n, z, sizeof(z)); }
+    cudaMemcpyFromSymbol(n, gb_tl_den_n, sizeof(gb_tl_den_n));
+    return (int)cudaMemcpyFromSymbol(out, gb_tl_den, sizeof(gb_tl_den));
+}
+#endif
 
 template <int NP>
 static void launch_t(int mode, const DenEdgeArgs& a, const float* wimg, int H, cudaStream_t s) {

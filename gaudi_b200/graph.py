@@ -70,14 +70,16 @@ class Topology:
     cedge: torch.Tensor = None       # int32 [n_edges] edge ids in CSC order
 
 
-def tile_pack(rowptr_host: np.ndarray) -> np.ndarray:
-    """Greedy tiling of consecutive nodes (<=128 edges and <=128 nodes per tile); C helper ``gb_tile_pack``."""
+def tile_pack(rowptr_host: np.ndarray, nodes_per_graph: int = 0) -> np.ndarray:
+    """Greedy tiling of consecutive nodes (<=128 edges and <=128 nodes per tile); C helper ``gb_tile_pack_graphs``.
+    With ``nodes_per_graph`` (the padded N) a tile also keeps  nodes + N * graphs_touched <= gb_stage_rows()  so that the
+    edge kernels can stage the node projections of the tile in shared memory."""
     rowptr_host = np.ascontiguousarray(rowptr_host, dtype=np.int32)
     n_nodes = rowptr_host.shape[0] - 1
     out = np.zeros(n_nodes + 1, dtype=np.int32)
     n_tiles = C.c_int(0)
-    _lib.check(_lib.lib().gb_tile_pack(rowptr_host.ctypes.data_as(C.c_void_p), n_nodes,
-                                       out.ctypes.data_as(C.c_void_p), C.byref(n_tiles)))
+    _lib.check(_lib.lib().gb_tile_pack_graphs(rowptr_host.ctypes.data_as(C.c_void_p), n_nodes, int(nodes_per_graph),
+                                              out.ctypes.data_as(C.c_void_p), C.byref(n_tiles)))
     return out[: n_tiles.value + 1].copy()
 
 
@@ -95,7 +97,7 @@ def build_topology(node_mask: torch.Tensor, edge_mask: torch.Tensor, B: int, N: 
     erow = torch.div(flat, N, rounding_mode="floor")
     ecol = torch.div(erow, N, rounding_mode="floor") * N + flat % N
     n_edges = int(flat.numel())
-    tile_ptr_h = tile_pack(rowptr.cpu().numpy().astype(np.int32))
+    tile_ptr_h = tile_pack(rowptr.cpu().numpy().astype(np.int32), N)
     n_tiles = tile_ptr_h.shape[0] - 1
     tile_ptr = torch.from_numpy(tile_ptr_h).to(dev)
     # per-tile grouping of the edges by column node (backward column scatter)

@@ -56,6 +56,11 @@ int gb_net_hidden_padded(const gb_net* net);
  *   tc_ptr[n_tiles+1], tc_node[n_tc], tc_start[n_tc+1], cperm[n_edges]: each tile's edges grouped by column node
  *   colptr[n_nodes+1], cedge[n_edges]: CSC view (edge ids grouped by column node, ascending edge id inside a group) */
 int gb_tile_pack(const int32_t* rowptr_host, int n_nodes, int32_t* tile_ptr_host_out, int* n_tiles_out);
+/* Same greedy packing for a batch of graphs with nodes_per_graph padded nodes each (edges never leave their graph): a tile
+ * additionally satisfies  n_nodes(tile) + nodes_per_graph * graphs_touched(tile) <= gb_stage_rows(),  the number of node-projection
+ * rows the tcgen05 edge kernels stage in shared memory per K-atom.  gb_graph_create requires tiles packed this way. */
+int gb_tile_pack_graphs(const int32_t* rowptr_host, int n_nodes, int nodes_per_graph, int32_t* tile_ptr_host_out, int* n_tiles_out);
+int gb_stage_rows(void);
 int gb_graph_create(gb_graph** out, int B, int N, int n_edges, int n_tiles, int n_tc, const int32_t* rowptr,
                     const int32_t* erow, const int32_t* ecol, const int32_t* tile_ptr, const int32_t* tc_ptr,
                     const int32_t* tc_node, const int32_t* tc_start, const int32_t* cperm, const int32_t* colptr,
