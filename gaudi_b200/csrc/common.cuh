@@ -45,6 +45,41 @@ __device__ __forceinline__ void silu_both(float x, float& y, float& dy) {
     dy = s * (1.f + x * (1.f - s));
 }
 
+// ---- packed FP32 (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per issue slot) versions of the activation math.
+// The worker warps of the edge kernels are issue-bound (clock64 timelines, round 2): halving the FMUL / FADD / FFMA count of
+// the element-wise phases is worth more than anything else there.  The MUFU ops stay scalar (there is no packed MUFU).
+typedef float2 f2;
+__device__ __forceinline__ f2 f2s(float s) { return make_float2(s, s); }
+__device__ __forceinline__ f2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ f2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float4 cat2(f2 a, f2 b) { return make_float4(a.x, a.y, b.x, b.y); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 ex2_2(f2 x) {
+    f2 r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(x.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(x.y));
+    return r;
+}
+__device__ __forceinline__ f2 rcp_2(f2 x) {
+    f2 r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(x.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(x.y));
+    return r;
+}
+__device__ __forceinline__ f2 sigmoid2(f2 x) { return rcp_2(add2(ex2_2(mul2(x, f2s(-1.4426950408889634f))), f2s(1.f))); }
+__device__ __forceinline__ f2 silu2(f2 x) { return mul2(x, sigmoid2(x)); }
+__device__ __forceinline__ f2 dsilu2(f2 x) {                    // s * (1 + x * (1 - s))
+    const f2 s = sigmoid2(x);
+    return mul2(s, fma2(x, fma2(s, f2s(-1.f), f2s(1.f)), f2s(1.f)));
+}
+__device__ __forceinline__ void silu_both2(f2 x, f2& y, f2& dy) {
+    const f2 s = sigmoid2(x);
+    y = mul2(x, s);
+    dy = mul2(s, fma2(x, fma2(s, f2s(-1.f), f2s(1.f)), f2s(1.f)));
+}
+
 // packed FP32 FMA (sm_100+ FFMA2): (d0,d1) += (a,a) * (b0,b1) in one issue slot
 __device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, float b1) {
     asm("{\n\t.reg .b64 ra, rb, rc;\n\t"

@@ -116,6 +116,17 @@ __device__ __forceinline__ void tmem_ld16_issue_f(uint32_t taddr, float (&v)[16]
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 lanes x 16 columns back into tensor memory (thread t writes row lane base + t): lets an epilogue park a partially processed
+// accumulator chunk in TMEM instead of in 16 registers while it waits for a row-wide reduction
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+          "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Write 4 consecutive fp32 (one 16-byte chunk c of row r) of an A atom as the hi / lo split.
 __device__ __forceinline__ void store_split(unsigned char* atom_hi, unsigned char* atom_lo, int r, int c, float4 x) {
@@ -125,6 +136,15 @@ __device__ __forceinline__ void store_split(unsigned char* atom_hi, unsigned cha
     const uint32_t off = swz_offset(r, c);
     *reinterpret_cast<float4*>(atom_hi + off) = h;
     *reinterpret_cast<float4*>(atom_lo + off) = l;
+}
+
+// the same for two packed pairs: hi by masking (exactly a TF32 value), lo = x - hi as one packed FMA each (exact)
+__device__ __forceinline__ void store_split2(unsigned char* atom_hi, unsigned char* atom_lo, int r, int c, f2 a, f2 b) {
+    const f2 ha = make_float2(tf32_hi(a.x), tf32_hi(a.y)), hb = make_float2(tf32_hi(b.x), tf32_hi(b.y));
+    const f2 la = fma2(ha, f2s(-1.f), a), lb = fma2(hb, f2s(-1.f), b);
+    const uint32_t off = swz_offset(r, c);
+    *reinterpret_cast<float4*>(atom_hi + off) = cat2(ha, hb);
+    *reinterpret_cast<float4*>(atom_lo + off) = cat2(la, lb);
 }
 
 // named barriers of the worker warps: ids 1-4 = the four warps sharing a TMEM lane quadrant (one per part; they exchange
@@ -206,6 +226,16 @@ struct Rings {
             }
             mma_commit(&empty_a[sa]);
         }
+    }
+    // worker, packed form: x[2c], x[2c+1] = the two halves of 16-byte chunk c
+    __device__ __forceinline__ void put_chunk2(uint32_t it, int r, int half, const f2 (&x)[8]) const {
+        const uint32_t s = it % SA, rr = it / SA;
+        if (rr > 0) mbar_wait(&empty_a[s], (rr - 1) & 1);
+        unsigned char* a_hi = a_base + s * A_STAGE;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) store_split2(a_hi, a_hi + A_BYTES, r, 4 * half + c, x[2 * c], x[2 * c + 1]);
+        fence_proxy_async();
+        mbar_arrive(&full_a[s]);
     }
     // worker: publish this thread's 16 columns (4 x float4) of atom `it`; half h writes the 16-byte chunks 4h..4h+3 of its row
     __device__ __forceinline__ void put_chunk(uint32_t it, int r, int half, const float4 (&x)[4]) const {

@@ -15,38 +15,47 @@
 namespace gb {
 using namespace tc;
 
+// Optional clock64 timeline of CTA 0 (make EXTRA=-DGB_TIMELINE; tools/edge_timeline.py): role 0 = worker part 0, 1 = worker part 3
+// (lane 0 of the first quadrant), 2 = MMA lane.  Each record = (code, clock).
+#ifdef GB_TIMELINE
+__device__ unsigned long long gb_tl_pred[5][2048];
+__device__ unsigned int gb_tl_pred_n[5];
+#define TLP(role, code) do { if (blockIdx.x == 0) { unsigned int i_ = gb_tl_pred_n[role]; if (i_ < 1023) { gb_tl_pred[role][2 * i_] = (code); gb_tl_pred[role][2 * i_ + 1] = clock64(); gb_tl_pred_n[role] = i_ + 1; } } } while (0)
+#define TLW(code) do { if (tlr >= 0) TLP(tlr, code); } while (0)
+#else
+#define TLP(role, code) do {} while (0)
+#define TLW(code) do {} while (0)
+#endif
+
 template <int NP>
 struct TcPredCfg {
-    static constexpr int S = 2;
-    static constexpr int A_BYTES = 128 * ATOM_ROW_BYTES;
-    static constexpr int W_BYTES = NP * ATOM_ROW_BYTES;
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+    using R = Rings<NP>;
+    static constexpr int A_BYTES = R::A_BYTES;
+    static constexpr int A_STAGE = R::A_STAGE;
     static constexpr int NPARTS = GB_PRED_NPARTS;                          // worker parts of 4 warps; part p owns 16-column chunks ch == p (mod 4)
     static constexpr int NWORK = 128 * NPARTS;
     static constexpr int THREADS = 64 + NWORK;
     static constexpr int MAXCH = (NP + 15) / 16;
     static constexpr int MYCH = (MAXCH + NPARTS - 1) / NPARTS;
     static constexpr int EF_STRIDE = 17;
-    static constexpr int SCRATCH = 6 * NP * 4 + 4 * NPARTS * 128 * 4 + NPARTS * 128 * EF_STRIDE * 4 + 129 * 4 + 128 * 3 * 4 + 64 + 3 * 132 * 4;
-    static constexpr int SMEM = S * STAGE_BYTES + 1024 + 256 + SCRATCH;
+    static constexpr int BAR_BYTES = 512;                                  // up to 64 mbarriers + the TMEM address slot
     static constexpr int D2_COL = 256;
     // backward only: one extra producer warp streams the saved activations (16-column chunks of the float4 "Q layout",
-    // 4 planes x 128 rows x 16 B = 8 KB, contiguous in HBM) through a 4-slot ring that lives in the ef_s scratch area
-    static constexpr int BWD_THREADS = THREADS + 32;
-    static constexpr int SV_SLOTS = 4;
+    // 4 planes x 128 rows x 16 B = 8 KB, contiguous in HBM) through an 8-slot ring (two chunks per worker part in flight: with
+    // one slot per part the HBM latency of every chunk was exposed -- ~1.5 us on each of the 13 chunk steps of a part and tile)
+    static constexpr int SV_SLOTS = 8;
     static constexpr int SV_SLOT_BYTES = 4 * 128 * 16;
-    static_assert(SV_SLOTS * SV_SLOT_BYTES <= NPARTS * 128 * EF_STRIDE * 4, "saved-activation ring must fit the ef scratch");
 };
 
 struct SvRing { unsigned char* buf; uint64_t* full; uint64_t* empty; };
 
 // consumer side of the saved-activation ring: wait for chunk q, return this row's first float4 (plane c at +128*c)
 __device__ __forceinline__ const float4* sv_acquire(const SvRing& sv, uint32_t q, int r) {
-    const uint32_t s = q & 3, rr = q >> 2;
+    const uint32_t s = q & 7, rr = q >> 3;
     mbar_wait(&sv.full[s], rr & 1);
     return reinterpret_cast<const float4*>(sv.buf + s * 8192) + r;
 }
-__device__ __forceinline__ void sv_release(const SvRing& sv, uint32_t q) { mbar_arrive(&sv.empty[q & 3]); }
+__device__ __forceinline__ void sv_release(const SvRing& sv, uint32_t q) { mbar_arrive(&sv.empty[q & 7]); }
 
 template <int NPARTS>
 __device__ __forceinline__ float psum_parts(const float* red, int r) {
@@ -56,86 +65,54 @@ __device__ __forceinline__ float psum_parts(const float* red, int r) {
     return s;
 }
 
-__device__ __forceinline__ void nbar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-struct TcPipe {      // shared bookkeeping of the atom ring (same counter sequence in every role)
-    unsigned char* base; uint64_t *full_a, *full_w, *empty; int stage_bytes, S;
-};
-
-// one GEMM worth of MMAs: na atoms from the ring into accumulator d_tmem
-template <int NP>
-__device__ __forceinline__ void mma_gemm(const TcPipe& p, uint32_t& it, int na, int H, uint32_t d_tmem) {
-    using CF = TcPredCfg<NP>;
-    constexpr uint32_t idesc = instr_desc_tf32(NP);
-    for (int j = 0; j < na; ++j, ++it) {
-        const uint32_t s = it % CF::S, r = it / CF::S;
-        const int kvalid = H - j * ATOM_K;
-        const int ksteps = kvalid >= ATOM_K ? 4 : (kvalid + 7) / 8;
-        mbar_wait(&p.full_a[s], r & 1);
-        mbar_wait(&p.full_w[s], r & 1);
-        fence_after_sync();
-        const uint32_t a_hi = smem_u32(p.base + s * CF::STAGE_BYTES), a_lo = a_hi + CF::A_BYTES;
-        const uint32_t w_hi = a_hi + 2 * CF::A_BYTES, w_lo = w_hi + CF::W_BYTES;
-        for (int kk = 0; kk < ksteps; ++kk) {
-            const uint32_t ko = kk * 32;
-            mma_tf32(d_tmem, smem_desc(a_lo + ko), smem_desc(w_hi + ko), idesc, (j | kk) != 0);
-            mma_tf32(d_tmem, smem_desc(a_hi + ko), smem_desc(w_lo + ko), idesc, 1);
-            mma_tf32(d_tmem, smem_desc(a_hi + ko), smem_desc(w_hi + ko), idesc, 1);
-        }
-        mma_commit(&p.empty[s]);
-    }
-}
-
-template <int NP>
-__device__ __forceinline__ void tma_gemm(const TcPipe& p, uint32_t& it, int na, const float* wimg) {
-    using CF = TcPredCfg<NP>;
-    const size_t atom_floats = (size_t)2 * NP * ATOM_K;
-    for (int j = 0; j < na; ++j, ++it) {
-        const uint32_t s = it % CF::S, r = it / CF::S;
-        if (r > 0) mbar_wait(&p.empty[s], (r - 1) & 1);
-        mbar_arrive_expect_tx(&p.full_w[s], 2 * CF::W_BYTES);
-        bulk_g2s(p.base + s * CF::STAGE_BYTES + 2 * CF::A_BYTES, wimg + (size_t)j * atom_floats, 2 * CF::W_BYTES, &p.full_w[s]);
-    }
-}
-
-// worker side: publish this thread's 16 columns (4 x float4) of atom `it` (chunk parity h writes 16-byte chunks 4h..4h+3)
-template <int NP>
-__device__ __forceinline__ void put_chunk(const TcPipe& p, uint32_t it, int r, int half, const float4 (&x)[4]) {
-    using CF = TcPredCfg<NP>;
-    const uint32_t s = it % CF::S, rr = it / CF::S;
-    if (rr > 0) mbar_wait(&p.empty[s], (rr - 1) & 1);
-    unsigned char* a_hi = p.base + s * CF::STAGE_BYTES;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) store_split(a_hi, a_hi + CF::A_BYTES, r, 4 * half + c, x[c]);
-    fence_proxy_async();
-    mbar_arrive(&p.full_a[s]);
-}
-
 // ==================================================================================================================
 // forward
 // ==================================================================================================================
+// Warps: 0 = weight TMA, 1 = MMA issue, 2..17 = workers, 18 / 19 = auxiliary (staged P rows of the even / odd K-atoms of GEMM 1;
+// warp 19 also prepares the next tile's edge geometry).  Worker schedule, software-pipelined over the CTA's tiles:
+//     build1(0);  for k: epilogue1(k) [= operand of GEMM 2(k)], build1(k+1), epilogue2(k)
+// so that GEMM 1 of tile k+1 runs on the tensor pipe while the workers are in epilogue 2 of tile k, and GEMM 2 of tile k while they
+// build tile k+1 (accumulator 1 is free again once epilogue 1 has read it, accumulator 2 once epilogue 2 has).
+template <int NP>
+struct TcFwdCfg : TcPredCfg<NP> {
+    using B = TcPredCfg<NP>;
+    static constexpr int AUX_WARP = 2 + 4 * B::NPARTS;
+    static constexpr int THREADS = B::THREADS + 64;
+    static constexpr int GEO_NF = 6;                                       // P-stage rows (row | col << 16), radial, edge_attr, unit vector (3)
+    static constexpr int GEO_WORDS = geo_words(GEO_NF);
+    static constexpr int NGEO = 3;
+    static constexpr int SCRATCH = 6 * NP * 4 + 2 * B::NPARTS * 128 * 4 + B::NPARTS * 128 * B::EF_STRIDE * 4 + NGEO * GEO_WORDS * 4 + 128 * 3 * 4 + PS_BYTES + 64;
+    static constexpr int SMEM = B::R::BYTES + 1024 + B::BAR_BYTES + SCRATCH;
+    static_assert(NP > 208 || SMEM <= 232448, "shared memory budget (forward)");
+};
+
 template <int NP, bool SAVE>
-__global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_kernel(PredEdgeArgs a, const float* __restrict__ w2img,
+__global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_kernel(PredEdgeArgs a, const float* __restrict__ w2img,
                                                                    const float* __restrict__ wcimg, int H) {
-    using CF = TcPredCfg<NP>;
+    using CF = TcFwdCfg<NP>;
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment by pointer arithmetic on the __shared__ array: the compiler keeps the address space (LDS / STS
     // instead of generic LD / ST for every staging and operand access)
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::S * CF::STAGE_BYTES);
-    TcPipe p{base, bars, bars + CF::S, bars + 2 * CF::S, CF::STAGE_BYTES, CF::S};
-    uint64_t* d1_full = bars + 3 * CF::S; uint64_t* d2_full = d1_full + 1; uint64_t* d_empty = d2_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 1);
-    float* vec_s = reinterpret_cast<float*>(base + CF::S * CF::STAGE_BYTES + 256);    // [6][NP]: w_r, w_a, b2, att_w, bc, wc_last
-    float* red_s = vec_s + 6 * NP;                                                       // [2][2][128]
-    float* ef_s = red_s + 4 * CF::NPARTS * 128;                                                       // [2][128][17]
-    int* seg_s = reinterpret_cast<int*>(ef_s + CF::NPARTS * 128 * CF::EF_STRIDE);
-    float* tr_s = reinterpret_cast<float*>(seg_s + 129);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::R::BYTES);
+    Rings<NP> rg; rg.carve(base, bars);
+    uint64_t* d1_full = bars + CF::R::NBARS; uint64_t* d2_full = d1_full + 1; uint64_t* d1_empty = d2_full + 1; uint64_t* d2_empty = d1_empty + 1;
+    uint64_t* geo_full = d2_empty + 1; uint64_t* geo_empty = geo_full + CF::NGEO;
+    uint64_t* ps_full = geo_empty + CF::NGEO; uint64_t* ps_empty = ps_full + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ps_empty + 4);
+    float* vec_s = reinterpret_cast<float*>(base + CF::R::BYTES + CF::BAR_BYTES);     // [6][NP]: w_r, w_a, b2, att_w, bc, wc_last
+    float* red_s = vec_s + 6 * NP;                                                       // [2][NPARTS][128]: gate logits | coordinate head
+    float* ef_s = red_s + 2 * CF::NPARTS * 128;                                          // [NPARTS][128][17]
+    int* geo_s = reinterpret_cast<int*>(ef_s + CF::NPARTS * 128 * CF::EF_STRIDE);        // [NGEO][GEO_WORDS]
+    float* tr_s = reinterpret_cast<float*>(geo_s + CF::NGEO * CF::GEO_WORDS);            // [128][3]
+    const PStage ps{tr_s + 128 * 3, ps_full, ps_empty, a.g.ps_rows <= PS_ROWS / 2 ? 2 : 1};
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < CF::S; ++s) { mbar_init(&p.full_a[s], 256); mbar_init(&p.full_w[s], 1); mbar_init(&p.empty[s], 1); }
-        mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d_empty, CF::NWORK);
+        rg.init(256);
+        mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d1_empty, CF::NWORK); mbar_init(d2_empty, CF::NWORK);
+        for (int b = 0; b < CF::NGEO; ++b) { mbar_init(&geo_full[b], 1); mbar_init(&geo_empty[b], CF::NWORK); }
+        ps.init();
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -153,39 +130,43 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
 
     if (warp == 0) {
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) { tma_gemm<NP>(p, it, na, w2img); tma_gemm<NP>(p, it, na, wcimg); }
+            uint32_t wq = 0;
+            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) { rg.tma_gemm(wq, na, w2img); rg.tma_gemm(wq, na, wcimg); }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            uint32_t it = 0, tcnt = 0;
+            uint32_t it = 0, wq = 0, tcnt = 0;
             for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
-                if (tcnt > 0) mbar_wait(d_empty, (tcnt - 1) & 1);
+                if (tcnt > 0) mbar_wait(d1_empty, (tcnt - 1) & 1);
                 fence_after_sync();
-                mma_gemm<NP>(p, it, na, H, tmem_base);
+                TLP(2, 1);
+                rg.mma_gemm(it, wq, na, H, tmem_base);
                 mma_commit(d1_full);
-                mma_gemm<NP>(p, it, na, H, tmem_base + CF::D2_COL);
+                TLP(2, 2);
+                if (tcnt > 0) mbar_wait(d2_empty, (tcnt - 1) & 1);
+                fence_after_sync();
+                TLP(2, 3);
+                rg.mma_gemm(it, wq, na, H, tmem_base + CF::D2_COL);
                 mma_commit(d2_full);
+                TLP(2, 4);
             }
         }
-    } else {
-        const int group = warp & 3, part = (warp - 2) >> 2, half = part & 1;
-        const int r = group * 32 + lane;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(group * 32) << 16);
-        const int nchunks = (H + 15) / 16;
-        float* my_ef = ef_s + part * 128 * CF::EF_STRIDE;
-        uint32_t tcnt = 0;
-        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
-            const int4 ti = __ldg(g.tile_info + tile);
-            const int node_lo = ti.x, nn = ti.y, e_lo = ti.z, ne = ti.w;
-            const bool valid = r < ne;
-            int rown = 0, coln = 0; float rad = 0.f, a0 = 0.f;
-            {   // the unit difference vector is needed again only for the coordinate update at the end of the tile (part 0):
-                // it waits in tr_s instead of in three registers of every worker
-                float ux = 0.f, uy = 0.f, uz = 0.f;
-                if (valid) {
-                    const int e = e_lo + r;
-                    rown = g.erow[e]; coln = g.ecol[e];
+    } else if (warp >= CF::AUX_WARP) {
+        const int ldw = warp - CF::AUX_WARP;
+        auto geo_emit = [&](const TileMeta& m, uint32_t tc) {
+            const uint32_t gb_ = tc % CF::NGEO, use = tc / CF::NGEO;
+            if (use > 0) mbar_wait(&geo_empty[gb_], (use - 1) & 1);
+            int* gi = geo_s + gb_ * CF::GEO_WORDS;
+            float* gf = reinterpret_cast<float*>(gi);
+            if (lane == 0) { gi[0] = m.node_lo; gi[1] = m.nn; gi[2] = m.e_lo; gi[3] = m.ne; }
+            for (int i = lane; i <= m.nn; i += 32) gi[4 + i] = __ldg(g.rowptr + m.node_lo + i) - m.e_lo;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = lane + 32 * q;
+                int prc = 0; float rad = 0.f, a0 = 0.f, ux = 0.f, uy = 0.f, uz = 0.f;
+                if (r < m.ne) {
+                    const int e = m.e_lo + r, rown = m.row[q], coln = m.col[q];
+                    prc = (rown - m.node_lo) | ((m.nn + coln - m.cn_lo) << 16);
                     const float dx = a.x[3 * rown] - a.x[3 * coln], dy = a.x[3 * rown + 1] - a.x[3 * coln + 1], dz = a.x[3 * rown + 2] - a.x[3 * coln + 2];
                     rad = dx * dx + dy * dy + dz * dz;
                     const float inv = 1.f / (sqrtf(rad + 1e-8f) + 1.f);
@@ -194,22 +175,62 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
                     a0 = ex * ex + ey * ey + ez * ez;
                     if (a.a_edge) a0 = a.a_edge[e];
                 }
-                if (part == 0) { tr_s[3 * r] = ux; tr_s[3 * r + 1] = uy; tr_s[3 * r + 2] = uz; }
+                gi[GEO_HDR + r] = prc; gf[GEO_HDR + 128 + r] = rad; gf[GEO_HDR + 256 + r] = a0;
+                gf[GEO_HDR + 384 + r] = ux; gf[GEO_HDR + 512 + r] = uy; gf[GEO_HDR + 640 + r] = uz;
             }
-            if (part == 0) for (int i = r; i <= nn; i += 128) seg_s[i] = g.rowptr[node_lo + i] - e_lo;
-            const uint32_t it0 = tcnt * 2 * na;
-            // ---- GEMM 1 operand: s1 = SiLU(pre1); SiLU'(pre1) is saved ----
-            const float* pa_row = a.P + (size_t)rown * (2 * H);
-            const float* pb_row = a.P + (size_t)coln * (2 * H) + H;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&geo_full[gb_]);
+        };
+        TileMeta cur, nxt;
+        int tile = blockIdx.x;
+        if (tile < g.n_tiles) {
+            tile_meta_load(cur, g, tile, lane, ldw == 1);
+            if (ldw == 1) geo_emit(cur, 0);
+        }
+        for (uint32_t tcnt = 0; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
+            const int ntile = tile + gridDim.x;
+            if (ntile < g.n_tiles) tile_meta_load(nxt, g, ntile, lane, ldw == 1);
+            for (int j = 0; j < na; ++j) {
+                const uint32_t pit = tcnt * na + j;
+                if ((int)(pit & 1) == ldw) pstage_load_atom(ps, pit, j, H, a.P, cur.node_lo, cur.nn, cur.cn_lo, cur.ncn, lane);
+            }
+            if (ntile < g.n_tiles) {
+                if (ldw == 1) geo_emit(nxt, tcnt + 1);
+                cur = nxt;
+            }
+        }
+    } else {
+        const int group = warp & 3, part = (warp - 2) >> 2, half = part & 1;
+        const int r = group * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(group * 32) << 16);
+        const int nchunks = (H + 15) / 16;
+        float* my_ef = ef_s + part * 128 * CF::EF_STRIDE;
+        float* red1 = red_s; float* red2 = red_s + CF::NPARTS * 128;
+        const int tlr = (lane == 0 && group == 0) ? (part == 0 ? 0 : (part == 3 ? 1 : -1)) : -1;
+        (void)tlr;
+        // ---- GEMM 1 operand of the CTA's k-th tile: s1 = SiLU(pre1) from the staged P rows; SiLU'(pre1) is saved ----
+        auto build1 = [&](uint32_t k, int tile) {
+            const uint32_t gb_ = k % CF::NGEO;
+            TLW(10);
+            mbar_wait(&geo_full[gb_], (k / CF::NGEO) & 1);
+            TLW(11);
+            const int* gi = geo_s + gb_ * CF::GEO_WORDS;
+            const float* gf = reinterpret_cast<const float*>(gi);
+            const bool valid = r < gi[3];
+            const int prc = gi[GEO_HDR + r];
+            const int pa_off = (prc & 0xffff) * PS_PITCH + 16 * half, pb_off = (prc >> 16) * PS_PITCH + 16 * half;
+            const float rad = gf[GEO_HDR + 128 + r], a0 = gf[GEO_HDR + 256 + r];
             for (int j = part >> 1; j < na; j += CF::NPARTS / 2) {
+                const uint32_t pit = k * na + j;
+                const float* pst = ps.acquire(pit);
                 float4 x[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int k0 = j * ATOM_K + 16 * half + 4 * c;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f), dv = v;
                     if (valid && k0 < H) {
-                        const float4 pa = __ldg(reinterpret_cast<const float4*>(pa_row + k0));
-                        const float4 pb = __ldg(reinterpret_cast<const float4*>(pb_row + k0));
+                        const float4 pa = *reinterpret_cast<const float4*>(pst + pa_off + 4 * c);
+                        const float4 pb = *reinterpret_cast<const float4*>(pst + pb_off + 4 * c);
                         const float4 wr = *reinterpret_cast<const float4*>(vec_s + k0);
                         const float4 wa = *reinterpret_cast<const float4*>(vec_s + NP + k0);
                         silu_both(pa.x + pb.x + wr.x * rad + wa.x * a0, v.x, dv.x);
@@ -220,10 +241,27 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
                     x[c] = v;
                     if (SAVE && k0 < H) *reinterpret_cast<float4*>(a.sv_d1 + (((size_t)tile * (H / 4) + (k0 >> 2)) * 128 + r) * 4) = dv;
                 }
-                put_chunk<NP>(p, it0 + j, r, half, x);
+                ps.release(pit);
+                TLW(20 + j);
+                rg.put_chunk(k * 2 * na + j, r, half, x);
+                TLW(30 + j);
             }
+        };
+        uint32_t k = 0;
+        int tile = blockIdx.x;
+        if (tile < g.n_tiles) build1(0, tile);
+        for (; tile < g.n_tiles; tile += gridDim.x, ++k) {
+            const uint32_t gb_ = k % CF::NGEO;
+            const int* gi = geo_s + gb_ * CF::GEO_WORDS;
+            const float* gf = reinterpret_cast<const float*>(gi);
+            const int* seg_s = gi + 4;
+            const int node_lo = gi[0], nn = gi[1], e_lo = gi[2], ne = gi[3];
+            const bool valid = r < ne;
+            const uint32_t it0 = k * 2 * na;
             // ---- epilogue 1: q = SiLU(pre2), attention gate ----
-            mbar_wait(d1_full, tcnt & 1);
+            TLW(40);
+            mbar_wait(d1_full, k & 1);
+            TLW(41);
             fence_after_sync();
             float q[CF::MYCH][16];
             float psum = 0.f;
@@ -248,9 +286,15 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
                     }
                 }
             }
-            red_s[part * 128 + r] = psum;
-            nbar(1, CF::NWORK);
-            const float gate = a.attention ? sigmoid_f(psum_parts<CF::NPARTS>(red_s, r) + a.att_b) : 1.f;
+            fence_before_sync();
+            mbar_arrive(d1_empty);                              // accumulator 1 is in registers: GEMM 1 of the next tile may start
+            // red1 / red2 alternate (gate logits of tile k, coordinate head of tile k, gate logits of tile k+1, ...): a warp is never
+            // more than one quadrant barrier ahead of the warps it shares the rows with, so one copy of each is enough
+            red1[part * 128 + r] = psum;
+            TLW(42);
+            bar_named(BAR_QUAD + group, 128);
+            TLW(43);
+            const float gate = a.attention ? sigmoid_f(psum_parts<CF::NPARTS>(red1, r) + a.att_b) : 1.f;
             // ---- gated edge feature: segment sums -> agg, and operand atoms of GEMM 2 ----
 #pragma unroll
             for (int ci = 0; ci < CF::MYCH; ++ci) {
@@ -264,23 +308,28 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
                         my_ef[r * CF::EF_STRIDE + 4 * c] = x[c].x; my_ef[r * CF::EF_STRIDE + 4 * c + 1] = x[c].y;
                         my_ef[r * CF::EF_STRIDE + 4 * c + 2] = x[c].z; my_ef[r * CF::EF_STRIDE + 4 * c + 3] = x[c].w;
                     }
-                    put_chunk<NP>(p, it0 + na + (ch >> 1), r, half, x);
-                    nbar(2 + part, 128);
+                    rg.put_chunk(it0 + na + (ch >> 1), r, half, x);
+                    bar_named(BAR_PART + part, 128);
                     for (int nl = r >> 4; nl < nn; nl += 8) {
                         const int col = r & 15, c = ch * 16 + col;
                         float sum = 0.f;
                         for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += my_ef[mm * CF::EF_STRIDE + col];
                         if (c < H) a.agg[(size_t)(node_lo + nl) * H + c] = sum;
                     }
-                    nbar(2 + part, 128);
+                    bar_named(BAR_PART + part, 128);
                 } else if (ch < 2 * na) {
                     // chunk beyond the hidden width but inside the last atom: publish zeros so the atom completes
                     float4 x[4] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-                    put_chunk<NP>(p, it0 + na + (ch >> 1), r, half, x);
+                    rg.put_chunk(it0 + na + (ch >> 1), r, half, x);
                 }
             }
+            // ---- GEMM 1 operand of the next tile (its MMAs overlap epilogue 2 below) ----
+            TLW(50);
+            if (tile + (int)gridDim.x < g.n_tiles) build1(k + 1, tile + gridDim.x);
             // ---- epilogue 2: coordinate head ----
-            mbar_wait(d2_full, tcnt & 1);
+            TLW(60);
+            mbar_wait(d2_full, k & 1);
+            TLW(61);
             fence_after_sync();
             float phi_part = 0.f;
 #pragma unroll 1
@@ -302,18 +351,21 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
                 }
             }
             fence_before_sync();
-            mbar_arrive(d_empty);
-            red_s[CF::NPARTS * 128 + part * 128 + r] = phi_part;
-            nbar(1, CF::NWORK);
+            mbar_arrive(d2_empty);
+            red2[part * 128 + r] = phi_part;
+            TLW(62);
+            bar_named(BAR_QUAD + group, 128);
+            TLW(63);
             if (part == 0) {
-                const float phi = psum_parts<CF::NPARTS>(red_s + CF::NPARTS * 128, r);
+                const float phi = psum_parts<CF::NPARTS>(red2, r);
                 const float tau = a.use_tanh ? tanhf(phi) : phi;
                 if (SAVE && valid) a.sv_tau[e_lo + r] = tau;
-                const float ux = tr_s[3 * r], uy = tr_s[3 * r + 1], uz = tr_s[3 * r + 2];
-                if (a.use_tanh) { tr_s[3 * r] = ux * tau * a.coords_range; tr_s[3 * r + 1] = uy * tau * a.coords_range; tr_s[3 * r + 2] = uz * tau * a.coords_range; }
-                else { tr_s[3 * r] = ux * tau; tr_s[3 * r + 1] = uy * tau; tr_s[3 * r + 2] = uz * tau; }
+                const float sc = a.use_tanh ? tau * a.coords_range : tau;
+                tr_s[3 * r] = gf[GEO_HDR + 384 + r] * sc; tr_s[3 * r + 1] = gf[GEO_HDR + 512 + r] * sc; tr_s[3 * r + 2] = gf[GEO_HDR + 640 + r] * sc;
             }
-            nbar(1, CF::NWORK);
+            // tr_s is single-buffered: its next writer has to pass build1 of tile k+2, whose ring slots are only released by
+            // MMAs that consumed GEMM-2 atoms of tile k+1 from every part, i.e. after every warp has left this tile
+            bar_named(BAR_WORKERS, CF::NWORK);
             for (int idx = part * 128 + r; idx < nn * 3; idx += CF::NWORK) {
                 const int nl = idx / 3, d = idx - 3 * nl;
                 float sum = 0.f;
@@ -321,7 +373,8 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
                 const int node = node_lo + nl;
                 a.x_out[3 * node + d] = (a.x[3 * node + d] + sum) * g.node_mask[node];
             }
-            nbar(1, CF::NWORK);
+            mbar_arrive(&geo_empty[gb_]);
+            TLW(70);
         }
     }
     fence_before_sync();
@@ -332,31 +385,45 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ke
 // ==================================================================================================================
 // backward (input gradient only)
 // ==================================================================================================================
+// Warps: 0 = weight TMA, 1 = MMA issue, 2..17 = workers, 18 = saved-activation TMA, 19 = edge geometry of the next tile.
 template <int NP>
-__global__ void __launch_bounds__(TcPredCfg<NP>::BWD_THREADS, 1) tc_pred_edge_bwd_kernel(PredEdgeArgs a, const float* __restrict__ wcimg_nt,
+struct TcBwdCfg : TcPredCfg<NP> {
+    using B = TcPredCfg<NP>;
+    static constexpr int SV_WARP = 2 + 4 * B::NPARTS, GEO_WARP = SV_WARP + 1;
+    static constexpr int THREADS = B::THREADS + 64;
+    static constexpr int GEO_NF = 8;                                       // local row node, g_phi, d (3), g_u (3)
+    static constexpr int GEO_WORDS = geo_words(GEO_NF);
+    static constexpr int SCRATCH = 6 * NP * 4 + 2 * B::NPARTS * 128 * 4 + B::SV_SLOTS * B::SV_SLOT_BYTES + 2 * GEO_WORDS * 4 + 64;
+    static constexpr int SMEM = B::R::BYTES + 1024 + B::BAR_BYTES + SCRATCH;
+    static_assert(NP > 208 || SMEM <= 232448, "shared memory budget (backward)");
+};
+
+template <int NP>
+__global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_kernel(PredEdgeArgs a, const float* __restrict__ wcimg_nt,
                                                                    const float* __restrict__ w2img_nt, int H) {
-    using CF = TcPredCfg<NP>;
+    using CF = TcBwdCfg<NP>;
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment by pointer arithmetic on the __shared__ array: the compiler keeps the address space (LDS / STS
     // instead of generic LD / ST for every staging and operand access)
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::S * CF::STAGE_BYTES);
-    TcPipe p{base, bars, bars + CF::S, bars + 2 * CF::S, CF::STAGE_BYTES, CF::S};
-    uint64_t* d1_full = bars + 3 * CF::S; uint64_t* d2_full = d1_full + 1; uint64_t* d_empty = d2_full + 1;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::R::BYTES);
+    Rings<NP> rg; rg.carve(base, bars);
+    uint64_t* d1_full = bars + CF::R::NBARS; uint64_t* d2_full = d1_full + 1; uint64_t* d_empty = d2_full + 1;
     uint64_t* sv_full = d_empty + 1; uint64_t* sv_empty = sv_full + CF::SV_SLOTS;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sv_empty + CF::SV_SLOTS);
-    float* vec_s = reinterpret_cast<float*>(base + CF::S * CF::STAGE_BYTES + 256);    // [6][NP]: w_r, w_a, b2(unused), att_w, bc(unused), wc_last
-    float* red_s = vec_s + 6 * NP;                                                       // [4][128]
-    float* ef_s = red_s + 4 * CF::NPARTS * 128;                                          // saved-activation ring (4 x 8 KB)
-    int* seg_s = reinterpret_cast<int*>(ef_s + CF::NPARTS * 128 * CF::EF_STRIDE);
-    float* geo_s = reinterpret_cast<float*>(seg_s + 132);                                // [6][128] dx, dy, dz, g_u of every tile edge
-    const SvRing sv{reinterpret_cast<unsigned char*>(ef_s), sv_full, sv_empty};
+    uint64_t* geo_full = sv_empty + CF::SV_SLOTS; uint64_t* geo_empty = geo_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(geo_empty + 2);
+    float* vec_s = reinterpret_cast<float*>(base + CF::R::BYTES + CF::BAR_BYTES);     // [6][NP]: w_r, w_a, -, att_w, -, wc_last
+    float* red_s = vec_s + 6 * NP;                                                       // [2][NPARTS][128]
+    unsigned char* sv_buf = reinterpret_cast<unsigned char*>(red_s + 2 * CF::NPARTS * 128);   // saved-activation ring (8 x 8 KB)
+    int* geo_s = reinterpret_cast<int*>(sv_buf + CF::SV_SLOTS * CF::SV_SLOT_BYTES);      // [2][GEO_WORDS]
+    const SvRing sv{sv_buf, sv_full, sv_empty};
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < CF::S; ++s) { mbar_init(&p.full_a[s], 256); mbar_init(&p.full_w[s], 1); mbar_init(&p.empty[s], 1); }
+        rg.init(256);
         mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d_empty, CF::NWORK);
         for (int s = 0; s < CF::SV_SLOTS; ++s) { mbar_init(&sv_full[s], 1); mbar_init(&sv_empty[s], 128); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&geo_full[b], 1); mbar_init(&geo_empty[b], CF::NWORK); }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -365,6 +432,10 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::BWD_THREADS, 1) tc_pred_edge_bw
         vec_s[i] = v ? a.ext[i] : 0.f; vec_s[NP + i] = v ? a.ext[H + i] : 0.f;
         vec_s[3 * NP + i] = v ? a.att_w[i] : 0.f; vec_s[5 * NP + i] = v ? a.wc_last[i] : 0.f;
     }
+    // the last 16-column chunk of a tile is only partly filled by the producer (H / 4 planes): the remaining planes are read as
+    // they are and multiplied by zero-padded weights, so they must hold finite values from the start
+    for (int i = tid; i < CF::SV_SLOTS * CF::SV_SLOT_BYTES / 16; i += blockDim.x) reinterpret_cast<float4*>(sv_buf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_proxy_async();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -374,22 +445,25 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::BWD_THREADS, 1) tc_pred_edge_bw
 
     if (warp == 0) {
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) { tma_gemm<NP>(p, it, na, wcimg_nt); tma_gemm<NP>(p, it, na, w2img_nt); }
+            uint32_t wq = 0;
+            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) { rg.tma_gemm(wq, na, wcimg_nt); rg.tma_gemm(wq, na, w2img_nt); }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            uint32_t it = 0, tcnt = 0;
+            uint32_t it = 0, wq = 0, tcnt = 0;
             for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
                 if (tcnt > 0) mbar_wait(d_empty, (tcnt - 1) & 1);
                 fence_after_sync();
-                mma_gemm<NP>(p, it, na, H, tmem_base);
+                TLP(2, 1);
+                rg.mma_gemm(it, wq, na, H, tmem_base);
                 mma_commit(d1_full);
-                mma_gemm<NP>(p, it, na, H, tmem_base + CF::D2_COL);
+                TLP(2, 2);
+                rg.mma_gemm(it, wq, na, H, tmem_base + CF::D2_COL);
                 mma_commit(d2_full);
+                TLP(2, 4);
             }
         }
-    } else if (warp == 2 + 4 * CF::NPARTS) {
+    } else if (warp == CF::SV_WARP) {
         // saved-activation producer: per tile the chunks of d3 (GEMM-1 operand), pre2 (epilogue 1), pre2 again (GEMM-2
         // operand) and d1 (epilogue 2), in the order the worker parts consume them
         if (lane == 0) {
@@ -400,7 +474,7 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::BWD_THREADS, 1) tc_pred_edge_bw
                 for (int ph = 0; ph < 4; ++ph) {
                     const float* src = (ph == 0 ? a.sv_d3 : (ph == 3 ? a.sv_d1 : a.sv_pre2)) + (size_t)tile * planes * 512;
                     for (int ch = 0; ch < nchunks; ++ch, ++q) {
-                        const uint32_t s = q & 3, rr = q >> 2;
+                        const uint32_t s = q & 7, rr = q >> 3;
                         const uint32_t bytes = (uint32_t)min(4, planes - 4 * ch) * 2048u;
                         if (rr > 0) mbar_wait(&sv_empty[s], (rr - 1) & 1);
                         mbar_arrive_expect_tx(&sv_full[s], bytes);
@@ -409,26 +483,24 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::BWD_THREADS, 1) tc_pred_edge_bw
                 }
             }
         }
-    } else {
-        const int group = warp & 3, part = (warp - 2) >> 2, half = part & 1;
-        const int r = group * 32 + lane;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(group * 32) << 16);
-        const int nchunks = (H + 15) / 16;
-        uint32_t tcnt = 0;
-        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
-            const uint32_t q0 = tcnt * 4 * nchunks;                 // first saved-activation chunk of this tile
-            const int node_lo = g.tile_ptr[tile], node_hi = g.tile_ptr[tile + 1];     // (tile_info costs registers here: slower)
-            const int nn = node_hi - node_lo;
-            const int e_lo = g.rowptr[node_lo], ne = g.rowptr[node_hi] - e_lo;
-            const bool valid = r < ne;
-            int rown = 0, coln = 0;
-            float gphi = 0.f;
-            {   // the edge geometry is needed again only at the very end (dL/d(x_i - x_j), part 0): it waits in shared memory
-                // instead of occupying seven registers of every worker across both GEMMs
-                float dx = 0.f, dy = 0.f, dz = 0.f, gux = 0.f, guy = 0.f, guz = 0.f;
-                if (valid) {
-                    const int e = e_lo + r;
-                    rown = g.erow[e]; coln = g.ecol[e];
+    } else if (warp == CF::GEO_WARP) {
+        // ---- geometry warp: the NEXT tile's header, row-segment table and per-edge backward geometry (its dependent load chain
+        //      tile_info -> erow/ecol -> x / g_xout / tau used to stall all worker warps at every tile start) ----
+        auto geo_emit = [&](const TileMeta& m, uint32_t tc) {
+            const uint32_t gb_ = tc & 1, use = tc >> 1;
+            if (use > 0) mbar_wait(&geo_empty[gb_], (use - 1) & 1);
+            int* gi = geo_s + gb_ * CF::GEO_WORDS;
+            float* gf = reinterpret_cast<float*>(gi);
+            if (lane == 0) { gi[0] = m.node_lo; gi[1] = m.nn; gi[2] = m.e_lo; gi[3] = m.ne; }
+            for (int i = lane; i <= m.nn; i += 32) gi[4 + i] = __ldg(g.rowptr + m.node_lo + i) - m.e_lo;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = lane + 32 * q;
+                int rloc = 0;
+                float gphi = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, gux = 0.f, guy = 0.f, guz = 0.f;
+                if (r < m.ne) {
+                    const int e = m.e_lo + r, rown = m.row[q], coln = m.col[q];
+                    rloc = rown - m.node_lo;
                     dx = a.x[3 * rown] - a.x[3 * coln]; dy = a.x[3 * rown + 1] - a.x[3 * coln + 1]; dz = a.x[3 * rown + 2] - a.x[3 * coln + 2];
                     const float nrm = sqrtf(dx * dx + dy * dy + dz * dz + 1e-8f);
                     const float inv = 1.f / (nrm + 1.f);
@@ -439,168 +511,227 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::BWD_THREADS, 1) tc_pred_edge_bw
                     if (a.use_tanh) { gphi = gdotu * a.coords_range * (1.f - tau * tau); const float sc = tau * a.coords_range; gux = gx * sc; guy = gy * sc; guz = gz * sc; }
                     else { gphi = gdotu; gux = gx * tau; guy = gy * tau; guz = gz * tau; }
                 }
-                if (part == 0) {
-                    geo_s[r] = dx; geo_s[128 + r] = dy; geo_s[256 + r] = dz;
-                    geo_s[384 + r] = gux; geo_s[512 + r] = guy; geo_s[640 + r] = guz;
-                }
+                gi[GEO_HDR + r] = rloc; gf[GEO_HDR + 128 + r] = gphi;
+                gf[GEO_HDR + 256 + r] = dx; gf[GEO_HDR + 384 + r] = dy; gf[GEO_HDR + 512 + r] = dz;
+                gf[GEO_HDR + 640 + r] = gux; gf[GEO_HDR + 768 + r] = guy; gf[GEO_HDR + 896 + r] = guz;
             }
-            if (part == 0) for (int i = r; i <= nn; i += 128) seg_s[i] = g.rowptr[node_lo + i] - e_lo;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&geo_full[gb_]);
+        };
+        TileMeta cur;
+        uint32_t tcnt = 0;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
+            tile_meta_load(cur, g, tile, lane, true);
+            geo_emit(cur, tcnt);                                 // blocks on geo_empty: at most two tiles ahead of the workers
+        }
+    } else {
+        const int group = warp & 3, part = (warp - 2) >> 2, half = part & 1;
+        const int r = group * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(group * 32) << 16);
+        const int nchunks = (H + 15) / 16;
+        const int tlr = (lane == 0 && group == 0) ? (part == 0 ? 0 : (part == 3 ? 1 : -1)) : -1;
+        (void)tlr;
+        uint32_t tcnt = 0;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
+            const uint32_t q0 = tcnt * 4 * nchunks;                 // first saved-activation chunk of this tile
+            const uint32_t gb_ = tcnt & 1;
+            TLW(10);
+            mbar_wait(&geo_full[gb_], (tcnt >> 1) & 1);
+            TLW(11);
+            const int* gi = geo_s + gb_ * CF::GEO_WORDS;
+            const float* gf = reinterpret_cast<const float*>(gi);
+            const int node_lo = gi[0], nn = gi[1], e_lo = gi[2], ne = gi[3];
+            const bool valid = r < ne;
+            const float gphi = gf[GEO_HDR + 128 + r];
             const uint32_t it0 = tcnt * 2 * na;
             // ---- GEMM 1 operand: g_pre3 = g_phi * w_c * SiLU'(pre3) ----
+            // (no per-element bounds checks: w_c is zero-padded beyond H, rows beyond the tile's edges have g_phi = 0)
+            const f2 gphi2 = f2s(gphi);
             for (int j = part >> 1; j < na; j += CF::NPARTS / 2) {
-                float4 x[4];
+                f2 x[8];
                 const int ch = 2 * j + half;
-                const bool have = ch < nchunks;
-                const float4* d3p = have ? sv_acquire(sv, q0 + ch, r) : nullptr;
+                if (ch < nchunks) {
+                    const float4* d3p = sv_acquire(sv, q0 + ch, r);
+                    TLW(100 + j);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int k0 = j * ATOM_K + 16 * half + 4 * c;
-                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (k0 < H) {
+                    for (int c = 0; c < 4; ++c) {
                         const float4 d3 = d3p[c * 128];
-                        const float4 wl = *reinterpret_cast<const float4*>(vec_s + 5 * NP + k0);
-                        t = make_float4(gphi * wl.x * d3.x, gphi * wl.y * d3.y, gphi * wl.z * d3.z, gphi * wl.w * d3.w);
+                        const float4 wl = *reinterpret_cast<const float4*>(vec_s + 5 * NP + ch * 16 + 4 * c);
+                        x[2 * c] = mul2(mul2(gphi2, lo2(wl)), lo2(d3));
+                        x[2 * c + 1] = mul2(mul2(gphi2, hi2(wl)), hi2(d3));
                     }
-                    x[c] = t;
+                    sv_release(sv, q0 + ch);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) x[c] = f2s(0.f);
                 }
-                if (have) sv_release(sv, q0 + ch);
-                put_chunk<NP>(p, it0 + j, r, half, x);
+                TLW(110 + j);
+                rg.put_chunk2(it0 + j, r, half, x);
+                TLW(120 + j);
             }
             // ---- epilogue 1: g_ef = coordinate branch + aggregation branch; attention backward ----
+            TLW(40);
             mbar_wait(d1_full, tcnt & 1);
+            TLW(41);
             fence_after_sync();
-            // the tile's rows of g_agg (one per row node, shared by its ~9 edges) are copied once, coalesced, into the A half of
-            // the operand ring (idle between GEMM 1 and the first operand store of GEMM 2) instead of being gathered from L2
+            // the tile's rows of g_agg (one per row node, shared by its ~9 edges) are copied once, coalesced, into the A ring
+            // (idle between GEMM 1 and the first operand store of GEMM 2) instead of being gathered from L2
             // with four dependent 16-byte loads per chunk and thread
-            constexpr int GA_ROWS = CF::A_BYTES * 2 / (NP * 4);            // rows per ring stage (A hi + A lo)
+            constexpr int GA_ROWS = CF::A_STAGE / (NP * 4);                // rows per ring stage (A hi + A lo)
             const bool ga_staged = nn <= 2 * GA_ROWS;
             if (ga_staged) {
                 const int h4 = H >> 2;
                 for (int idx = (warp - 2) * 32 + lane; idx < nn * h4; idx += CF::NWORK) {
                     const int nl = idx / h4, k4 = idx - nl * h4;
-                    float* dst = reinterpret_cast<float*>(base + (nl / GA_ROWS) * CF::STAGE_BYTES) + (nl % GA_ROWS) * NP + 4 * k4;
+                    float* dst = reinterpret_cast<float*>(rg.a_base + (nl / GA_ROWS) * CF::A_STAGE) + (nl % GA_ROWS) * NP + 4 * k4;
                     *reinterpret_cast<float4*>(dst) = __ldg(reinterpret_cast<const float4*>(a.g_agg + (size_t)(node_lo + nl) * a.ld_gagg + 4 * k4));
                 }
-                nbar(1, CF::NWORK);
+                TLW(42);
+                bar_named(BAR_WORKERS, CF::NWORK);
+                TLW(43);
             }
-            float gef[CF::MYCH][16];
-            float plog = 0.f, pdot = 0.f;
-            const int rloc = valid ? rown - node_lo : 0;
-            const float* ga_row = ga_staged ? reinterpret_cast<const float*>(base + (rloc / GA_ROWS) * CF::STAGE_BYTES) + (rloc % GA_ROWS) * NP
-                                            : a.g_agg + (size_t)rown * a.ld_gagg;
-#pragma unroll
-            for (int ci = 0; ci < CF::MYCH; ++ci) {
-                const int ch = part + CF::NPARTS * ci;
-                if (ch < nchunks) {
-                    tmem_ld16(lane_addr + ch * 16, gef[ci]);
+            f2 plog2 = f2s(0.f), pdot2 = f2s(0.f);
+            const int rloc = gi[GEO_HDR + r];
+            const float* ga_row = ga_staged ? reinterpret_cast<const float*>(rg.a_base + (rloc / GA_ROWS) * CF::A_STAGE) + (rloc % GA_ROWS) * NP
+                                            : a.g_agg + (size_t)(node_lo + rloc) * a.ld_gagg;
+            // chunk-streaming: g_ef = accumulator 1 + g_agg[row] goes BACK to tensor memory (same columns) instead of waiting in 64
+            // registers for the row-wide attention reduction; the operand build of GEMM 2 reads it again.  The TMEM read of the
+            // next chunk is in flight while the current one is processed.
+            {
+                float v[16];
+                if (part < nchunks) tmem_ld16_issue_f(lane_addr + part * 16, v);
+#pragma unroll 1
+                for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
+                    tmem_ld_wait();
+                    TLW(200 + ch);
                     const float4* p2p = sv_acquire(sv, q0 + nchunks + ch, r);
+                    TLW(220 + ch);
+                    float w[16];
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         const int c0 = ch * 16 + 4 * c4;
-                        if (c0 < H) {
-                            const float4 ga = *reinterpret_cast<const float4*>(ga_row + c0);
-                            const float4 p2 = p2p[c4 * 128];
-                            const float gadd[4] = {ga.x, ga.y, ga.z, ga.w};
-                            const float pv[4] = {p2.x, p2.y, p2.z, p2.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float qv = silu_f(pv[e]);
-                                const float gv = gef[ci][4 * c4 + e] + gadd[e];
-                                gef[ci][4 * c4 + e] = gv;
-                                plog = fmaf(vec_s[3 * NP + c0 + e], qv, plog);
-                                pdot = fmaf(gv, qv, pdot);
-                            }
-                        }
+                        float4 ga = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ga_staged || c0 < H) ga = *reinterpret_cast<const float4*>(ga_row + c0);     // staged rows are NP wide
+                        const float4 p2 = p2p[c4 * 128];
+                        const float4 wq = *reinterpret_cast<const float4*>(vec_s + 3 * NP + c0);
+                        const f2 qa = silu2(lo2(p2)), qb = silu2(hi2(p2));
+                        const f2 ga_ = add2(make_float2(v[4 * c4], v[4 * c4 + 1]), lo2(ga));
+                        const f2 gb2 = add2(make_float2(v[4 * c4 + 2], v[4 * c4 + 3]), hi2(ga));
+                        w[4 * c4] = ga_.x; w[4 * c4 + 1] = ga_.y; w[4 * c4 + 2] = gb2.x; w[4 * c4 + 3] = gb2.y;
+                        plog2 = fma2(lo2(wq), qa, plog2); plog2 = fma2(hi2(wq), qb, plog2);
+                        pdot2 = fma2(ga_, qa, pdot2); pdot2 = fma2(gb2, qb, pdot2);
                     }
                     sv_release(sv, q0 + nchunks + ch);
+                    if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + (ch + CF::NPARTS) * 16, v);
+                    tmem_st16(lane_addr + ch * 16, w);
                 }
+                tmem_st_wait();
             }
-            red_s[part * 128 + r] = plog;
-            red_s[CF::NPARTS * 128 + part * 128 + r] = pdot;
-            nbar(1, CF::NWORK);
+            red_s[part * 128 + r] = plog2.x + plog2.y;
+            red_s[CF::NPARTS * 128 + part * 128 + r] = pdot2.x + pdot2.y;
+            TLW(44);
+            bar_named(BAR_WORKERS, CF::NWORK);                     // also: nobody reads the staged g_agg rows in the A ring any more
+            TLW(45);
             float gate = 1.f, kap = 0.f;
             if (a.attention) {
                 gate = sigmoid_f(psum_parts<CF::NPARTS>(red_s, r) + a.att_b);
                 kap = (psum_parts<CF::NPARTS>(red_s + CF::NPARTS * 128, r)) * gate * (1.f - gate);
             }
             // ---- GEMM 2 operand: g_pre2 = (g_ef gate + kappa w_att) SiLU'(pre2) ----
+            {
+                const f2 gate2 = f2s(gate), kap2 = f2s(kap);
+                float v[16];
+                if (part < nchunks) tmem_ld16_issue_f(lane_addr + part * 16, v);
+#pragma unroll 1
+                for (int ch = part; ch < 2 * na; ch += CF::NPARTS) {
+                    f2 x[8];
+                    if (ch < nchunks) {
+                        tmem_ld_wait();
+                        const float4* p2p = sv_acquire(sv, q0 + 2 * nchunks + ch, r);
+                        TLW(300 + ch);
 #pragma unroll
-            for (int ci = 0; ci < CF::MYCH; ++ci) {
-                const int ch = part + CF::NPARTS * ci;
-                if (ch < 2 * na) {
-                    float4 x[4];
-                    const float4* p2p = ch < nchunks ? sv_acquire(sv, q0 + 2 * nchunks + ch, r) : nullptr;
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {
-                        const int c0 = ch * 16 + 4 * c4;
-                        float t[4] = {0.f, 0.f, 0.f, 0.f};
-                        if (ch < nchunks && c0 < H && valid) {
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            const int c0 = ch * 16 + 4 * c4;
                             const float4 p2 = p2p[c4 * 128];
-                            const float pv[4] = {p2.x, p2.y, p2.z, p2.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                t[e] = (gef[ci][4 * c4 + e] * gate + kap * vec_s[3 * NP + c0 + e]) * dsilu_f(pv[e]);
+                            const float4 wq = *reinterpret_cast<const float4*>(vec_s + 3 * NP + c0);
+                            const f2 ta = fma2(kap2, lo2(wq), mul2(make_float2(v[4 * c4], v[4 * c4 + 1]), gate2));
+                            const f2 tb = fma2(kap2, hi2(wq), mul2(make_float2(v[4 * c4 + 2], v[4 * c4 + 3]), gate2));
+                            x[2 * c4] = mul2(ta, dsilu2(lo2(p2)));
+                            x[2 * c4 + 1] = mul2(tb, dsilu2(hi2(p2)));
                         }
-                        x[c4] = make_float4(t[0], t[1], t[2], t[3]);
+                        sv_release(sv, q0 + 2 * nchunks + ch);
+                        if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + (ch + CF::NPARTS) * 16, v);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) x[c] = f2s(0.f);
                     }
-                    if (ch < nchunks) sv_release(sv, q0 + 2 * nchunks + ch);
-                    put_chunk<NP>(p, it0 + na + (ch >> 1), r, half, x);
+                    TLW(320 + ch);
+                    rg.put_chunk2(it0 + na + (ch >> 1), r, half, x);
+                    TLW(340 + ch);
                 }
             }
             // ---- epilogue 2: g_pre1 = g_s1 * SiLU'(pre1) -> HBM (row-major per edge); radial / attr dots ----
             //      the row sums (g_Pa), column sums (g_Pb) and the coordinate gradient are reduced afterwards by the
             //      node-parallel pred_bwd_reduce_kernel: fixed summation order, no atomics, no per-chunk barriers here
+            TLW(60);
             mbar_wait(d2_full, tcnt & 1);
+            TLW(61);
             fence_after_sync();
-            float pr = 0.f, pa = 0.f;
+            f2 pr2 = f2s(0.f), pa2 = f2s(0.f);
             // g_pre1 rows are written through a per-warp transpose block: thread = row is what TMEM gives, but 16 bytes of 32
             // different rows per store instruction cost 32 L1 tag lookups; transposed, one instruction covers 8 rows x 64 bytes.
-            // The block lives in the A half of the operand ring, which is idle between the last MMA of GEMM 2 (d2_full) and the
-            // next tile's first operand store (after the barriers below).
-            float* stg = reinterpret_cast<float*>(base + ((warp - 2) >> 3) * CF::STAGE_BYTES) + ((warp - 2) & 7) * (32 * 20);
+            // The block (32 rows x 16 floats, 16-byte chunk c of row l at position c ^ ((l >> 1) & 3): conflict-free both ways)
+            // lives in the A ring, which is idle between the last MMA of GEMM 2 (d2_full) and the next tile's first operand
+            // store (after the barrier that ends the tile).
+            float* stg = reinterpret_cast<float*>(rg.a_base + ((warp - 2) >> 3) * CF::A_STAGE) + ((warp - 2) & 7) * (32 * 16);
             const int piece = lane & 3, rsub = lane >> 2;
+            const int wsw = (lane >> 1) & 3;
+            float v[16];
+            if (part < nchunks) tmem_ld16_issue_f(lane_addr + CF::D2_COL + part * 16, v);
 #pragma unroll 1
             for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
-                float v[16];
-                tmem_ld16(lane_addr + CF::D2_COL + ch * 16, v);
+                tmem_ld_wait();
+                TLW(400 + ch);
                 const float4* d1p = sv_acquire(sv, q0 + 3 * nchunks + ch, r);
+                TLW(420 + ch);
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
                     const int c0 = ch * 16 + 4 * c4;
-                    float4 gp = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (c0 < H) {
-                        const float4 d1 = d1p[c4 * 128];
-                        gp = make_float4(v[4 * c4] * d1.x, v[4 * c4 + 1] * d1.y, v[4 * c4 + 2] * d1.z, v[4 * c4 + 3] * d1.w);
-                        const float4 wr = *reinterpret_cast<const float4*>(vec_s + c0);
-                        const float4 wa = *reinterpret_cast<const float4*>(vec_s + NP + c0);
-                        pr += wr.x * gp.x + wr.y * gp.y + wr.z * gp.z + wr.w * gp.w;
-                        pa += wa.x * gp.x + wa.y * gp.y + wa.z * gp.z + wa.w * gp.w;
-                    }
-                    *reinterpret_cast<float4*>(stg + lane * 20 + 4 * c4) = gp;
+                    const float4 d1 = d1p[c4 * 128];
+                    const float4 wr = *reinterpret_cast<const float4*>(vec_s + c0);
+                    const float4 wa = *reinterpret_cast<const float4*>(vec_s + NP + c0);
+                    const f2 ga_ = mul2(make_float2(v[4 * c4], v[4 * c4 + 1]), lo2(d1)), gb2 = mul2(make_float2(v[4 * c4 + 2], v[4 * c4 + 3]), hi2(d1));
+                    pr2 = fma2(lo2(wr), ga_, pr2); pr2 = fma2(hi2(wr), gb2, pr2);
+                    pa2 = fma2(lo2(wa), ga_, pa2); pa2 = fma2(hi2(wa), gb2, pa2);
+                    *reinterpret_cast<float4*>(stg + lane * 16 + 4 * (c4 ^ wsw)) = cat2(ga_, gb2);
                 }
                 sv_release(sv, q0 + 3 * nchunks + ch);
+                if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + CF::D2_COL + (ch + CF::NPARTS) * 16, v);   // next chunk in flight during the stores
                 __syncwarp();
                 const int c = ch * 16 + 4 * piece;
                 if (c < H) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const int rl = group * 32 + rsub + 8 * i;
-                        if (rl < ne) *reinterpret_cast<float4*>(a.g_pre1 + (size_t)(e_lo + rl) * H + c) = *reinterpret_cast<const float4*>(stg + (rsub + 8 * i) * 20 + 4 * piece);
+                        const int rw = rsub + 8 * i, rl = group * 32 + rw;
+                        if (rl < ne) *reinterpret_cast<float4*>(a.g_pre1 + (size_t)(e_lo + rl) * H + c) = *reinterpret_cast<const float4*>(stg + rw * 16 + 4 * (piece ^ ((rw >> 1) & 3)));
                     }
                 }
                 __syncwarp();
             }
+            const float pr = pr2.x + pr2.y, pa = pa2.x + pa2.y;
             fence_before_sync();
             mbar_arrive(d_empty);
-            red_s[2 * CF::NPARTS * 128 + part * 128 + r] = pr;
-            red_s[3 * CF::NPARTS * 128 + part * 128 + r] = pa;
-            nbar(1, CF::NWORK);
+            red_s[part * 128 + r] = pr;
+            red_s[CF::NPARTS * 128 + part * 128 + r] = pa;
+            TLW(62);
+            bar_named(BAR_WORKERS, CF::NWORK);                     // also: the transpose blocks in the A ring are free again
+            TLW(63);
             if (part == 0 && valid) {
-                const float g_r = psum_parts<CF::NPARTS>(red_s + 2 * CF::NPARTS * 128, r);
-                const float g_a = psum_parts<CF::NPARTS>(red_s + 3 * CF::NPARTS * 128, r);
+                const float g_r = psum_parts<CF::NPARTS>(red_s, r);
+                const float g_a = psum_parts<CF::NPARTS>(red_s + CF::NPARTS * 128, r);
                 a.g_attr[e_lo + r] += g_a;
-                const float dx = geo_s[r], dy = geo_s[128 + r], dz = geo_s[256 + r];
-                const float gux = geo_s[384 + r], guy = geo_s[512 + r], guz = geo_s[640 + r];
+                const float dx = gf[GEO_HDR + 256 + r], dy = gf[GEO_HDR + 384 + r], dz = gf[GEO_HDR + 512 + r];
+                const float gux = gf[GEO_HDR + 640 + r], guy = gf[GEO_HDR + 768 + r], guz = gf[GEO_HDR + 896 + r];
                 const float nrm = sqrtf(dx * dx + dy * dy + dz * dz + 1e-8f);
                 const float inv = 1.f / (nrm + 1.f);
                 const float k2 = (gux * dx + guy * dy + guz * dz) * inv * inv / nrm;
@@ -609,7 +740,10 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::BWD_THREADS, 1) tc_pred_edge_bw
                 gd[1] = 2.f * g_r * dy + guy * inv - k2 * dy;
                 gd[2] = 2.f * g_r * dz + guz * inv - k2 * dz;
             }
-            nbar(1, CF::NWORK);                                  // red_s / seg_s free for the next tile
+            mbar_arrive(&geo_empty[gb_]);
+            TLW(70);
+            // red_s: the next write (epilogue 1 of the next tile) needs d1_full of that tile, i.e. operand atoms from every worker
+            // thread, which each thread stores after it has read red_s here
         }
     }
     fence_before_sync();
@@ -617,19 +751,27 @@ __global__ void __launch_bounds__(TcPredCfg<NP>::BWD_THREADS, 1) tc_pred_edge_bw
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+#ifdef GB_TIMELINE
+extern "C" int gb_debug_timeline_pred(unsigned long long* out, unsigned int* n, int reset) {
+    if (reset) { unsigned int z[5] = {0, 0, 0, 0, 0}; return (int)cudaMemcpyToSymbol(gb_tl_pred_n, z, sizeof(z)); }
+    cudaMemcpyFromSymbol(n, gb_tl_pred_n, sizeof(gb_tl_pred_n));
+    return (int)cudaMemcpyFromSymbol(out, gb_tl_pred, sizeof(gb_tl_pred));
+}
+#endif
+
 template <int NP>
 static void launch_bwd_t(const PredEdgeArgs& a, const float* wcimg_nt, const float* w2img_nt, int H, cudaStream_t s) {
     using CF = TcPredCfg<NP>;
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(tc_pred_edge_bwd_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM);
+        cudaFuncSetAttribute(tc_pred_edge_bwd_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcBwdCfg<NP>::SMEM);
         configured = true;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = a.g.n_tiles < sms ? a.g.n_tiles : sms;
-    tc_pred_edge_bwd_kernel<NP><<<grid, CF::BWD_THREADS, CF::SMEM, s>>>(a, wcimg_nt, w2img_nt, H);
+    tc_pred_edge_bwd_kernel<NP><<<grid, TcBwdCfg<NP>::THREADS, TcBwdCfg<NP>::SMEM, s>>>(a, wcimg_nt, w2img_nt, H);
 }
 
 void launch_pred_edge_bwd_tc(int H, const PredEdgeArgs& a, const float* wcimg_nt, const float* w2img_nt, cudaStream_t s) {
@@ -686,16 +828,16 @@ static void launch_fwd_t(bool save, const PredEdgeArgs& a, const float* w2img, c
     using CF = TcPredCfg<NP>;
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(tc_pred_edge_fwd_kernel<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM);
-        cudaFuncSetAttribute(tc_pred_edge_fwd_kernel<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM);
+        cudaFuncSetAttribute(tc_pred_edge_fwd_kernel<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcFwdCfg<NP>::SMEM);
+        cudaFuncSetAttribute(tc_pred_edge_fwd_kernel<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcFwdCfg<NP>::SMEM);
         configured = true;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = a.g.n_tiles < sms ? a.g.n_tiles : sms;
-    if (save) tc_pred_edge_fwd_kernel<NP, true><<<grid, CF::THREADS, CF::SMEM, s>>>(a, w2img, wcimg, H);
-    else tc_pred_edge_fwd_kernel<NP, false><<<grid, CF::THREADS, CF::SMEM, s>>>(a, w2img, wcimg, H);
+    if (save) tc_pred_edge_fwd_kernel<NP, true><<<grid, TcFwdCfg<NP>::THREADS, TcFwdCfg<NP>::SMEM, s>>>(a, w2img, wcimg, H);
+    else tc_pred_edge_fwd_kernel<NP, false><<<grid, TcFwdCfg<NP>::THREADS, TcFwdCfg<NP>::SMEM, s>>>(a, w2img, wcimg, H);
 }
 
 void launch_pred_edge_fwd_tc(int H, bool save, const PredEdgeArgs& a, const float* w2img, const float* wcimg, cudaStream_t s) {

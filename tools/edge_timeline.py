@@ -47,7 +47,7 @@ def main():
             d = 0 if prev is None else clk - prev
             print(f"  {code:4d} t={clk / 1.9:9.0f}ns  +{d / 1.9:7.0f}ns")
             prev = clk
-            if code in (60, 2, 70) or (r == 3 and code == 24):
+            if code in ((60, 2, 70) if fam == 'den' else (70, 4)) or (r == 3 and code == 24):
                 cnt += 1
                 if cnt >= tiles + 1:
                     break
