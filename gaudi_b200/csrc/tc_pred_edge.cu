@@ -216,34 +216,33 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
             TLW(11);
             const int* gi = geo_s + gb_ * CF::GEO_WORDS;
             const float* gf = reinterpret_cast<const float*>(gi);
-            const bool valid = r < gi[3];
             const int prc = gi[GEO_HDR + r];
             const int pa_off = (prc & 0xffff) * PS_PITCH + 16 * half, pb_off = (prc >> 16) * PS_PITCH + 16 * half;
             const float rad = gf[GEO_HDR + 128 + r], a0 = gf[GEO_HDR + 256 + r];
+            const f2 rad2 = f2s(rad), a02 = f2s(a0);
             for (int j = part >> 1; j < na; j += CF::NPARTS / 2) {
                 const uint32_t pit = k * na + j;
                 const float* pst = ps.acquire(pit);
-                float4 x[4];
+                TLW(15 + j);
+                // no per-element bounds checks: columns beyond H are multiplied by zero-padded weights downstream, rows beyond the
+                // tile's edges read P-stage row 0 and produce finite values nobody sums
+                f2 x[8];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int k0 = j * ATOM_K + 16 * half + 4 * c;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), dv = v;
-                    if (valid && k0 < H) {
-                        const float4 pa = *reinterpret_cast<const float4*>(pst + pa_off + 4 * c);
-                        const float4 pb = *reinterpret_cast<const float4*>(pst + pb_off + 4 * c);
-                        const float4 wr = *reinterpret_cast<const float4*>(vec_s + k0);
-                        const float4 wa = *reinterpret_cast<const float4*>(vec_s + NP + k0);
-                        silu_both(pa.x + pb.x + wr.x * rad + wa.x * a0, v.x, dv.x);
-                        silu_both(pa.y + pb.y + wr.y * rad + wa.y * a0, v.y, dv.y);
-                        silu_both(pa.z + pb.z + wr.z * rad + wa.z * a0, v.z, dv.z);
-                        silu_both(pa.w + pb.w + wr.w * rad + wa.w * a0, v.w, dv.w);
-                    }
-                    x[c] = v;
-                    if (SAVE && k0 < H) *reinterpret_cast<float4*>(a.sv_d1 + (((size_t)tile * (H / 4) + (k0 >> 2)) * 128 + r) * 4) = dv;
+                    const float4 pa = *reinterpret_cast<const float4*>(pst + pa_off + 4 * c);
+                    const float4 pb = *reinterpret_cast<const float4*>(pst + pb_off + 4 * c);
+                    const float4 wr = *reinterpret_cast<const float4*>(vec_s + k0);
+                    const float4 wa = *reinterpret_cast<const float4*>(vec_s + NP + k0);
+                    f2 da, db;
+                    silu_both2(fma2(lo2(wa), a02, fma2(lo2(wr), rad2, add2(lo2(pa), lo2(pb)))), x[2 * c], da);
+                    silu_both2(fma2(hi2(wa), a02, fma2(hi2(wr), rad2, add2(hi2(pa), hi2(pb)))), x[2 * c + 1], db);
+                    // (plain stores: the cache-streaming form st.global.cs made this kernel 8 % slower)
+                    if (SAVE && k0 < H) *reinterpret_cast<float4*>(a.sv_d1 + (((size_t)tile * (H / 4) + (k0 >> 2)) * 128 + r) * 4) = cat2(da, db);
                 }
                 ps.release(pit);
                 TLW(20 + j);
-                rg.put_chunk(k * 2 * na + j, r, half, x);
+                rg.put_chunk2(k * 2 * na + j, r, half, x);
                 TLW(30 + j);
             }
         };
@@ -263,66 +262,75 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
             mbar_wait(d1_full, k & 1);
             TLW(41);
             fence_after_sync();
-            float q[CF::MYCH][16];
-            float psum = 0.f;
-#pragma unroll
-            for (int ci = 0; ci < CF::MYCH; ++ci) {
-                const int ch = part + CF::NPARTS * ci;
-                if (ch < nchunks) {
-                    tmem_ld16(lane_addr + ch * 16, q[ci]);
+            f2 psum2 = f2s(0.f);
+            // chunk-streaming: q = SiLU(pre2) goes BACK to tensor memory (same columns of accumulator 1) instead of waiting in 64
+            // registers for the row-wide gate; the pass below reads it again.  The next chunk's TMEM read is always in flight.
+            {
+                float v[16];
+                if (part < nchunks) tmem_ld16_issue_f(lane_addr + part * 16, v);
+#pragma unroll 1
+                for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
+                    tmem_ld_wait();
+                    float w[16];
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         const int c0 = ch * 16 + 4 * c4;
-                        float pre[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            pre[e] = q[ci][4 * c4 + e] + vec_s[2 * NP + c0 + e];
-                            const float v = silu_f(pre[e]);
-                            q[ci][4 * c4 + e] = v;
-                            psum = fmaf(vec_s[3 * NP + c0 + e], v, psum);
-                        }
-                        if (SAVE && c0 < H)
-                            *reinterpret_cast<float4*>(a.sv_pre2 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4) = make_float4(pre[0], pre[1], pre[2], pre[3]);
+                        const float4 b2 = *reinterpret_cast<const float4*>(vec_s + 2 * NP + c0);
+                        const float4 wq = *reinterpret_cast<const float4*>(vec_s + 3 * NP + c0);
+                        const f2 pa_ = add2(make_float2(v[4 * c4], v[4 * c4 + 1]), lo2(b2));
+                        const f2 pb_ = add2(make_float2(v[4 * c4 + 2], v[4 * c4 + 3]), hi2(b2));
+                        if (SAVE && c0 < H) *reinterpret_cast<float4*>(a.sv_pre2 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4) = cat2(pa_, pb_);
+                        const f2 va = silu2(pa_), vb = silu2(pb_);
+                        w[4 * c4] = va.x; w[4 * c4 + 1] = va.y; w[4 * c4 + 2] = vb.x; w[4 * c4 + 3] = vb.y;
+                        psum2 = fma2(lo2(wq), va, psum2); psum2 = fma2(hi2(wq), vb, psum2);
                     }
+                    if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + (ch + CF::NPARTS) * 16, v);
+                    tmem_st16(lane_addr + ch * 16, w);
                 }
+                tmem_st_wait();
             }
-            fence_before_sync();
-            mbar_arrive(d1_empty);                              // accumulator 1 is in registers: GEMM 1 of the next tile may start
             // red1 / red2 alternate (gate logits of tile k, coordinate head of tile k, gate logits of tile k+1, ...): a warp is never
             // more than one quadrant barrier ahead of the warps it shares the rows with, so one copy of each is enough
-            red1[part * 128 + r] = psum;
+            red1[part * 128 + r] = psum2.x + psum2.y;
             TLW(42);
             bar_named(BAR_QUAD + group, 128);
             TLW(43);
             const float gate = a.attention ? sigmoid_f(psum_parts<CF::NPARTS>(red1, r) + a.att_b) : 1.f;
+            const f2 gate2 = f2s(gate);
             // ---- gated edge feature: segment sums -> agg, and operand atoms of GEMM 2 ----
+            {
+                float v[16];
+                if (part < nchunks) tmem_ld16_issue_f(lane_addr + part * 16, v);
+#pragma unroll 1
+                for (int ch = part; ch < 2 * na; ch += CF::NPARTS) {
+                    f2 x[8];
+                    if (ch < nchunks) {
+                        tmem_ld_wait();
 #pragma unroll
-            for (int ci = 0; ci < CF::MYCH; ++ci) {
-                const int ch = part + CF::NPARTS * ci;
-                if (ch < nchunks) {
-                    float4 x[4];
+                        for (int c = 0; c < 8; ++c) {
+                            x[c] = mul2(make_float2(v[2 * c], v[2 * c + 1]), gate2);
+                            my_ef[r * CF::EF_STRIDE + 2 * c] = x[c].x; my_ef[r * CF::EF_STRIDE + 2 * c + 1] = x[c].y;
+                        }
+                        if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + (ch + CF::NPARTS) * 16, v);
+                        rg.put_chunk2(it0 + na + (ch >> 1), r, half, x);
+                        bar_named(BAR_PART + part, 128);
+                        for (int nl = r >> 4; nl < nn; nl += 8) {
+                            const int col = r & 15, c = ch * 16 + col;
+                            float sum = 0.f;
+                            for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += my_ef[mm * CF::EF_STRIDE + col];
+                            if (c < H) a.agg[(size_t)(node_lo + nl) * H + c] = sum;
+                        }
+                        bar_named(BAR_PART + part, 128);
+                    } else {
+                        // chunk beyond the hidden width but inside the last atom: publish zeros so the atom completes
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        x[c] = make_float4(q[ci][4 * c] * gate, q[ci][4 * c + 1] * gate, q[ci][4 * c + 2] * gate, q[ci][4 * c + 3] * gate);
-                        if (!valid) x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        my_ef[r * CF::EF_STRIDE + 4 * c] = x[c].x; my_ef[r * CF::EF_STRIDE + 4 * c + 1] = x[c].y;
-                        my_ef[r * CF::EF_STRIDE + 4 * c + 2] = x[c].z; my_ef[r * CF::EF_STRIDE + 4 * c + 3] = x[c].w;
+                        for (int c = 0; c < 8; ++c) x[c] = f2s(0.f);
+                        rg.put_chunk2(it0 + na + (ch >> 1), r, half, x);
                     }
-                    rg.put_chunk(it0 + na + (ch >> 1), r, half, x);
-                    bar_named(BAR_PART + part, 128);
-                    for (int nl = r >> 4; nl < nn; nl += 8) {
-                        const int col = r & 15, c = ch * 16 + col;
-                        float sum = 0.f;
-                        for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += my_ef[mm * CF::EF_STRIDE + col];
-                        if (c < H) a.agg[(size_t)(node_lo + nl) * H + c] = sum;
-                    }
-                    bar_named(BAR_PART + part, 128);
-                } else if (ch < 2 * na) {
-                    // chunk beyond the hidden width but inside the last atom: publish zeros so the atom completes
-                    float4 x[4] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-                    rg.put_chunk(it0 + na + (ch >> 1), r, half, x);
                 }
             }
+            fence_before_sync();
+            mbar_arrive(d1_empty);                              // accumulator 1 (and q parked in it) is consumed: GEMM 1 of the next tile may start
             // ---- GEMM 1 operand of the next tile (its MMAs overlap epilogue 2 below) ----
             TLW(50);
             if (tile + (int)gridDim.x < g.n_tiles) build1(k + 1, tile + gridDim.x);
@@ -331,25 +339,31 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
             mbar_wait(d2_full, k & 1);
             TLW(61);
             fence_after_sync();
-            float phi_part = 0.f;
-#pragma unroll 1
-            for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
+            f2 phi2 = f2s(0.f);
+            {
                 float v[16];
-                tmem_ld16(lane_addr + CF::D2_COL + ch * 16, v);
+                if (part < nchunks) tmem_ld16_issue_f(lane_addr + CF::D2_COL + part * 16, v);
+#pragma unroll 1
+                for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
+                    tmem_ld_wait();
+                    float w[16];
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    const int c0 = ch * 16 + 4 * c4;
-                    float d3[4];
+                    for (int i = 0; i < 16; ++i) w[i] = v[i];
+                    if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + CF::D2_COL + (ch + CF::NPARTS) * 16, v);   // next chunk in flight
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float s3;
-                        silu_both(v[4 * c4 + e] + vec_s[4 * NP + c0 + e], s3, d3[e]);
-                        phi_part = fmaf(vec_s[5 * NP + c0 + e], s3, phi_part);
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const int c0 = ch * 16 + 4 * c4;
+                        const float4 bc = *reinterpret_cast<const float4*>(vec_s + 4 * NP + c0);
+                        const float4 wl = *reinterpret_cast<const float4*>(vec_s + 5 * NP + c0);
+                        f2 sa, sb, da, db;
+                        silu_both2(add2(make_float2(w[4 * c4], w[4 * c4 + 1]), lo2(bc)), sa, da);
+                        silu_both2(add2(make_float2(w[4 * c4 + 2], w[4 * c4 + 3]), hi2(bc)), sb, db);
+                        phi2 = fma2(lo2(wl), sa, phi2); phi2 = fma2(hi2(wl), sb, phi2);
+                        if (SAVE && c0 < H) *reinterpret_cast<float4*>(a.sv_d3 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4) = cat2(da, db);
                     }
-                    if (SAVE && c0 < H)
-                        *reinterpret_cast<float4*>(a.sv_d3 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4) = make_float4(d3[0], d3[1], d3[2], d3[3]);
                 }
             }
+            const float phi_part = phi2.x + phi2.y;
             fence_before_sync();
             mbar_arrive(d2_empty);
             red2[part * 128 + r] = phi_part;
@@ -611,7 +625,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                     for (int c4 = 0; c4 < 4; ++c4) {
                         const int c0 = ch * 16 + 4 * c4;
                         float4 ga = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (ga_staged || c0 < H) ga = *reinterpret_cast<const float4*>(ga_row + c0);     // staged rows are NP wide
+                        if (c0 < H) ga = *reinterpret_cast<const float4*>(ga_row + c0);     // (the staged copy only holds the H real columns)
                         const float4 p2 = p2p[c4 * 128];
                         const float4 wq = *reinterpret_cast<const float4*>(vec_s + 3 * NP + c0);
                         const f2 qa = silu2(lo2(p2)), qb = silu2(hi2(p2));
