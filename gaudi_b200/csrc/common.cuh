@@ -107,8 +107,42 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+#ifdef GB_DEBUG_HANG
+// development aid: a wait that gives up after a long spin, records (block, thread, barrier smem offset, parity) in a host-mapped
+// buffer (gb_debug_set_hang_buf) and traps, so that a deadlock turns into a readable report instead of a hung GPU
+__device__ int* gb_hang_buf;
+#endif
+#ifdef GB_DEBUG_HANG
+__device__ int gb_dbg_tag_unused;
+#define GB_TAG(x) , (x)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = -1) {
+#else
+#define GB_TAG(x)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#endif
     uint32_t done;
+#ifdef GB_DEBUG_HANG
+    for (long long spin = 0;; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spin > 30000) {
+            volatile int* hb = gb_hang_buf;
+            if (hb && (threadIdx.x & 31) == 0 && blockIdx.x < 24) {
+                const int i = atomicAdd((int*)hb, 1);
+                if (i < 1000) { hb[4 + 4 * i] = blockIdx.x; hb[5 + 4 * i] = threadIdx.x; hb[6 + 4 * i] = (int)smem_u32(bar); hb[7 + 4 * i] = (int)parity | (tag << 4); }
+                __threadfence_system();
+            }
+            for (int w = 0; w < 3000000; ++w) __nanosleep(1000);
+            __trap();
+        }
+    }
+#endif
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"

@@ -116,6 +116,15 @@ __device__ __forceinline__ void tmem_ld16_issue_f(uint32_t taddr, float (&v)[16]
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait form that also carries the destination registers of the outstanding loads as in/out operands: without it the compiler is
+// free to move pure register operations on them (e.g. the MOVs that pair two values for a packed FP32x2 instruction) ABOVE the
+// wait, where the asynchronous load may not have written them yet
+__device__ __forceinline__ void tmem_ld_wait16(float (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                   "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+                 :: "memory");
+}
 // 32 lanes x 16 columns back into tensor memory (thread t writes row lane base + t): lets an epilogue park a partially processed
 // accumulator chunk in TMEM instead of in 16 registers while it waits for a row-wide reduction
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
@@ -184,6 +193,16 @@ struct Rings {
         for (int s = 0; s < SA; ++s) { mbar_init(&full_a[s], a_arrivals); mbar_init(&empty_a[s], 1); }
         for (int s = 0; s < SW; ++s) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], 1); }
     }
+    // Stage and round of K-atom j of the CTA's g-th GEMM (every GEMM has na atoms).  The stage is the parity of j INSIDE its
+    // GEMM, not of a running atom count: an atom with even j is always built by worker parts 0/1 and one with odd j by parts
+    // 2/3, so each pair owns one stage and observes every phase of that stage's `empty` barrier in order.  (With a running
+    // count and an odd na the pairs swap stages from one GEMM to the next; a pair that had not touched a stage for a whole GEMM
+    // could then be two phases behind its `empty` barrier, which a parity wait cannot distinguish from "ready": a real,
+    // timing-dependent deadlock of the software-pipelined kernels.)
+    static __device__ __forceinline__ void slot(uint32_t g, int j, int na, uint32_t& s, uint32_t& round) {
+        s = (uint32_t)j & 1u;
+        round = g * (uint32_t)((na + 1 - (int)s) >> 1) + ((uint32_t)j >> 1);
+    }
     // TMA warp (one lane): the 2*na half-atoms of one GEMM; wq = running half-atom counter of this CTA
     __device__ __forceinline__ void tma_gemm(uint32_t& wq, int na, const float* wimg) const {
         for (int h = 0; h < 2 * na; ++h, ++wq) {
@@ -193,15 +212,16 @@ struct Rings {
             bulk_g2s(w_base + s * W_BYTES, wimg + (size_t)h * NP * ATOM_K, W_BYTES, &full_w[s]);
         }
     }
-    // MMA warp (one lane): na atoms of K (H columns) into accumulator d_tmem; it = running atom counter, wq as above
-    __device__ __forceinline__ void mma_gemm(uint32_t& it, uint32_t& wq, int na, int H, uint32_t d_tmem) const {
+    // MMA warp (one lane): na atoms of K (H columns) into accumulator d_tmem; g = running GEMM counter of this CTA, wq as above
+    __device__ __forceinline__ void mma_gemm(uint32_t& g, uint32_t& wq, int na, int H, uint32_t d_tmem) const {
         constexpr uint32_t idesc = instr_desc_tf32(NP);
-        for (int j = 0; j < na; ++j, ++it) {
-            const uint32_t sa = it % SA, ra = it / SA;
+        for (int j = 0; j < na; ++j) {
+            uint32_t sa, ra;
+            slot(g, j, na, sa, ra);
             const int kvalid = H - j * ATOM_K;
             const int ksteps = kvalid >= ATOM_K ? 4 : (kvalid + 7) / 8;
             const uint32_t a_hi = smem_u32(a_base + sa * A_STAGE), a_lo = a_hi + A_BYTES;
-            mbar_wait(&full_a[sa], ra & 1);
+            mbar_wait(&full_a[sa], ra & 1 GB_TAG((int)(g * 16 + j)));
             {
                 const uint32_t s = wq % SW, r = wq / SW;
                 mbar_wait(&full_w[s], r & 1);
@@ -226,11 +246,13 @@ struct Rings {
             }
             mma_commit(&empty_a[sa]);
         }
+        ++g;
     }
     // worker, packed form: x[2c], x[2c+1] = the two halves of 16-byte chunk c
-    __device__ __forceinline__ void put_chunk2(uint32_t it, int r, int half, const f2 (&x)[8]) const {
-        const uint32_t s = it % SA, rr = it / SA;
-        if (rr > 0) mbar_wait(&empty_a[s], (rr - 1) & 1);
+    __device__ __forceinline__ void put_chunk2(uint32_t g, int j, int na, int r, int half, const f2 (&x)[8]) const {
+        uint32_t s, rr;
+        slot(g, j, na, s, rr);
+        if (rr > 0) mbar_wait(&empty_a[s], (rr - 1) & 1 GB_TAG((int)(g * 16 + j)));
         unsigned char* a_hi = a_base + s * A_STAGE;
 #pragma unroll
         for (int c = 0; c < 4; ++c) store_split2(a_hi, a_hi + A_BYTES, r, 4 * half + c, x[2 * c], x[2 * c + 1]);
@@ -238,8 +260,9 @@ struct Rings {
         mbar_arrive(&full_a[s]);
     }
     // worker: publish this thread's 16 columns (4 x float4) of atom `it`; half h writes the 16-byte chunks 4h..4h+3 of its row
-    __device__ __forceinline__ void put_chunk(uint32_t it, int r, int half, const float4 (&x)[4]) const {
-        const uint32_t s = it % SA, rr = it / SA;
+    __device__ __forceinline__ void put_chunk(uint32_t g, int j, int na, int r, int half, const float4 (&x)[4]) const {
+        uint32_t s, rr;
+        slot(g, j, na, s, rr);
         if (rr > 0) mbar_wait(&empty_a[s], (rr - 1) & 1);
         unsigned char* a_hi = a_base + s * A_STAGE;
 #pragma unroll
@@ -266,20 +289,31 @@ struct PStage {
     float* buf; uint64_t* full; uint64_t* empty;            // [4] each; full: 1 arrival (loader lane 0), empty: 256 (two parts)
     int lg;                                                 // log2(stages): 2 when every tile of the launch needs <= 48 rows, else 1
     __device__ __forceinline__ void init() const { for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 256); } }
-    __device__ __forceinline__ uint32_t stage(uint32_t it) const { return it & ((1u << lg) - 1u); }
-    __device__ __forceinline__ uint32_t round(uint32_t it) const { return it >> lg; }
+    // Stage and round of K-atom j of the CTA's k-th tile.  As in Rings::slot the worker pair (j & 1) owns its stages: stage =
+    // pair (+ 2 for every other atom of that pair when there are four stages), so a pair sees every phase of its barriers.
+    __device__ __forceinline__ void slot(uint32_t k, int j, int na, uint32_t& s, uint32_t& round) const {
+        const uint32_t pair = (uint32_t)j & 1u;
+        const uint32_t idx = k * (uint32_t)((na + 1 - (int)pair) >> 1) + ((uint32_t)j >> 1);
+        if (lg == 2) { s = pair + 2u * (idx & 1u); round = idx >> 1; }
+        else { s = pair; round = idx; }
+    }
     __device__ __forceinline__ float* ptr(uint32_t s) const { return buf + s * (PS_FLOATS >> lg); }
     // worker side
-    __device__ __forceinline__ const float* acquire(uint32_t it) const { mbar_wait(&full[stage(it)], round(it) & 1); return ptr(stage(it)); }
-    __device__ __forceinline__ void release(uint32_t it) const { mbar_arrive(&empty[stage(it)]); }
+    __device__ __forceinline__ const float* acquire(uint32_t k, int j, int na) const {
+        uint32_t s, rr; slot(k, j, na, s, rr);
+        mbar_wait(&full[s], rr & 1);
+        return ptr(s);
+    }
+    __device__ __forceinline__ void release(uint32_t k, int j, int na) const { uint32_t s, rr; slot(k, j, na, s, rr); mbar_arrive(&empty[s]); }
 };
 
-// One loader warp (ldw = 0 / 1 handles the even / odd atoms of the CTA's running atom sequence): atom j of a tile.
+// One loader warp (warp ldw stages the atoms with j & 1 == ldw): atom j of the CTA's k-th tile.
 // P is [n_nodes][2H]; cn_lo/ncn = first node / node count of the molecules the tile's rows belong to.
-__device__ __forceinline__ void pstage_load_atom(const PStage& ps, uint32_t it, int j, int H, const float* __restrict__ P,
+__device__ __forceinline__ void pstage_load_atom(const PStage& ps, uint32_t k, int j, int na, int H, const float* __restrict__ P,
                                                  int node_lo, int nn, int cn_lo, int ncn, int lane) {
     const int rows = nn + ncn;
-    const uint32_t s = ps.stage(it), rr = ps.round(it);
+    uint32_t s, rr;
+    ps.slot(k, j, na, s, rr);
     if (rr > 0) mbar_wait(&ps.empty[s], (rr - 1) & 1);
     float* dst = ps.ptr(s);
     const int kbase = j * ATOM_K;

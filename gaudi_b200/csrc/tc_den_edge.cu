@@ -94,13 +94,13 @@ __global__ void __launch_bounds__(TcEdgeCfg<NP>::THREADS, 1) tc_den_edge_kernel(
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            uint32_t it = 0, wq = 0, tcnt = 0;
+            uint32_t gq = 0, wq = 0, tcnt = 0;
             for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
                 const uint32_t ab = tcnt & 1, use = tcnt >> 1;
                 if (use > 0) mbar_wait(&d_empty[ab], (use - 1) & 1);
                 fence_after_sync();
                 TLD(2, 1);
-                rg.mma_gemm(it, wq, na, H, tmem_base + ab * CF::ACC_STRIDE);
+                rg.mma_gemm(gq, wq, na, H, tmem_base + ab * CF::ACC_STRIDE);
                 mma_commit(&d_full[ab]);
                 TLD(2, 2);
             }
@@ -151,9 +151,9 @@ __global__ void __launch_bounds__(TcEdgeCfg<NP>::THREADS, 1) tc_den_edge_kernel(
         for (uint32_t tcnt = 0; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
             const int ntile = tile + gridDim.x;
             if (ntile < g.n_tiles) tile_meta_load(nxt, g, ntile, lane, ldw == 1);
-            for (int j = 0; j < na; ++j) {
-                const uint32_t it = tcnt * na + j;
-                if ((int)(it & 1) == ldw) { pstage_load_atom(ps, it, j, H, a.P, cur.node_lo, cur.nn, cur.cn_lo, cur.ncn, lane); if (lane == 0) TLD(3 + ldw, 20 + j); }
+            for (int j = ldw; j < na; j += 2) {
+                pstage_load_atom(ps, tcnt, j, na, H, a.P, cur.node_lo, cur.nn, cur.cn_lo, cur.ncn, lane);
+                if (lane == 0) TLD(3 + ldw, 20 + j);
             }
             if (ntile < g.n_tiles) {
                 if (ldw == 1) { geo_emit(nxt, tcnt + 1); if (lane == 0) TLD(4, 70); }
@@ -181,8 +181,7 @@ __global__ void __launch_bounds__(TcEdgeCfg<NP>::THREADS, 1) tc_den_edge_kernel(
             const int pa_off = gi[GEO_HDR + r] * PS_PITCH + 16 * half, pb_off = gi[GEO_HDR + 128 + r] * PS_PITCH + 16 * half;
             const float rad = gf[GEO_HDR + 256 + r], d0 = gf[GEO_HDR + 384 + r];
             for (int j = part >> 1; j < na; j += 2) {
-                const uint32_t it = k * na + j;
-                const float* pst = ps.acquire(it);
+                const float* pst = ps.acquire(k, j, na);
                 if (tlr >= 0) TLD(tlr, 20 + j);
                 float4 x[4];
 #pragma unroll
@@ -200,9 +199,9 @@ __global__ void __launch_bounds__(TcEdgeCfg<NP>::THREADS, 1) tc_den_edge_kernel(
                         x[c].w = silu_f(pa.w + pb.w + wr.w * rad + wd.w * d0);
                     }
                 }
-                ps.release(it);                                  // P slice consumed (the loads above fed the arithmetic)
+                ps.release(k, j, na);                            // P slice consumed (the loads above fed the arithmetic)
                 if (tlr >= 0) TLD(tlr, 30 + j);
-                rg.put_chunk(it, r, half, x);
+                rg.put_chunk(k, j, na, r, half, x);
                 if (tlr >= 0) TLD(tlr, 40 + j);
             }
         };

@@ -43,19 +43,15 @@ struct TcPredCfg {
     // backward only: one extra producer warp streams the saved activations (16-column chunks of the float4 "Q layout",
     // 4 planes x 128 rows x 16 B = 8 KB, contiguous in HBM) through an 8-slot ring (two chunks per worker part in flight: with
     // one slot per part the HBM latency of every chunk was exposed -- ~1.5 us on each of the 13 chunk steps of a part and tile)
-    static constexpr int SV_SLOTS = 8;
-    static constexpr int SV_SLOT_BYTES = 4 * 128 * 16;
+    static constexpr int SV_SLOT_BYTES = 4 * 128 * 16;                     // one 16-column chunk of a tile: 4 planes x 128 rows x 16 B
 };
 
-struct SvRing { unsigned char* buf; uint64_t* full; uint64_t* empty; };
-
-// consumer side of the saved-activation ring: wait for chunk q, return this row's first float4 (plane c at +128*c)
-__device__ __forceinline__ const float4* sv_acquire(const SvRing& sv, uint32_t q, int r) {
-    const uint32_t s = q & 7, rr = q >> 3;
-    mbar_wait(&sv.full[s], rr & 1);
-    return reinterpret_cast<const float4*>(sv.buf + s * 8192) + r;
-}
-__device__ __forceinline__ void sv_release(const SvRing& sv, uint32_t q) { mbar_arrive(&sv.empty[q & 7]); }
+// saved-activation ring.  `round[s]` = number of the round (q / slots) whose chunk the producer last started to load into slot s.
+// A consumer checks it before waiting on full[s]: the occupants of a slot alternate between two worker parts when the slot count
+// is not a multiple of the part count, so a part can reach its wait for round r while the producer has not even started round
+// r-1 of that slot -- and an mbarrier parity wait cannot tell "round r" from "round r-2" (it would pass on stale data and then
+// release the slot a second time; this was a real, timing-dependent deadlock with 6 slots and 4 parts).
+struct SvRing { unsigned char* buf; uint64_t* full; uint64_t* empty; volatile uint32_t* round; };
 
 template <int NPARTS>
 __device__ __forceinline__ float psum_parts(const float* red, int r) {
@@ -135,18 +131,18 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            uint32_t it = 0, wq = 0, tcnt = 0;
+            uint32_t gq = 0, wq = 0, tcnt = 0;
             for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
                 if (tcnt > 0) mbar_wait(d1_empty, (tcnt - 1) & 1);
                 fence_after_sync();
                 TLP(2, 1);
-                rg.mma_gemm(it, wq, na, H, tmem_base);
+                rg.mma_gemm(gq, wq, na, H, tmem_base);
                 mma_commit(d1_full);
                 TLP(2, 2);
                 if (tcnt > 0) mbar_wait(d2_empty, (tcnt - 1) & 1);
                 fence_after_sync();
                 TLP(2, 3);
-                rg.mma_gemm(it, wq, na, H, tmem_base + CF::D2_COL);
+                rg.mma_gemm(gq, wq, na, H, tmem_base + CF::D2_COL);
                 mma_commit(d2_full);
                 TLP(2, 4);
             }
@@ -190,10 +186,7 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
         for (uint32_t tcnt = 0; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
             const int ntile = tile + gridDim.x;
             if (ntile < g.n_tiles) tile_meta_load(nxt, g, ntile, lane, ldw == 1);
-            for (int j = 0; j < na; ++j) {
-                const uint32_t pit = tcnt * na + j;
-                if ((int)(pit & 1) == ldw) pstage_load_atom(ps, pit, j, H, a.P, cur.node_lo, cur.nn, cur.cn_lo, cur.ncn, lane);
-            }
+            for (int j = ldw; j < na; j += 2) pstage_load_atom(ps, tcnt, j, na, H, a.P, cur.node_lo, cur.nn, cur.cn_lo, cur.ncn, lane);
             if (ntile < g.n_tiles) {
                 if (ldw == 1) geo_emit(nxt, tcnt + 1);
                 cur = nxt;
@@ -216,33 +209,33 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
             TLW(11);
             const int* gi = geo_s + gb_ * CF::GEO_WORDS;
             const float* gf = reinterpret_cast<const float*>(gi);
+            const bool valid = r < gi[3];
             const int prc = gi[GEO_HDR + r];
             const int pa_off = (prc & 0xffff) * PS_PITCH + 16 * half, pb_off = (prc >> 16) * PS_PITCH + 16 * half;
             const float rad = gf[GEO_HDR + 128 + r], a0 = gf[GEO_HDR + 256 + r];
-            const f2 rad2 = f2s(rad), a02 = f2s(a0);
             for (int j = part >> 1; j < na; j += CF::NPARTS / 2) {
-                const uint32_t pit = k * na + j;
-                const float* pst = ps.acquire(pit);
-                TLW(15 + j);
-                // no per-element bounds checks: columns beyond H are multiplied by zero-padded weights downstream, rows beyond the
-                // tile's edges read P-stage row 0 and produce finite values nobody sums
-                f2 x[8];
+                const float* pst = ps.acquire(k, j, na);
+                float4 x[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int k0 = j * ATOM_K + 16 * half + 4 * c;
-                    const float4 pa = *reinterpret_cast<const float4*>(pst + pa_off + 4 * c);
-                    const float4 pb = *reinterpret_cast<const float4*>(pst + pb_off + 4 * c);
-                    const float4 wr = *reinterpret_cast<const float4*>(vec_s + k0);
-                    const float4 wa = *reinterpret_cast<const float4*>(vec_s + NP + k0);
-                    f2 da, db;
-                    silu_both2(fma2(lo2(wa), a02, fma2(lo2(wr), rad2, add2(lo2(pa), lo2(pb)))), x[2 * c], da);
-                    silu_both2(fma2(hi2(wa), a02, fma2(hi2(wr), rad2, add2(hi2(pa), hi2(pb)))), x[2 * c + 1], db);
-                    // (plain stores: the cache-streaming form st.global.cs made this kernel 8 % slower)
-                    if (SAVE && k0 < H) *reinterpret_cast<float4*>(a.sv_d1 + (((size_t)tile * (H / 4) + (k0 >> 2)) * 128 + r) * 4) = cat2(da, db);
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), dv = v;
+                    if (valid && k0 < H) {
+                        const float4 pa = *reinterpret_cast<const float4*>(pst + pa_off + 4 * c);
+                        const float4 pb = *reinterpret_cast<const float4*>(pst + pb_off + 4 * c);
+                        const float4 wr = *reinterpret_cast<const float4*>(vec_s + k0);
+                        const float4 wa = *reinterpret_cast<const float4*>(vec_s + NP + k0);
+                        silu_both(pa.x + pb.x + wr.x * rad + wa.x * a0, v.x, dv.x);
+                        silu_both(pa.y + pb.y + wr.y * rad + wa.y * a0, v.y, dv.y);
+                        silu_both(pa.z + pb.z + wr.z * rad + wa.z * a0, v.z, dv.z);
+                        silu_both(pa.w + pb.w + wr.w * rad + wa.w * a0, v.w, dv.w);
+                    }
+                    x[c] = v;
+                    if (SAVE && k0 < H) *reinterpret_cast<float4*>(a.sv_d1 + (((size_t)tile * (H / 4) + (k0 >> 2)) * 128 + r) * 4) = dv;
                 }
-                ps.release(pit);
+                ps.release(k, j, na);
                 TLW(20 + j);
-                rg.put_chunk2(k * 2 * na + j, r, half, x);
+                rg.put_chunk(2 * k, j, na, r, half, x);
                 TLW(30 + j);
             }
         };
@@ -256,81 +249,71 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
             const int* seg_s = gi + 4;
             const int node_lo = gi[0], nn = gi[1], e_lo = gi[2], ne = gi[3];
             const bool valid = r < ne;
-            const uint32_t it0 = k * 2 * na;
             // ---- epilogue 1: q = SiLU(pre2), attention gate ----
             TLW(40);
             mbar_wait(d1_full, k & 1);
             TLW(41);
             fence_after_sync();
-            f2 psum2 = f2s(0.f);
-            // chunk-streaming: q = SiLU(pre2) goes BACK to tensor memory (same columns of accumulator 1) instead of waiting in 64
-            // registers for the row-wide gate; the pass below reads it again.  The next chunk's TMEM read is always in flight.
-            {
-                float v[16];
-                if (part < nchunks) tmem_ld16_issue_f(lane_addr + part * 16, v);
-#pragma unroll 1
-                for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
-                    tmem_ld_wait();
-                    float w[16];
+            float q[CF::MYCH][16];
+            float psum = 0.f;
+#pragma unroll
+            for (int ci = 0; ci < CF::MYCH; ++ci) {
+                const int ch = part + CF::NPARTS * ci;
+                if (ch < nchunks) {
+                    tmem_ld16(lane_addr + ch * 16, q[ci]);
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         const int c0 = ch * 16 + 4 * c4;
-                        const float4 b2 = *reinterpret_cast<const float4*>(vec_s + 2 * NP + c0);
-                        const float4 wq = *reinterpret_cast<const float4*>(vec_s + 3 * NP + c0);
-                        const f2 pa_ = add2(make_float2(v[4 * c4], v[4 * c4 + 1]), lo2(b2));
-                        const f2 pb_ = add2(make_float2(v[4 * c4 + 2], v[4 * c4 + 3]), hi2(b2));
-                        if (SAVE && c0 < H) *reinterpret_cast<float4*>(a.sv_pre2 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4) = cat2(pa_, pb_);
-                        const f2 va = silu2(pa_), vb = silu2(pb_);
-                        w[4 * c4] = va.x; w[4 * c4 + 1] = va.y; w[4 * c4 + 2] = vb.x; w[4 * c4 + 3] = vb.y;
-                        psum2 = fma2(lo2(wq), va, psum2); psum2 = fma2(hi2(wq), vb, psum2);
-                    }
-                    if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + (ch + CF::NPARTS) * 16, v);
-                    tmem_st16(lane_addr + ch * 16, w);
-                }
-                tmem_st_wait();
-            }
-            // red1 / red2 alternate (gate logits of tile k, coordinate head of tile k, gate logits of tile k+1, ...): a warp is never
-            // more than one quadrant barrier ahead of the warps it shares the rows with, so one copy of each is enough
-            red1[part * 128 + r] = psum2.x + psum2.y;
-            TLW(42);
-            bar_named(BAR_QUAD + group, 128);
-            TLW(43);
-            const float gate = a.attention ? sigmoid_f(psum_parts<CF::NPARTS>(red1, r) + a.att_b) : 1.f;
-            const f2 gate2 = f2s(gate);
-            // ---- gated edge feature: segment sums -> agg, and operand atoms of GEMM 2 ----
-            {
-                float v[16];
-                if (part < nchunks) tmem_ld16_issue_f(lane_addr + part * 16, v);
-#pragma unroll 1
-                for (int ch = part; ch < 2 * na; ch += CF::NPARTS) {
-                    f2 x[8];
-                    if (ch < nchunks) {
-                        tmem_ld_wait();
+                        float pre[4];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            x[c] = mul2(make_float2(v[2 * c], v[2 * c + 1]), gate2);
-                            my_ef[r * CF::EF_STRIDE + 2 * c] = x[c].x; my_ef[r * CF::EF_STRIDE + 2 * c + 1] = x[c].y;
+                        for (int e = 0; e < 4; ++e) {
+                            pre[e] = q[ci][4 * c4 + e] + vec_s[2 * NP + c0 + e];
+                            const float v = silu_f(pre[e]);
+                            q[ci][4 * c4 + e] = v;
+                            psum = fmaf(vec_s[3 * NP + c0 + e], v, psum);
                         }
-                        if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + (ch + CF::NPARTS) * 16, v);
-                        rg.put_chunk2(it0 + na + (ch >> 1), r, half, x);
-                        bar_named(BAR_PART + part, 128);
-                        for (int nl = r >> 4; nl < nn; nl += 8) {
-                            const int col = r & 15, c = ch * 16 + col;
-                            float sum = 0.f;
-                            for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += my_ef[mm * CF::EF_STRIDE + col];
-                            if (c < H) a.agg[(size_t)(node_lo + nl) * H + c] = sum;
-                        }
-                        bar_named(BAR_PART + part, 128);
-                    } else {
-                        // chunk beyond the hidden width but inside the last atom: publish zeros so the atom completes
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) x[c] = f2s(0.f);
-                        rg.put_chunk2(it0 + na + (ch >> 1), r, half, x);
+                        if (SAVE && c0 < H)
+                            *reinterpret_cast<float4*>(a.sv_pre2 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4) = make_float4(pre[0], pre[1], pre[2], pre[3]);
                     }
                 }
             }
             fence_before_sync();
-            mbar_arrive(d1_empty);                              // accumulator 1 (and q parked in it) is consumed: GEMM 1 of the next tile may start
+            mbar_arrive(d1_empty);                              // accumulator 1 is in registers: GEMM 1 of the next tile may start
+            // red1 / red2 alternate (gate logits of tile k, coordinate head of tile k, gate logits of tile k+1, ...): a warp is never
+            // more than one quadrant barrier ahead of the warps it shares the rows with, so one copy of each is enough
+            red1[part * 128 + r] = psum;
+            TLW(42);
+            bar_named(BAR_QUAD + group, 128);
+            TLW(43);
+            const float gate = a.attention ? sigmoid_f(psum_parts<CF::NPARTS>(red1, r) + a.att_b) : 1.f;
+            // ---- gated edge feature: segment sums -> agg, and operand atoms of GEMM 2 ----
+#pragma unroll
+            for (int ci = 0; ci < CF::MYCH; ++ci) {
+                const int ch = part + CF::NPARTS * ci;
+                if (ch < nchunks) {
+                    float4 x[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        x[c] = make_float4(q[ci][4 * c] * gate, q[ci][4 * c + 1] * gate, q[ci][4 * c + 2] * gate, q[ci][4 * c + 3] * gate);
+                        if (!valid) x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        my_ef[r * CF::EF_STRIDE + 4 * c] = x[c].x; my_ef[r * CF::EF_STRIDE + 4 * c + 1] = x[c].y;
+                        my_ef[r * CF::EF_STRIDE + 4 * c + 2] = x[c].z; my_ef[r * CF::EF_STRIDE + 4 * c + 3] = x[c].w;
+                    }
+                    rg.put_chunk(2 * k + 1, ch >> 1, na, r, half, x);
+                    bar_named(BAR_PART + part, 128);
+                    for (int nl = r >> 4; nl < nn; nl += 8) {
+                        const int col = r & 15, c = ch * 16 + col;
+                        float sum = 0.f;
+                        for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += my_ef[mm * CF::EF_STRIDE + col];
+                        if (c < H) a.agg[(size_t)(node_lo + nl) * H + c] = sum;
+                    }
+                    bar_named(BAR_PART + part, 128);
+                } else if (ch < 2 * na) {
+                    // chunk beyond the hidden width but inside the last atom: publish zeros so the atom completes
+                    float4 x[4] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+                    rg.put_chunk(2 * k + 1, ch >> 1, na, r, half, x);
+                }
+            }
             // ---- GEMM 1 operand of the next tile (its MMAs overlap epilogue 2 below) ----
             TLW(50);
             if (tile + (int)gridDim.x < g.n_tiles) build1(k + 1, tile + gridDim.x);
@@ -339,31 +322,25 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
             mbar_wait(d2_full, k & 1);
             TLW(61);
             fence_after_sync();
-            f2 phi2 = f2s(0.f);
-            {
-                float v[16];
-                if (part < nchunks) tmem_ld16_issue_f(lane_addr + CF::D2_COL + part * 16, v);
+            float phi_part = 0.f;
 #pragma unroll 1
-                for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
-                    tmem_ld_wait();
-                    float w[16];
+            for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
+                float v[16];
+                tmem_ld16(lane_addr + CF::D2_COL + ch * 16, v);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) w[i] = v[i];
-                    if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + CF::D2_COL + (ch + CF::NPARTS) * 16, v);   // next chunk in flight
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const int c0 = ch * 16 + 4 * c4;
+                    float d3[4];
 #pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {
-                        const int c0 = ch * 16 + 4 * c4;
-                        const float4 bc = *reinterpret_cast<const float4*>(vec_s + 4 * NP + c0);
-                        const float4 wl = *reinterpret_cast<const float4*>(vec_s + 5 * NP + c0);
-                        f2 sa, sb, da, db;
-                        silu_both2(add2(make_float2(w[4 * c4], w[4 * c4 + 1]), lo2(bc)), sa, da);
-                        silu_both2(add2(make_float2(w[4 * c4 + 2], w[4 * c4 + 3]), hi2(bc)), sb, db);
-                        phi2 = fma2(lo2(wl), sa, phi2); phi2 = fma2(hi2(wl), sb, phi2);
-                        if (SAVE && c0 < H) *reinterpret_cast<float4*>(a.sv_d3 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4) = cat2(da, db);
+                    for (int e = 0; e < 4; ++e) {
+                        float s3;
+                        silu_both(v[4 * c4 + e] + vec_s[4 * NP + c0 + e], s3, d3[e]);
+                        phi_part = fmaf(vec_s[5 * NP + c0 + e], s3, phi_part);
                     }
+                    if (SAVE && c0 < H)
+                        *reinterpret_cast<float4*>(a.sv_d3 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4) = make_float4(d3[0], d3[1], d3[2], d3[3]);
                 }
             }
-            const float phi_part = phi2.x + phi2.y;
             fence_before_sync();
             mbar_arrive(d2_empty);
             red2[part * 128 + r] = phi_part;
@@ -399,7 +376,11 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
 // ==================================================================================================================
 // backward (input gradient only)
 // ==================================================================================================================
-// Warps: 0 = weight TMA, 1 = MMA issue, 2..17 = workers, 18 = saved-activation TMA, 19 = edge geometry of the next tile.
+// Warps: 0 = weight TMA, 1 = MMA issue, 2..17 = workers, 18 = saved-activation TMA, 19 = edge geometry of the next tiles.
+// Worker schedule, software-pipelined over the CTA's tiles (same idea as the forward kernel):
+//     build1(0);  for k: epilogue1(k), build2(k) [operand of GEMM 2(k)], build1(k+1) [operand of GEMM 1(k+1)], epilogue2(k)
+// GEMM 1 of tile k+1 runs while the workers are in epilogue 2 of tile k; accumulator 1 (which also parks g_ef between epilogue 1
+// and build2) is released after build2(k), accumulator 2 after epilogue2(k).
 template <int NP>
 struct TcBwdCfg : TcPredCfg<NP> {
     using B = TcPredCfg<NP>;
@@ -407,36 +388,67 @@ struct TcBwdCfg : TcPredCfg<NP> {
     static constexpr int THREADS = B::THREADS + 64;
     static constexpr int GEO_NF = 8;                                       // local row node, g_phi, d (3), g_u (3)
     static constexpr int GEO_WORDS = geo_words(GEO_NF);
-    static constexpr int SCRATCH = 6 * NP * 4 + 2 * B::NPARTS * 128 * 4 + B::SV_SLOTS * B::SV_SLOT_BYTES + 2 * GEO_WORDS * 4 + 64;
+    static constexpr int SV_SLOTS = 6;                                     // saved-activation ring: 6 x 8 KB
+    static constexpr int STG_WARP_FLOATS = 32 * 8;                         // per-warp transpose block of epilogue 2: 32 rows x 8 columns
+    static constexpr int SCRATCH = 6 * NP * 4 + 2 * B::NPARTS * 128 * 4 + SV_SLOTS * B::SV_SLOT_BYTES + (B::NWORK / 32) * STG_WARP_FLOATS * 4 +
+                                   2 * GEO_WORDS * 4 + 64;
     static constexpr int SMEM = B::R::BYTES + 1024 + B::BAR_BYTES + SCRATCH;
     static_assert(NP > 208 || SMEM <= 232448, "shared memory budget (backward)");
 };
+
+template <int SLOTS>
+__device__ __forceinline__ const float4* svq_acquire(const SvRing& sv, uint32_t q, int r) {
+    const uint32_t s = q % SLOTS, rr = q / SLOTS;
+#ifdef GB_DEBUG_HANG
+    for (long long spin = 0; sv.round[s] != rr; ++spin) {
+        if (spin > 3000000) {
+            volatile int* hb = gb_hang_buf;
+            if (hb && (threadIdx.x & 31) == 0 && blockIdx.x < 24) {
+                const int i = atomicAdd((int*)hb, 1);
+                if (i < 1000) { hb[4 + 4 * i] = blockIdx.x; hb[5 + 4 * i] = threadIdx.x; hb[6 + 4 * i] = 0x1000000 + (int)q; hb[7 + 4 * i] = (int)sv.round[s]; }
+                __threadfence_system();
+            }
+            for (int w = 0; w < 3000000; ++w) __nanosleep(1000);
+            __trap();
+        }
+    }
+#else
+    while (sv.round[s] != rr) { }
+#endif
+    mbar_wait(&sv.full[s], rr & 1);
+    return reinterpret_cast<const float4*>(sv.buf + s * 8192) + r;
+}
+template <int SLOTS>
+__device__ __forceinline__ void svq_release(const SvRing& sv, uint32_t q) { mbar_arrive(&sv.empty[q % SLOTS]); }
 
 template <int NP>
 __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_kernel(PredEdgeArgs a, const float* __restrict__ wcimg_nt,
                                                                    const float* __restrict__ w2img_nt, int H) {
     using CF = TcBwdCfg<NP>;
+    constexpr int SVS = CF::SV_SLOTS;
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment by pointer arithmetic on the __shared__ array: the compiler keeps the address space (LDS / STS
     // instead of generic LD / ST for every staging and operand access)
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::R::BYTES);
     Rings<NP> rg; rg.carve(base, bars);
-    uint64_t* d1_full = bars + CF::R::NBARS; uint64_t* d2_full = d1_full + 1; uint64_t* d_empty = d2_full + 1;
-    uint64_t* sv_full = d_empty + 1; uint64_t* sv_empty = sv_full + CF::SV_SLOTS;
-    uint64_t* geo_full = sv_empty + CF::SV_SLOTS; uint64_t* geo_empty = geo_full + 2;
+    uint64_t* d1_full = bars + CF::R::NBARS; uint64_t* d2_full = d1_full + 1; uint64_t* d1_empty = d2_full + 1; uint64_t* d2_empty = d1_empty + 1;
+    uint64_t* sv_full = d2_empty + 1; uint64_t* sv_empty = sv_full + SVS;
+    uint64_t* geo_full = sv_empty + SVS; uint64_t* geo_empty = geo_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(geo_empty + 2);
+    volatile uint32_t* sv_round = reinterpret_cast<volatile uint32_t*>(base + CF::R::BYTES + 384);     // [SV_SLOTS], inside the barrier block
     float* vec_s = reinterpret_cast<float*>(base + CF::R::BYTES + CF::BAR_BYTES);     // [6][NP]: w_r, w_a, -, att_w, -, wc_last
     float* red_s = vec_s + 6 * NP;                                                       // [2][NPARTS][128]
-    unsigned char* sv_buf = reinterpret_cast<unsigned char*>(red_s + 2 * CF::NPARTS * 128);   // saved-activation ring (8 x 8 KB)
-    int* geo_s = reinterpret_cast<int*>(sv_buf + CF::SV_SLOTS * CF::SV_SLOT_BYTES);      // [2][GEO_WORDS]
-    const SvRing sv{sv_buf, sv_full, sv_empty};
+    unsigned char* sv_buf = reinterpret_cast<unsigned char*>(red_s + 2 * CF::NPARTS * 128);   // saved-activation ring
+    float* stg_s = reinterpret_cast<float*>(sv_buf + SVS * CF::SV_SLOT_BYTES);           // [16 warps][32][8]
+    int* geo_s = reinterpret_cast<int*>(stg_s + (CF::NWORK / 32) * CF::STG_WARP_FLOATS);  // [2][GEO_WORDS]
+    const SvRing sv{sv_buf, sv_full, sv_empty, sv_round};
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         rg.init(256);
-        mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d_empty, CF::NWORK);
-        for (int s = 0; s < CF::SV_SLOTS; ++s) { mbar_init(&sv_full[s], 1); mbar_init(&sv_empty[s], 128); }
+        mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d1_empty, CF::NWORK); mbar_init(d2_empty, CF::NWORK);
+        for (int s = 0; s < SVS; ++s) { mbar_init(&sv_full[s], 1); mbar_init(&sv_empty[s], 128); sv_round[s] = 0xffffffffu; }
         for (int b = 0; b < 2; ++b) { mbar_init(&geo_full[b], 1); mbar_init(&geo_empty[b], CF::NWORK); }
         mbar_fence_init();
     }
@@ -448,7 +460,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
     }
     // the last 16-column chunk of a tile is only partly filled by the producer (H / 4 planes): the remaining planes are read as
     // they are and multiplied by zero-padded weights, so they must hold finite values from the start
-    for (int i = tid; i < CF::SV_SLOTS * CF::SV_SLOT_BYTES / 16; i += blockDim.x) reinterpret_cast<float4*>(sv_buf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < SVS * CF::SV_SLOT_BYTES / 16; i += blockDim.x) reinterpret_cast<float4*>(sv_buf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
@@ -456,49 +468,65 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
     const uint32_t tmem_base = *tmem_slot;
     const Graph& g = a.g;
     const int na = (H + ATOM_K - 1) / ATOM_K;
+    const int my_tiles = (int)blockIdx.x < g.n_tiles ? (g.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (lane == 0 && my_tiles > 0) {
             uint32_t wq = 0;
-            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) { rg.tma_gemm(wq, na, wcimg_nt); rg.tma_gemm(wq, na, w2img_nt); }
+            rg.tma_gemm(wq, na, wcimg_nt);
+            for (int k = 0; k < my_tiles; ++k) { rg.tma_gemm(wq, na, w2img_nt); if (k + 1 < my_tiles) rg.tma_gemm(wq, na, wcimg_nt); }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            uint32_t it = 0, wq = 0, tcnt = 0;
-            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
-                if (tcnt > 0) mbar_wait(d_empty, (tcnt - 1) & 1);
+        if (lane == 0 && my_tiles > 0) {
+            uint32_t gq = 0, wq = 0;
+            TLP(2, 1);
+            rg.mma_gemm(gq, wq, na, H, tmem_base);                       // GEMM 1 of the first tile
+            mma_commit(d1_full);
+            for (int k = 0; k < my_tiles; ++k) {
+                if (k > 0) mbar_wait(d2_empty, (k - 1) & 1);
                 fence_after_sync();
-                TLP(2, 1);
-                rg.mma_gemm(it, wq, na, H, tmem_base);
-                mma_commit(d1_full);
-                TLP(2, 2);
-                rg.mma_gemm(it, wq, na, H, tmem_base + CF::D2_COL);
+                TLP(2, 3);
+                rg.mma_gemm(gq, wq, na, H, tmem_base + CF::D2_COL);      // GEMM 2 of tile k
                 mma_commit(d2_full);
                 TLP(2, 4);
-            }
-        }
-    } else if (warp == CF::SV_WARP) {
-        // saved-activation producer: per tile the chunks of d3 (GEMM-1 operand), pre2 (epilogue 1), pre2 again (GEMM-2
-        // operand) and d1 (epilogue 2), in the order the worker parts consume them
-        if (lane == 0) {
-            const int nchunks = (H + 15) / 16, planes = H / 4;
-            uint32_t q = 0;
-            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-#pragma unroll 1
-                for (int ph = 0; ph < 4; ++ph) {
-                    const float* src = (ph == 0 ? a.sv_d3 : (ph == 3 ? a.sv_d1 : a.sv_pre2)) + (size_t)tile * planes * 512;
-                    for (int ch = 0; ch < nchunks; ++ch, ++q) {
-                        const uint32_t s = q & 7, rr = q >> 3;
-                        const uint32_t bytes = (uint32_t)min(4, planes - 4 * ch) * 2048u;
-                        if (rr > 0) mbar_wait(&sv_empty[s], (rr - 1) & 1);
-                        mbar_arrive_expect_tx(&sv_full[s], bytes);
-                        bulk_g2s(sv.buf + s * CF::SV_SLOT_BYTES, src + (size_t)ch * 2048, bytes, &sv_full[s]);
-                    }
+                if (k + 1 < my_tiles) {
+                    mbar_wait(d1_empty, k & 1);
+                    fence_after_sync();
+                    TLP(2, 1);
+                    rg.mma_gemm(gq, wq, na, H, tmem_base);               // GEMM 1 of tile k+1
+                    mma_commit(d1_full);
+                    TLP(2, 2);
                 }
             }
         }
+    } else if (warp == CF::SV_WARP) {
+        // saved-activation producer, in the order the worker parts consume the 16-column chunks:
+        //   d3(0);  for k: pre2(k) [epilogue 1], pre2(k) [GEMM-2 operand], d3(k+1) [GEMM-1 operand of the next tile], d1(k) [epilogue 2]
+        if (lane == 0 && my_tiles > 0) {
+            const int nchunks = (H + 15) / 16, planes = H / 4;
+            uint32_t q = 0;
+            auto stream = [&](const float* src) {
+                for (int ch = 0; ch < nchunks; ++ch, ++q) {
+                    const uint32_t s = q % SVS, rr = q / SVS;
+                    const uint32_t bytes = (uint32_t)min(4, planes - 4 * ch) * 2048u;
+                    if (rr > 0) mbar_wait(&sv_empty[s], (rr - 1) & 1);
+                    sv_round[s] = rr;                        // full[s] is in phase rr from here on (see SvRing)
+                    mbar_arrive_expect_tx(&sv_full[s], bytes);
+                    bulk_g2s(sv.buf + s * CF::SV_SLOT_BYTES, src + (size_t)ch * 2048, bytes, &sv_full[s]);
+                }
+            };
+            const size_t tstride = (size_t)planes * 512;
+            stream(a.sv_d3 + (size_t)blockIdx.x * tstride);
+            int tile = blockIdx.x;
+            for (int k = 0; k < my_tiles; ++k, tile += gridDim.x) {
+                stream(a.sv_pre2 + (size_t)tile * tstride);
+                stream(a.sv_pre2 + (size_t)tile * tstride);
+                if (k + 1 < my_tiles) stream(a.sv_d3 + (size_t)(tile + gridDim.x) * tstride);
+                stream(a.sv_d1 + (size_t)tile * tstride);
+            }
+        }
     } else if (warp == CF::GEO_WARP) {
-        // ---- geometry warp: the NEXT tile's header, row-segment table and per-edge backward geometry (its dependent load chain
+        // ---- geometry warp: header and per-edge backward geometry of the coming tiles (its dependent load chain
         //      tile_info -> erow/ecol -> x / g_xout / tau used to stall all worker warps at every tile start) ----
         auto geo_emit = [&](const TileMeta& m, uint32_t tc) {
             const uint32_t gb_ = tc & 1, use = tc >> 1;
@@ -506,7 +534,6 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
             int* gi = geo_s + gb_ * CF::GEO_WORDS;
             float* gf = reinterpret_cast<float*>(gi);
             if (lane == 0) { gi[0] = m.node_lo; gi[1] = m.nn; gi[2] = m.e_lo; gi[3] = m.ne; }
-            for (int i = lane; i <= m.nn; i += 32) gi[4 + i] = __ldg(g.rowptr + m.node_lo + i) - m.e_lo;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int r = lane + 32 * q;
@@ -545,27 +572,21 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
         const int nchunks = (H + 15) / 16;
         const int tlr = (lane == 0 && group == 0) ? (part == 0 ? 0 : (part == 3 ? 1 : -1)) : -1;
         (void)tlr;
-        uint32_t tcnt = 0;
-        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++tcnt) {
-            const uint32_t q0 = tcnt * 4 * nchunks;                 // first saved-activation chunk of this tile
-            const uint32_t gb_ = tcnt & 1;
+        float* stg = stg_s + (warp - 2) * CF::STG_WARP_FLOATS;
+        uint32_t sq = 0;                                             // first saved-activation chunk of the current stream
+        // ---- GEMM 1 operand of the CTA's k-th tile: g_pre3 = g_phi * w_c * SiLU'(pre3) ----
+        // (no per-element bounds checks: w_c is zero-padded beyond H, rows beyond the tile's edges have g_phi = 0)
+        auto build1 = [&](uint32_t k) {
+            const uint32_t gb_ = k & 1;
             TLW(10);
-            mbar_wait(&geo_full[gb_], (tcnt >> 1) & 1);
+            mbar_wait(&geo_full[gb_], (k >> 1) & 1);
             TLW(11);
-            const int* gi = geo_s + gb_ * CF::GEO_WORDS;
-            const float* gf = reinterpret_cast<const float*>(gi);
-            const int node_lo = gi[0], nn = gi[1], e_lo = gi[2], ne = gi[3];
-            const bool valid = r < ne;
-            const float gphi = gf[GEO_HDR + 128 + r];
-            const uint32_t it0 = tcnt * 2 * na;
-            // ---- GEMM 1 operand: g_pre3 = g_phi * w_c * SiLU'(pre3) ----
-            // (no per-element bounds checks: w_c is zero-padded beyond H, rows beyond the tile's edges have g_phi = 0)
-            const f2 gphi2 = f2s(gphi);
+            const f2 gphi2 = f2s(reinterpret_cast<const float*>(geo_s + gb_ * CF::GEO_WORDS)[GEO_HDR + 128 + r]);
             for (int j = part >> 1; j < na; j += CF::NPARTS / 2) {
                 f2 x[8];
                 const int ch = 2 * j + half;
                 if (ch < nchunks) {
-                    const float4* d3p = sv_acquire(sv, q0 + ch, r);
+                    const float4* d3p = svq_acquire<SVS>(sv, sq + ch, r);
                     TLW(100 + j);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -574,23 +595,32 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                         x[2 * c] = mul2(mul2(gphi2, lo2(wl)), lo2(d3));
                         x[2 * c + 1] = mul2(mul2(gphi2, hi2(wl)), hi2(d3));
                     }
-                    sv_release(sv, q0 + ch);
+                    svq_release<SVS>(sv, sq + ch);
                 } else {
 #pragma unroll
                     for (int c = 0; c < 8; ++c) x[c] = f2s(0.f);
                 }
                 TLW(110 + j);
-                rg.put_chunk2(it0 + j, r, half, x);
+                rg.put_chunk2(2 * k, j, na, r, half, x);
                 TLW(120 + j);
             }
+            sq += nchunks;
+        };
+        if (my_tiles > 0) build1(0);
+        int tile = blockIdx.x;
+        for (uint32_t k = 0; k < (uint32_t)my_tiles; ++k, tile += gridDim.x) {
+            const uint32_t gb_ = k & 1;
+            const int* gi = geo_s + gb_ * CF::GEO_WORDS;
+            const float* gf = reinterpret_cast<const float*>(gi);
+            const int node_lo = gi[0], nn = gi[1], e_lo = gi[2], ne = gi[3];
+            const bool valid = r < ne;
             // ---- epilogue 1: g_ef = coordinate branch + aggregation branch; attention backward ----
             TLW(40);
-            mbar_wait(d1_full, tcnt & 1);
+            mbar_wait(d1_full, k & 1);
             TLW(41);
             fence_after_sync();
-            // the tile's rows of g_agg (one per row node, shared by its ~9 edges) are copied once, coalesced, into the A ring
-            // (idle between GEMM 1 and the first operand store of GEMM 2) instead of being gathered from L2
-            // with four dependent 16-byte loads per chunk and thread
+            // the tile's rows of g_agg (one per row node, shared by its ~9 edges) are copied once, coalesced, into the A ring: every
+            // operand atom stored so far (GEMM 1 of this tile was the last) has been consumed, and nothing is stored before build2
             constexpr int GA_ROWS = CF::A_STAGE / (NP * 4);                // rows per ring stage (A hi + A lo)
             const bool ga_staged = nn <= 2 * GA_ROWS;
             if (ga_staged) {
@@ -600,10 +630,10 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                     float* dst = reinterpret_cast<float*>(rg.a_base + (nl / GA_ROWS) * CF::A_STAGE) + (nl % GA_ROWS) * NP + 4 * k4;
                     *reinterpret_cast<float4*>(dst) = __ldg(reinterpret_cast<const float4*>(a.g_agg + (size_t)(node_lo + nl) * a.ld_gagg + 4 * k4));
                 }
-                TLW(42);
-                bar_named(BAR_WORKERS, CF::NWORK);
-                TLW(43);
             }
+            TLW(42);
+            bar_named(BAR_WORKERS, CF::NWORK);                     // staged rows visible; also orders red_s against the previous tile
+            TLW(43);
             f2 plog2 = f2s(0.f), pdot2 = f2s(0.f);
             const int rloc = gi[GEO_HDR + r];
             const float* ga_row = ga_staged ? reinterpret_cast<const float*>(rg.a_base + (rloc / GA_ROWS) * CF::A_STAGE) + (rloc % GA_ROWS) * NP
@@ -616,9 +646,9 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                 if (part < nchunks) tmem_ld16_issue_f(lane_addr + part * 16, v);
 #pragma unroll 1
                 for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
-                    tmem_ld_wait();
+                    tmem_ld_wait16(v);
                     TLW(200 + ch);
-                    const float4* p2p = sv_acquire(sv, q0 + nchunks + ch, r);
+                    const float4* p2p = svq_acquire<SVS>(sv, sq + ch, r);
                     TLW(220 + ch);
                     float w[16];
 #pragma unroll
@@ -635,12 +665,13 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                         plog2 = fma2(lo2(wq), qa, plog2); plog2 = fma2(hi2(wq), qb, plog2);
                         pdot2 = fma2(ga_, qa, pdot2); pdot2 = fma2(gb2, qb, pdot2);
                     }
-                    sv_release(sv, q0 + nchunks + ch);
+                    svq_release<SVS>(sv, sq + ch);
                     if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + (ch + CF::NPARTS) * 16, v);
                     tmem_st16(lane_addr + ch * 16, w);
                 }
                 tmem_st_wait();
             }
+            sq += nchunks;
             red_s[part * 128 + r] = plog2.x + plog2.y;
             red_s[CF::NPARTS * 128 + part * 128 + r] = pdot2.x + pdot2.y;
             TLW(44);
@@ -660,8 +691,8 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                 for (int ch = part; ch < 2 * na; ch += CF::NPARTS) {
                     f2 x[8];
                     if (ch < nchunks) {
-                        tmem_ld_wait();
-                        const float4* p2p = sv_acquire(sv, q0 + 2 * nchunks + ch, r);
+                        tmem_ld_wait16(v);
+                        const float4* p2p = svq_acquire<SVS>(sv, sq + ch, r);
                         TLW(300 + ch);
 #pragma unroll
                         for (int c4 = 0; c4 < 4; ++c4) {
@@ -673,72 +704,84 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                             x[2 * c4] = mul2(ta, dsilu2(lo2(p2)));
                             x[2 * c4 + 1] = mul2(tb, dsilu2(hi2(p2)));
                         }
-                        sv_release(sv, q0 + 2 * nchunks + ch);
+                        svq_release<SVS>(sv, sq + ch);
                         if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + (ch + CF::NPARTS) * 16, v);
                     } else {
 #pragma unroll
                         for (int c = 0; c < 8; ++c) x[c] = f2s(0.f);
                     }
                     TLW(320 + ch);
-                    rg.put_chunk2(it0 + na + (ch >> 1), r, half, x);
+                    rg.put_chunk2(2 * k + 1, ch >> 1, na, r, half, x);
                     TLW(340 + ch);
                 }
             }
+            sq += nchunks;
+            fence_before_sync();
+            mbar_arrive(d1_empty);                                 // accumulator 1 (and g_ef parked in it) consumed: GEMM 1 of tile k+1 may start
+            // ---- GEMM 1 operand of the next tile (its MMAs overlap epilogue 2 below) ----
+            TLW(50);
+            if (k + 1 < (uint32_t)my_tiles) build1(k + 1);
             // ---- epilogue 2: g_pre1 = g_s1 * SiLU'(pre1) -> HBM (row-major per edge); radial / attr dots ----
             //      the row sums (g_Pa), column sums (g_Pb) and the coordinate gradient are reduced afterwards by the
             //      node-parallel pred_bwd_reduce_kernel: fixed summation order, no atomics, no per-chunk barriers here
             TLW(60);
-            mbar_wait(d2_full, tcnt & 1);
+            mbar_wait(d2_full, k & 1);
             TLW(61);
             fence_after_sync();
             f2 pr2 = f2s(0.f), pa2 = f2s(0.f);
             // g_pre1 rows are written through a per-warp transpose block: thread = row is what TMEM gives, but 16 bytes of 32
-            // different rows per store instruction cost 32 L1 tag lookups; transposed, one instruction covers 8 rows x 64 bytes.
-            // The block (32 rows x 16 floats, 16-byte chunk c of row l at position c ^ ((l >> 1) & 3): conflict-free both ways)
-            // lives in the A ring, which is idle between the last MMA of GEMM 2 (d2_full) and the next tile's first operand
-            // store (after the barrier that ends the tile).
-            float* stg = reinterpret_cast<float*>(rg.a_base + ((warp - 2) >> 3) * CF::A_STAGE) + ((warp - 2) & 7) * (32 * 16);
-            const int piece = lane & 3, rsub = lane >> 2;
-            const int wsw = (lane >> 1) & 3;
-            float v[16];
-            if (part < nchunks) tmem_ld16_issue_f(lane_addr + CF::D2_COL + part * 16, v);
+            // different rows per store instruction cost 32 L1 tag lookups; transposed, one instruction covers 16 rows x 32 bytes
+            // (full sectors).  The block holds 32 rows x 8 columns (16-byte chunk c of row l at position c ^ ((l >> 2) & 1):
+            // conflict-free both ways); a 16-column chunk goes through it in two halves.
+            {
+                const int piece = lane & 1, rsub = lane >> 1;
+                const int wsw = (lane >> 2) & 1;
+                float v[16];
+                if (part < nchunks) tmem_ld16_issue_f(lane_addr + CF::D2_COL + part * 16, v);
 #pragma unroll 1
-            for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
-                tmem_ld_wait();
-                TLW(400 + ch);
-                const float4* d1p = sv_acquire(sv, q0 + 3 * nchunks + ch, r);
-                TLW(420 + ch);
+                for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
+                    tmem_ld_wait16(v);
+                    TLW(400 + ch);
+                    const float4* d1p = svq_acquire<SVS>(sv, sq + ch, r);
+                    TLW(420 + ch);
+                    f2 gp[8];
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    const int c0 = ch * 16 + 4 * c4;
-                    const float4 d1 = d1p[c4 * 128];
-                    const float4 wr = *reinterpret_cast<const float4*>(vec_s + c0);
-                    const float4 wa = *reinterpret_cast<const float4*>(vec_s + NP + c0);
-                    const f2 ga_ = mul2(make_float2(v[4 * c4], v[4 * c4 + 1]), lo2(d1)), gb2 = mul2(make_float2(v[4 * c4 + 2], v[4 * c4 + 3]), hi2(d1));
-                    pr2 = fma2(lo2(wr), ga_, pr2); pr2 = fma2(hi2(wr), gb2, pr2);
-                    pa2 = fma2(lo2(wa), ga_, pa2); pa2 = fma2(hi2(wa), gb2, pa2);
-                    *reinterpret_cast<float4*>(stg + lane * 16 + 4 * (c4 ^ wsw)) = cat2(ga_, gb2);
-                }
-                sv_release(sv, q0 + 3 * nchunks + ch);
-                if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + CF::D2_COL + (ch + CF::NPARTS) * 16, v);   // next chunk in flight during the stores
-                __syncwarp();
-                const int c = ch * 16 + 4 * piece;
-                if (c < H) {
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const int c0 = ch * 16 + 4 * c4;
+                        const float4 d1 = d1p[c4 * 128];
+                        const float4 wr = *reinterpret_cast<const float4*>(vec_s + c0);
+                        const float4 wa = *reinterpret_cast<const float4*>(vec_s + NP + c0);
+                        gp[2 * c4] = mul2(make_float2(v[4 * c4], v[4 * c4 + 1]), lo2(d1));
+                        gp[2 * c4 + 1] = mul2(make_float2(v[4 * c4 + 2], v[4 * c4 + 3]), hi2(d1));
+                        pr2 = fma2(lo2(wr), gp[2 * c4], pr2); pr2 = fma2(hi2(wr), gp[2 * c4 + 1], pr2);
+                        pa2 = fma2(lo2(wa), gp[2 * c4], pa2); pa2 = fma2(hi2(wa), gp[2 * c4 + 1], pa2);
+                    }
+                    svq_release<SVS>(sv, sq + ch);
+                    if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + CF::D2_COL + (ch + CF::NPARTS) * 16, v);   // next chunk in flight during the stores
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int rw = rsub + 8 * i, rl = group * 32 + rw;
-                        if (rl < ne) *reinterpret_cast<float4*>(a.g_pre1 + (size_t)(e_lo + rl) * H + c) = *reinterpret_cast<const float4*>(stg + rw * 16 + 4 * (piece ^ ((rw >> 1) & 3)));
+                    for (int hh = 0; hh < 2; ++hh) {
+                        *reinterpret_cast<float4*>(stg + lane * 8 + 4 * (0 ^ wsw)) = cat2(gp[4 * hh], gp[4 * hh + 1]);
+                        *reinterpret_cast<float4*>(stg + lane * 8 + 4 * (1 ^ wsw)) = cat2(gp[4 * hh + 2], gp[4 * hh + 3]);
+                        __syncwarp();
+                        const int c = ch * 16 + 8 * hh + 4 * piece;
+                        if (c < H) {
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                const int rw = rsub + 16 * i, rl = group * 32 + rw;
+                                if (rl < ne) *reinterpret_cast<float4*>(a.g_pre1 + (size_t)(e_lo + rl) * H + c) = *reinterpret_cast<const float4*>(stg + rw * 8 + 4 * (piece ^ ((rw >> 2) & 1)));
+                            }
+                        }
+                        __syncwarp();
                     }
                 }
-                __syncwarp();
             }
-            const float pr = pr2.x + pr2.y, pa = pa2.x + pa2.y;
+            sq += nchunks;
             fence_before_sync();
-            mbar_arrive(d_empty);
-            red_s[part * 128 + r] = pr;
-            red_s[CF::NPARTS * 128 + part * 128 + r] = pa;
+            mbar_arrive(d2_empty);
+            red_s[part * 128 + r] = pr2.x + pr2.y;
+            red_s[CF::NPARTS * 128 + part * 128 + r] = pa2.x + pa2.y;
             TLW(62);
-            bar_named(BAR_WORKERS, CF::NWORK);                     // also: the transpose blocks in the A ring are free again
+            bar_named(BAR_WORKERS, CF::NWORK);
             TLW(63);
             if (part == 0 && valid) {
                 const float g_r = psum_parts<CF::NPARTS>(red_s, r);
@@ -756,14 +799,18 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
             }
             mbar_arrive(&geo_empty[gb_]);
             TLW(70);
-            // red_s: the next write (epilogue 1 of the next tile) needs d1_full of that tile, i.e. operand atoms from every worker
-            // thread, which each thread stores after it has read red_s here
+            // red_s: its next writers (epilogue 1 of tile k+1) first pass the worker barrier at the top of that epilogue, which the
+            // part-0 warps reach only after the reads above
         }
     }
     fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
+
+#ifdef GB_DEBUG_HANG
+extern "C" int gb_debug_set_hang_buf(int* dev_ptr) { return (int)cudaMemcpyToSymbol(gb_hang_buf, &dev_ptr, sizeof(dev_ptr)); }
+#endif
 
 #ifdef GB_TIMELINE
 extern "C" int gb_debug_timeline_pred(unsigned long long* out, unsigned int* n, int reset) {
