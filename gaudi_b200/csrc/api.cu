@@ -113,13 +113,14 @@ struct Packer {
     }
     // tensor-core image of ONE [Nv x Kv] block: atoms(Kv) x [hi|lo][NP][32]
     size_t tc_size(int K) const { return (size_t)((K + 31) / 32) * 2 * tc_np(net->HP) * 32; }
-    void tc_at(size_t dst, const float* w, int ld, int k_off, int n_off, int Kv, int Nv, int Kp, int transpose) {
-        if (!dry) { launch_pack_tc(net->buf + dst, w, ld, k_off, n_off, Kv, Nv, tc_np(net->HP), (Kp + 31) / 32, transpose, s); GB_LAUNCHED(1); }
+    void tc_at(size_t dst, const float* w, int ld, int k_off, int n_off, int Kv, int Nv, int Kp, int transpose, int fmt = 0) {
+        if (!dry) { launch_pack_tc(net->buf + dst, w, ld, k_off, n_off, Kv, Nv, tc_np(net->HP), (Kp + 31) / 32, transpose, s, fmt); GB_LAUNCHED(1); }
     }
     // transpose==1: forward use (k = input column, n = output row); 0: dgrad use (k = output row, n = input column)
-    size_t tc_block(const float* w, int ld, int k_off, int n_off, int Kv, int Nv, int transpose) {
+    // fmt: image format (launch_pack_tc): 0 for the node-Linear kernel, 1 (fp16 mix) / 2 (bf16 mix) for the edge kernels
+    size_t tc_block(const float* w, int ld, int k_off, int n_off, int Kv, int Nv, int transpose, int fmt = 0) {
         size_t o = take(tc_size(net->HP));
-        tc_at(o, w, ld, transpose ? k_off : k_off, n_off, Kv, Nv, net->HP, transpose ? 0 : 1);
+        tc_at(o, w, ld, transpose ? k_off : k_off, n_off, Kv, Nv, net->HP, transpose ? 0 : 1, fmt);
         return o;
     }
     size_t tc_block2(const float* w, int ld, int k0, int n0, int k1, int n1, int Kv, int Nv, int transpose) {
@@ -156,13 +157,14 @@ struct Packer {
             e.l1_nt_tc = tc_block2(w, ld, 0, 0, 0, H, H, H, 0);
         }
     }
-    void square(size_t& wt, size_t& bias, size_t* nt, const float* w, const float* b, size_t* tcw = nullptr, size_t* tcnt = nullptr) {
+    // edge = true: the image feeds an edge kernel (forward: activations -> fp16 mix; dgrad: gradients -> bf16 mix)
+    void square(size_t& wt, size_t& bias, size_t* nt, const float* w, const float* b, size_t* tcw = nullptr, size_t* tcnt = nullptr, bool edge = false) {
         const int H = net->H, HP = net->HP;
         wt = block(w, H, 0, 0, H, H, HP, 1);
         bias = vec(b, H, HP);
         if (nt) *nt = block(w, H, 0, 0, H, H, HP, 0);
-        if (tcw) *tcw = tc_block(w, H, 0, 0, H, H, 1);
-        if (tcnt) *tcnt = tc_block(w, H, 0, 0, H, H, 0);
+        if (tcw) *tcw = tc_block(w, H, 0, 0, H, H, 1, edge ? 1 : 0);
+        if (tcnt) *tcnt = tc_block(w, H, 0, 0, H, H, 0, edge ? 2 : 0);
     }
     void node_mlp(NodeMlpW& n, const float* w1, const float* b1, const float* w2, const float* b2, bool want_nt) {
         const int H = net->H, HP = net->HP;
@@ -224,7 +226,7 @@ static int build_net(gb_net* net, const float* const* P, int n_params, cudaStrea
                 for (int q = 0; q < net->n_sub; ++q) {
                     DenGcl& G = net->gcl[(size_t)b * net->n_sub + q];
                     pk.edge_l1(G.e, P[i], P[i + 1], false);
-                    pk.square(G.e.l2_wt, G.e.l2_b, nullptr, P[i + 2], P[i + 3], &G.e.l2_tc);
+                    pk.square(G.e.l2_wt, G.e.l2_b, nullptr, P[i + 2], P[i + 3], &G.e.l2_tc, nullptr, true);
                     pk.node_mlp(G.n, P[i + 4], P[i + 5], P[i + 6], P[i + 7], false);
                     i += 8;
                     if (net->attention) {
@@ -235,7 +237,7 @@ static int build_net(gb_net* net, const float* const* P, int n_params, cudaStrea
                 }
                 DenEquiv& E = net->eq[b];
                 pk.edge_l1(E.c, P[i], P[i + 1], false);
-                pk.square(E.c.l2_wt, E.c.l2_b, nullptr, P[i + 2], P[i + 3], &E.c.l2_tc);
+                pk.square(E.c.l2_wt, E.c.l2_b, nullptr, P[i + 2], P[i + 3], &E.c.l2_tc, nullptr, true);
                 E.last_w = pk.vec(P[i + 4], H, net->HP);
                 i += 5;
             }
@@ -244,9 +246,9 @@ static int build_net(gb_net* net, const float* const* P, int n_params, cudaStrea
             for (int l = 0; l < net->L; ++l) {
                 PredLayer& Lr = net->pl[l];
                 pk.edge_l1(Lr.e, P[i], P[i + 1], true);
-                pk.square(Lr.e.l2_wt, Lr.e.l2_b, &Lr.e.l2_nt, P[i + 2], P[i + 3], &Lr.e.l2_tc, &Lr.e.l2_nt_tc);
+                pk.square(Lr.e.l2_wt, Lr.e.l2_b, &Lr.e.l2_nt, P[i + 2], P[i + 3], &Lr.e.l2_tc, &Lr.e.l2_nt_tc, true);
                 pk.node_mlp(Lr.n, P[i + 4], P[i + 5], P[i + 6], P[i + 7], true);
-                pk.square(Lr.c_wt, Lr.c_b, &Lr.c_nt, P[i + 8], P[i + 9], &Lr.c_tc, &Lr.c_nt_tc);
+                pk.square(Lr.c_wt, Lr.c_b, &Lr.c_nt, P[i + 8], P[i + 9], &Lr.c_tc, &Lr.c_nt_tc, true);
                 Lr.c_last = pk.vec(P[i + 10], H, net->HP);
                 i += 11;
                 if (net->attention) {

@@ -59,7 +59,8 @@ int tc_np(int H);
 void launch_wgrad_tc(int K, int M, int N, const float* G, int ldg, const float* X, int ldx, float* C, int ldc, int accumulate,
                      float* scratch, float* colsum, cudaStream_t s);
 size_t wgrad_tc_scratch_bytes(int M, int N);
-void launch_pack_tc(float* dst, const float* src, int ld, int k_off, int n_off, int Kv, int Nv, int NP, int atoms, int transpose, cudaStream_t s);
+// fmt: 0 = [hi | lo] fp32 images (three TF32 MMAs: node Linear, training); 1 / 2 = [hi fp32 | hi+lo as fp16 / bf16] (edge kernels)
+void launch_pack_tc(float* dst, const float* src, int ld, int k_off, int n_off, int Kv, int Nv, int NP, int atoms, int transpose, cudaStream_t s, int fmt = 0);
 
 // tiny-K input embedding of both networks:  h0 = W [feat*mask , t] + b ;  x = z[:, :3]*mask
 struct EmbedInArgs {

@@ -9,11 +9,23 @@
 // Accuracy: error-compensated 3xTF32.  x = hi + lo with hi = x & 0xffffe000 (exactly a TF32 value) and lo = x - hi;
 //   a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi   (dropped term ~2^-22 relative), accumulated in FP32 in TMEM.
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "kernels.h"
 
+// Edge kernels (round 2): the two correction terms run as ONE 16-bit MMA per K step.  With a = a_hi + a_lo, w = w_hi + w_lo
+// (hi = TF32 part):   a*w ~= a_hi*w_hi                      kind::tf32, K = 8
+//                          + [a_lo | a_hi] . [w_hi | w_lo]   kind::f16,  K = 16 (the 8 a_lo*w_hi and the 8 a_hi*w_lo products)
+// where the operands of the second MMA are rounded to fp16 (activations, forward) or bf16 (gradients: fp16 has no range for
+// them).  Both terms are 2^-11 relative to the main one, so an 11- or 8-bit mantissa keeps the product error at ~2^-22 / 2^-19:
+// against an fp64 GEMM (K = 196) the rms error is 5.7e-7 (fp16) / 1.7e-6 (bf16) of the mean |y|, vs 2.2e-7 for three TF32 MMAs
+// and 3.1e-7 for a plain fp32 GEMM -- for 2/3 of the tensor-pipe time and 2/3 of the operand reads from shared memory, the two
+// resources that bound the operand-build phases of these kernels.  The images have the same size as before: per K-atom
+// [hi : rows x 32 fp32][mix : rows x 4 K-steps x (8 + 8) halfs], both 128 bytes per row with the 128-byte swizzle.
 namespace gb {
 namespace tc {
+enum MixFmt { MIX_FP16 = 0, MIX_BF16 = 1 };
 
 constexpr int ATOM_K = 32;                 // fp32 elements per 128-byte swizzle row
 constexpr int ATOM_ROW_BYTES = 128;
@@ -36,6 +48,25 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr) {
 // 32-bit instruction descriptor (cute::UMMA::InstrDescriptor): TF32 x TF32 -> F32, K-major A and B, M = 128.
 __host__ __device__ constexpr uint32_t instr_desc_tf32(int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// 32-bit instruction descriptor of the 16-bit MMA: F16 x F16 or BF16 x BF16 -> F32, K-major A and B, M = 128
+__host__ __device__ constexpr uint32_t instr_desc_mix(int N, int fmt) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+template <int FMT>
+__device__ __forceinline__ uint32_t pack16(float a, float b) {      // two floats -> one 32-bit word of two fp16 / bf16 (a in the low half)
+    if (FMT == MIX_BF16) { const __nv_bfloat162 v = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&v); }
+    const __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&v);
 }
 
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -156,6 +187,20 @@ __device__ __forceinline__ void store_split2(unsigned char* atom_hi, unsigned ch
     *reinterpret_cast<float4*>(atom_lo + off) = cat2(la, lb);
 }
 
+// One K step (8 consecutive k = the 16-byte chunks c0, c0 + 1 of row r; c0 even) of an activation atom in the hi + mix format:
+// hi image <- TF32 parts as fp32; mix image chunk c0 <- the 8 residuals, chunk c0 + 1 <- the 8 TF32 parts, both as 16-bit values.
+template <int FMT>
+__device__ __forceinline__ void store_kstep_mix(unsigned char* atom_hi, unsigned char* atom_mix, int r, int c0, f2 a, f2 b, f2 c, f2 d) {
+    const f2 ha = make_float2(tf32_hi(a.x), tf32_hi(a.y)), hb = make_float2(tf32_hi(b.x), tf32_hi(b.y));
+    const f2 hc = make_float2(tf32_hi(c.x), tf32_hi(c.y)), hd = make_float2(tf32_hi(d.x), tf32_hi(d.y));
+    const f2 la = fma2(ha, f2s(-1.f), a), lb = fma2(hb, f2s(-1.f), b), lc = fma2(hc, f2s(-1.f), c), ld = fma2(hd, f2s(-1.f), d);
+    const uint32_t o0 = swz_offset(r, c0), o1 = swz_offset(r, c0 + 1);
+    *reinterpret_cast<float4*>(atom_hi + o0) = cat2(ha, hb);
+    *reinterpret_cast<float4*>(atom_hi + o1) = cat2(hc, hd);
+    *reinterpret_cast<uint4*>(atom_mix + o0) = make_uint4(pack16<FMT>(la.x, la.y), pack16<FMT>(lb.x, lb.y), pack16<FMT>(lc.x, lc.y), pack16<FMT>(ld.x, ld.y));
+    *reinterpret_cast<uint4*>(atom_mix + o1) = make_uint4(pack16<FMT>(ha.x, ha.y), pack16<FMT>(hb.x, hb.y), pack16<FMT>(hc.x, hc.y), pack16<FMT>(hd.x, hd.y));
+}
+
 // named barriers of the worker warps: ids 1-4 = the four warps sharing a TMEM lane quadrant (one per part; they exchange
 // per-row partial sums), 5-12 = the four warps of one part (they cover the 128 rows of a chunk), 13 = all workers
 __device__ __forceinline__ void bar_named(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -169,13 +214,13 @@ constexpr int GEO_HDR = 136;
 __host__ __device__ constexpr int geo_words(int nf) { return GEO_HDR + 128 * nf; }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Operand rings of the edge kernels.  The activation (A) ring holds SA stages of [A hi | A lo] K-atoms written by the worker
-// warps; the weight (W) ring holds SW slots of ONE half-atom image each (hi or lo, NP x 128 B) streamed by the TMA warp in
-// the order the packed image stores them: hi(0), lo(0), hi(1), lo(1), ...  Per K-atom the MMA warp issues the two products
-// that read w_hi first, releases that slot, then the product that reads w_lo: three slots (instead of two stages of hi+lo)
-// keep one half-atom in flight ahead of the tensor pipe and free NP x 128 B of shared memory for the staged P rows.
+// Operand rings of the edge kernels.  The activation (A) ring holds SA stages of [A hi | A mix] K-atoms written by the worker
+// warps; the weight (W) ring holds SW slots of ONE half-atom image each (hi or mix, NP x 128 B) streamed by the TMA warp in
+// the order the packed image stores them: hi(0), mix(0), hi(1), mix(1), ...  Per K-atom the MMA warp issues the TF32 products
+// that read w_hi first, releases that slot, then the 16-bit products that read w_mix: three slots (instead of two stages of
+// hi + mix) keep one half-atom in flight ahead of the tensor pipe and free NP x 128 B of shared memory for the staged P rows.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int NP>
+template <int NP, int FMT>
 struct Rings {
     static constexpr int SA = 2, SW = 3;
     static constexpr int A_BYTES = 128 * ATOM_ROW_BYTES;     // one hi or lo image of a [128 x 32] activation atom
@@ -214,24 +259,20 @@ struct Rings {
     }
     // MMA warp (one lane): na atoms of K (H columns) into accumulator d_tmem; g = running GEMM counter of this CTA, wq as above
     __device__ __forceinline__ void mma_gemm(uint32_t& g, uint32_t& wq, int na, int H, uint32_t d_tmem) const {
-        constexpr uint32_t idesc = instr_desc_tf32(NP);
+        constexpr uint32_t idesc = instr_desc_tf32(NP), idesc_mix = instr_desc_mix(NP, FMT);
         for (int j = 0; j < na; ++j) {
             uint32_t sa, ra;
             slot(g, j, na, sa, ra);
             const int kvalid = H - j * ATOM_K;
             const int ksteps = kvalid >= ATOM_K ? 4 : (kvalid + 7) / 8;
-            const uint32_t a_hi = smem_u32(a_base + sa * A_STAGE), a_lo = a_hi + A_BYTES;
+            const uint32_t a_hi = smem_u32(a_base + sa * A_STAGE), a_mix = a_hi + A_BYTES;
             mbar_wait(&full_a[sa], ra & 1 GB_TAG((int)(g * 16 + j)));
             {
                 const uint32_t s = wq % SW, r = wq / SW;
                 mbar_wait(&full_w[s], r & 1);
                 fence_after_sync();
                 const uint32_t w_hi = smem_u32(w_base + s * W_BYTES);
-                for (int kk = 0; kk < ksteps; ++kk) {
-                    const uint32_t ko = kk * 32;
-                    mma_tf32(d_tmem, smem_desc(a_lo + ko), smem_desc(w_hi + ko), idesc, (j | kk) != 0);
-                    mma_tf32(d_tmem, smem_desc(a_hi + ko), smem_desc(w_hi + ko), idesc, 1);
-                }
+                for (int kk = 0; kk < ksteps; ++kk) mma_tf32(d_tmem, smem_desc(a_hi + kk * 32), smem_desc(w_hi + kk * 32), idesc, (j | kk) != 0);
                 mma_commit(&empty_w[s]);
                 ++wq;
             }
@@ -239,8 +280,8 @@ struct Rings {
                 const uint32_t s = wq % SW, r = wq / SW;
                 mbar_wait(&full_w[s], r & 1);
                 fence_after_sync();
-                const uint32_t w_lo = smem_u32(w_base + s * W_BYTES);
-                for (int kk = 0; kk < ksteps; ++kk) mma_tf32(d_tmem, smem_desc(a_hi + kk * 32), smem_desc(w_lo + kk * 32), idesc, 1);
+                const uint32_t w_mix = smem_u32(w_base + s * W_BYTES);
+                for (int kk = 0; kk < ksteps; ++kk) mma_f16(d_tmem, smem_desc(a_mix + kk * 32), smem_desc(w_mix + kk * 32), idesc_mix, 1);
                 mma_commit(&empty_w[s]);
                 ++wq;
             }
@@ -254,8 +295,8 @@ struct Rings {
         slot(g, j, na, s, rr);
         if (rr > 0) mbar_wait(&empty_a[s], (rr - 1) & 1 GB_TAG((int)(g * 16 + j)));
         unsigned char* a_hi = a_base + s * A_STAGE;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) store_split2(a_hi, a_hi + A_BYTES, r, 4 * half + c, x[2 * c], x[2 * c + 1]);
+        store_kstep_mix<FMT>(a_hi, a_hi + A_BYTES, r, 4 * half, x[0], x[1], x[2], x[3]);
+        store_kstep_mix<FMT>(a_hi, a_hi + A_BYTES, r, 4 * half + 2, x[4], x[5], x[6], x[7]);
         fence_proxy_async();
         mbar_arrive(&full_a[s]);
     }
@@ -265,8 +306,8 @@ struct Rings {
         slot(g, j, na, s, rr);
         if (rr > 0) mbar_wait(&empty_a[s], (rr - 1) & 1);
         unsigned char* a_hi = a_base + s * A_STAGE;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) store_split(a_hi, a_hi + A_BYTES, r, 4 * half + c, x[c]);
+        store_kstep_mix<FMT>(a_hi, a_hi + A_BYTES, r, 4 * half, lo2(x[0]), hi2(x[0]), lo2(x[1]), hi2(x[1]));
+        store_kstep_mix<FMT>(a_hi, a_hi + A_BYTES, r, 4 * half + 2, lo2(x[2]), hi2(x[2]), lo2(x[3]), hi2(x[3]));
         fence_proxy_async();
         mbar_arrive(&full_a[s]);
     }

@@ -24,7 +24,7 @@ __device__ unsigned int gb_tl_den_n[5];
 
 template <int NP>
 struct TcEdgeCfg {
-    using R = Rings<NP>;
+    using R = Rings<NP, MIX_FP16>;
     static constexpr int NPARTS = 4;                         // worker parts of 4 warps; part p owns 16-column chunks ch == p (mod 4)
     static constexpr int NWORK = 128 * NPARTS;
     // two auxiliary warps stage the P rows of every K-atom (even / odd atoms); the first one also prepares the edge geometry
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(TcEdgeCfg<NP>::THREADS, 1) tc_den_edge_kernel(
     // instead of generic LD / ST for every staging and operand access)
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::R::BYTES);
-    Rings<NP> rg; rg.carve(base, bars);
+    typename CF::R rg; rg.carve(base, bars);
     uint64_t* d_full = bars + CF::R::NBARS; uint64_t* d_empty = d_full + 2;
     uint64_t* geo_full = d_empty + 2; uint64_t* geo_empty = geo_full + CF::NGEO;
     uint64_t* ps_full = geo_empty + CF::NGEO; uint64_t* ps_empty = ps_full + 4;

@@ -285,10 +285,13 @@ void launch_lin_tc(int H, const LinArgs& a, const float* wimg, cudaStream_t s) {
     }
 }
 
-// Weight image for the tensor-core path: [atom j][hi | lo][NP rows][32] with the 128B swizzle applied, so that one
-// contiguous bulk copy lands a ready-to-use B operand.  value(n, k) = transpose ? W[(k+k_off)*ld + n_off+n]
+// Weight image for the tensor-core path: per K-atom j two images of [NP rows][128 bytes] with the 128B swizzle applied, so that
+// one contiguous bulk copy lands a ready-to-use B operand.  value(n, k) = transpose ? W[(k+k_off)*ld + n_off+n]
 //                                                                                : W[(n+n_off)*ld + k_off+k]
-__global__ void pack_tc_kernel(float* dst, const float* src, int ld, int k_off, int n_off, int Kv, int Nv, int NP, int atoms, int transpose) {
+//   fmt 0 (node Linear / training kernels, three TF32 MMAs): [hi | lo] as fp32
+//   fmt 1 / 2 (edge kernels, TF32 + one 16-bit MMA, tc_common.cuh): [hi as fp32 | per K step of 8: the 8 hi parts then the 8
+//              residuals, as fp16 (1) or bf16 (2)]
+__global__ void pack_tc_kernel(float* dst, const float* src, int ld, int k_off, int n_off, int Kv, int Nv, int NP, int atoms, int transpose, int fmt) {
     const int total = atoms * NP * ATOM_K;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int j = idx / (NP * ATOM_K), rem = idx % (NP * ATOM_K);
@@ -298,14 +301,25 @@ __global__ void pack_tc_kernel(float* dst, const float* src, int ld, int k_off, 
         const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
         const int c = kk >> 2, e = kk & 3;
         const size_t off = (size_t)(n >> 3) * 256 + (n & 7) * 32 + ((c ^ (n & 7)) << 2) + e;
-        dst[((size_t)j * 2 + 0) * NP * ATOM_K + off] = hi;
-        dst[((size_t)j * 2 + 1) * NP * ATOM_K + off] = w - hi;
+        float* img_hi = dst + ((size_t)j * 2 + 0) * NP * ATOM_K;
+        float* img_2 = dst + ((size_t)j * 2 + 1) * NP * ATOM_K;
+        img_hi[off] = hi;
+        if (fmt == 0) { img_2[off] = w - hi; continue; }
+        // mix image: K step q = kk / 8 occupies the 16-byte chunks 2q (hi parts) and 2q + 1 (residuals) of the row, 8 halfs each
+        const int q = kk >> 3, e8 = kk & 7;
+        unsigned short* m16 = reinterpret_cast<unsigned short*>(img_2) + (size_t)(n >> 3) * 512 + (n & 7) * 64;
+        const float lo = w - hi;
+        unsigned short h16, l16;
+        if (fmt == 2) { h16 = __bfloat16_as_ushort(__float2bfloat16_rn(hi)); l16 = __bfloat16_as_ushort(__float2bfloat16_rn(lo)); }
+        else { h16 = __half_as_ushort(__float2half_rn(hi)); l16 = __half_as_ushort(__float2half_rn(lo)); }
+        m16[(((2 * q) ^ (n & 7)) << 3) + e8] = h16;
+        m16[(((2 * q + 1) ^ (n & 7)) << 3) + e8] = l16;
     }
 }
 
-void launch_pack_tc(float* dst, const float* src, int ld, int k_off, int n_off, int Kv, int Nv, int NP, int atoms, int transpose, cudaStream_t s) {
+void launch_pack_tc(float* dst, const float* src, int ld, int k_off, int n_off, int Kv, int Nv, int NP, int atoms, int transpose, cudaStream_t s, int fmt) {
     const int total = atoms * NP * ATOM_K;
-    pack_tc_kernel<<<(total + 255) / 256, 256, 0, s>>>(dst, src, ld, k_off, n_off, Kv, Nv, NP, atoms, transpose);
+    pack_tc_kernel<<<(total + 255) / 256, 256, 0, s>>>(dst, src, ld, k_off, n_off, Kv, Nv, NP, atoms, transpose, fmt);
 }
 
 }  // namespace gb

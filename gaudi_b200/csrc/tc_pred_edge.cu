@@ -29,7 +29,8 @@ __device__ unsigned int gb_tl_pred_n[5];
 
 template <int NP>
 struct TcPredCfg {
-    using R = Rings<NP>;
+    using R = Rings<NP, MIX_FP16>;                                         // forward: activations (fp16 correction terms)
+    using RB = Rings<NP, MIX_BF16>;                                        // backward: gradients (bf16: fp16 has no range for them)
     static constexpr int A_BYTES = R::A_BYTES;
     static constexpr int A_STAGE = R::A_STAGE;
     static constexpr int NPARTS = GB_PRED_NPARTS;                          // worker parts of 4 warps; part p owns 16-column chunks ch == p (mod 4)
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
     // instead of generic LD / ST for every staging and operand access)
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::R::BYTES);
-    Rings<NP> rg; rg.carve(base, bars);
+    typename CF::R rg; rg.carve(base, bars);
     uint64_t* d1_full = bars + CF::R::NBARS; uint64_t* d2_full = d1_full + 1; uint64_t* d1_empty = d2_full + 1; uint64_t* d2_empty = d1_empty + 1;
     uint64_t* geo_full = d2_empty + 1; uint64_t* geo_empty = geo_full + CF::NGEO;
     uint64_t* ps_full = geo_empty + CF::NGEO; uint64_t* ps_empty = ps_full + 4;
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
     // instead of generic LD / ST for every staging and operand access)
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::R::BYTES);
-    Rings<NP> rg; rg.carve(base, bars);
+    typename CF::RB rg; rg.carve(base, bars);
     uint64_t* d1_full = bars + CF::R::NBARS; uint64_t* d2_full = d1_full + 1; uint64_t* d1_empty = d2_full + 1; uint64_t* d2_empty = d1_empty + 1;
     uint64_t* sv_full = d2_empty + 1; uint64_t* sv_empty = sv_full + SVS;
     uint64_t* geo_full = sv_empty + SVS; uint64_t* geo_empty = geo_full + 2;
