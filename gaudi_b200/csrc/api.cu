@@ -157,13 +157,13 @@ struct Packer {
             e.l1_nt_tc = tc_block2(w, ld, 0, 0, 0, H, H, H, 0);
         }
     }
-    // edge = true: the image feeds an edge kernel (forward: activations -> fp16 mix; dgrad: gradients -> bf16 mix)
+    // edge = true: the image feeds an edge kernel (TF32 + bf16 correction terms, tc_common.cuh)
     void square(size_t& wt, size_t& bias, size_t* nt, const float* w, const float* b, size_t* tcw = nullptr, size_t* tcnt = nullptr, bool edge = false) {
         const int H = net->H, HP = net->HP;
         wt = block(w, H, 0, 0, H, H, HP, 1);
         bias = vec(b, H, HP);
         if (nt) *nt = block(w, H, 0, 0, H, H, HP, 0);
-        if (tcw) *tcw = tc_block(w, H, 0, 0, H, H, 1, edge ? 1 : 0);
+        if (tcw) *tcw = tc_block(w, H, 0, 0, H, H, 1, edge ? 2 : 0);
         if (tcnt) *tcnt = tc_block(w, H, 0, 0, H, H, 0, edge ? 2 : 0);
     }
     void node_mlp(NodeMlpW& n, const float* w1, const float* b1, const float* w2, const float* b2, bool want_nt) {

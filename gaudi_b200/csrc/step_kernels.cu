@@ -211,7 +211,10 @@ __global__ void step_guide_kernel(GuideArgs a) {
             if (e % a.D == 0) cnt += a.node_mask[b * a.N + e / a.D];
         }
         n2 = warp_sum(n2); cnt = fmaxf(warp_sum(cnt), 1.f);
-        const float coef = fminf(a.max_norm / (sqrtf(n2) + 1e-6f), 1.0f);        // en_diffusion.py:905-909
+        // en_diffusion.py:905-909.  torch.clamp(x, max=1) propagates a NaN norm (the whole molecule then becomes NaN and is zeroed
+        // by the final nan_to_num); fminf alone would silently drop it
+        const float craw = a.max_norm / (sqrtf(n2) + 1e-6f);
+        const float coef = (craw != craw) ? craw : fminf(craw, 1.0f);
         float s[3] = {0.f, 0.f, 0.f};
         __syncwarp();
         for (int e = lane; e < ND; e += 32) {

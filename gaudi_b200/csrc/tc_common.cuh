@@ -17,11 +17,11 @@
 // Edge kernels (round 2): the two correction terms run as ONE 16-bit MMA per K step.  With a = a_hi + a_lo, w = w_hi + w_lo
 // (hi = TF32 part):   a*w ~= a_hi*w_hi                      kind::tf32, K = 8
 //                          + [a_lo | a_hi] . [w_hi | w_lo]   kind::f16,  K = 16 (the 8 a_lo*w_hi and the 8 a_hi*w_lo products)
-// where the operands of the second MMA are rounded to fp16 (activations, forward) or bf16 (gradients: fp16 has no range for
-// them).  Both terms are 2^-11 relative to the main one, so an 11- or 8-bit mantissa keeps the product error at ~2^-22 / 2^-19:
-// against an fp64 GEMM (K = 196) the rms error is 5.7e-7 (fp16) / 1.7e-6 (bf16) of the mean |y|, vs 2.2e-7 for three TF32 MMAs
-// and 3.1e-7 for a plain fp32 GEMM -- for 2/3 of the tensor-pipe time and 2/3 of the operand reads from shared memory, the two
-// resources that bound the operand-build phases of these kernels.  The images have the same size as before: per K-atom
+// where the operands of the second MMA are rounded to bf16 (fp16 is supported by the code but has no range for gradients and
+// overflows on activations of diverging trajectories).  Both terms are 2^-11 relative to the main one, so the 8-bit mantissa keeps
+// the product error at ~2^-19: against an fp64 GEMM (K = 196) the rms error is 1.7e-6 of the mean |y| (fp16: 5.7e-7), vs 2.2e-7
+// for three TF32 MMAs and 3.1e-7 for a plain fp32 GEMM -- for 2/3 of the tensor-pipe time and 2/3 of the operand reads from
+// shared memory, the two resources that bound the operand-build phases of these kernels.  The images have the same size as before: per K-atom
 // [hi : rows x 32 fp32][mix : rows x 4 K-steps x (8 + 8) halfs], both 128 bytes per row with the 128-byte swizzle.
 namespace gb {
 namespace tc {

@@ -24,7 +24,7 @@ __device__ unsigned int gb_tl_den_n[5];
 
 template <int NP>
 struct TcEdgeCfg {
-    using R = Rings<NP, MIX_FP16>;
+    using R = Rings<NP, MIX_BF16>;
     static constexpr int NPARTS = 4;                         // worker parts of 4 warps; part p owns 16-column chunks ch == p (mod 4)
     static constexpr int NWORK = 128 * NPARTS;
     // two auxiliary warps stage the P rows of every K-atom (even / odd atoms); the first one also prepares the edge geometry

@@ -29,8 +29,11 @@ __device__ unsigned int gb_tl_pred_n[5];
 
 template <int NP>
 struct TcPredCfg {
-    using R = Rings<NP, MIX_FP16>;                                         // forward: activations (fp16 correction terms)
-    using RB = Rings<NP, MIX_BF16>;                                        // backward: gradients (bf16: fp16 has no range for them)
+    // bf16 correction terms in both directions: fp16 would be 3x more accurate for O(1) activations, but it has no range for the
+    // gradients of the backward and it overflows on the forward too (random-init trajectories reach |x| ~ 1e3, i.e. squared
+    // distances and pre-activations beyond 65504: the 1000-step chain test diverged with fp16)
+    using R = Rings<NP, MIX_BF16>;
+    using RB = Rings<NP, MIX_BF16>;
     static constexpr int A_BYTES = R::A_BYTES;
     static constexpr int A_STAGE = R::A_STAGE;
     static constexpr int NPARTS = GB_PRED_NPARTS;                          // worker parts of 4 warps; part p owns 16-column chunks ch == p (mod 4)

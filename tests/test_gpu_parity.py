@@ -115,7 +115,7 @@ def test_full_chain_drift_vs_reference_golden(guided):
     rel = maxabs(x, ref) / float(ref.abs().max())
     mism = float((oh.cpu() != torch.from_numpy(g["one_hot"])).float().mean())
     print(f"[chain guided={guided}] |x|max={float(ref.abs().max()):.3g} rel drift={rel:.3e} one-hot mismatch={mism:.3f}")
-    assert rel <= 2e-2          # chaotic random-init trajectory; the per-step tests above are the parity gate
+    assert rel <= 5e-3          # chaotic random-init trajectory (measured 4e-4 .. 7e-4); the per-step tests above are the parity gate
     assert mism == 0.0
 
 
@@ -290,3 +290,87 @@ def test_hidden_256_matches_oracle():
     pr, gr = runtime.predictor_value_and_grad(pred, z.to(dev), nm, em, t.to(dev), w.to(dev))
     rp, rg = O.predictor_input_grad(wp, pcfg, z, nm.cpu(), em.cpu(), t, lambda p: (p * w).sum(1), 1.0)
     assert maxabs(pr, rp) <= TOL and maxabs(gr, rg) <= TOL
+
+
+def test_step_guide_nan_inf_semantics_match_torch_nan_to_num():
+    """en_diffusion.py:905-934 with non-finite values: the clipped, centred gradient is subtracted, the x part re-centred and the
+    result passed through ``zs.nan_to_num(0.)``: NaN -> 0, +-inf -> +-FLT_MAX.  The fused kernel must agree with the same torch
+    ops element for element (a NaN anywhere in a molecule's gradient makes its norm, hence its whole update, NaN -> zeros)."""
+    dev = _dev()
+    from gaudi_b200 import runtime
+    nx = torch.tensor([10, 7, 11, 3, 9])
+    nm, em = gb.build_masks(nx, 11, False, device=dev)
+    B, N, D = 5, 11, 4
+    gen = torch.Generator().manual_seed(9)
+    zs_pre = O.draw_noise(B, N, D, nm.cpu(), generator=gen)
+    grad = O.draw_noise(B, N, D, nm.cpu(), generator=gen) * 3.0
+    grad[1, 2, 0] = float("nan")            # molecule 1: NaN gradient entry
+    zs_pre[2, 0, 3] = float("inf")          # molecule 2: +inf feature in z_s itself (not centred: stays inf -> FLT_MAX)
+    zs_pre[3, 1, 3] = float("-inf")
+    zs_pre[4, 1, 1] = float("inf")          # molecule 4: +inf coordinate -> centring gives inf - inf = NaN for the column -> 0
+    sigma = 0.37
+    coef = torch.tensor([1.0, 0.5, sigma], device=dev)
+    ref = O._project_x(zs_pre - sigma * O.clip_and_center_grad(grad, nm.cpu()), nm.cpu())
+    ref = torch.nan_to_num(ref, 0.0)
+    got = runtime.step_guide(zs_pre.to(dev), grad.to(dev), coef, nm.reshape(-1).contiguous()).cpu()
+    assert torch.isfinite(got).all()
+    assert torch.equal(torch.isfinite(ref), torch.ones_like(ref, dtype=torch.bool))
+    big = ref.abs() > 1e30
+    assert torch.equal(got[big], ref[big]), "+-inf must become +-FLT_MAX exactly"
+    assert maxabs(got[~big], ref[~big]) <= 1e-5
+    assert float(got[1].abs().max()) == 0.0 and float(ref[1].abs().max()) == 0.0     # NaN norm -> the whole molecule is zeroed
+
+
+def test_denoiser_tail_scrubs_nan_like_the_reference():
+    """edm/egnn/models.py:138-141 + en_diffusion.py:881: a NaN produced by the network is reset to zero before the centre of
+    gravity is removed (so one bad coordinate does not poison its molecule), and the guided step scrubs eps again.
+    Documented deviation: the reference also turns +-inf into +-FLT_MAX inside vel, but only in batches that contain a
+    NaN somewhere; the kernel scrubs NaN element-wise and leaves that batch-wide coupling out."""
+    dev = _dev()
+    args, model, pred, prop = build_models("cata", dev, hidden=(64, 64), layers=(1, 1))
+    nx = torch.tensor([4, 3])
+    nm, em = gb.build_masks(nx, 4, False, device=dev)
+    gen = torch.Generator().manual_seed(2)
+    z = O.draw_noise(2, 4, 4, nm.cpu(), generator=gen).to(dev)
+    t = torch.tensor([0.5], device=dev)
+    clean = model.phi(z, t, nm, em, None)
+    zn = z.clone(); zn[0, 1, 0] = float("nan")          # NaN coordinate of molecule 0 -> NaN activations all over molecule 0
+    eps = model.phi(zn, t, nm, em, None)
+    assert torch.isfinite(eps[:, :, :3]).all(), "vel must be NaN-free after the scrub"
+    assert torch.equal(eps[1], clean[1]), "molecules are independent: molecule 1 is untouched"
+    assert float(eps[0, :, :3].abs().max()) == 0.0       # every coordinate update of molecule 0 was NaN -> zeros, centred zeros
+
+
+def test_check_stats_raises_the_reference_assertions():
+    """The device-side running maxima replace assert_mean_zero_with_mask / assert_correctly_masked (utils.py:52-65): a doctored
+    stats row must raise the same AssertionError texts."""
+    stats = torch.zeros(3, 8)
+    stats[:, 0] = 1.0; stats[:, 2] = 1.0
+    gb.EnVariationalDiffusion._check_stats(stats)                       # clean
+    bad = stats.clone(); bad[1, 4] = 2e-4
+    with pytest.raises(AssertionError, match="Variables not masked properly."):
+        gb.EnVariationalDiffusion._check_stats(bad)
+    bad = stats.clone(); bad[2, 1] = 0.5                                 # centre of gravity of z_t drifted: 0.5 / 1.0 >= 1e-2
+    with pytest.raises(AssertionError, match="Mean is not zero, relative_error"):
+        gb.EnVariationalDiffusion._check_stats(bad)
+    bad = stats.clone(); bad[0, 3] = float("nan")                        # NaN anywhere in eps_x surfaces as a failed invariant
+    with pytest.raises(AssertionError, match="Mean is not zero"):
+        gb.EnVariationalDiffusion._check_stats(bad)
+
+
+def test_seeded_sampling_is_reproducible_and_seed_dependent():
+    """With ``set_seed`` every draw (z_T, per-step noise, decode noise) comes from the Philox stream: the same seed reproduces the
+    molecules bit for bit, another seed changes z_T itself, and torch's global generator plays no part."""
+    dev = _dev()
+    args, model, pred, prop = build_models("cata", dev, hidden=(64, 64), layers=(2, 2), timesteps=25)
+    nx = torch.tensor([10, 9, 11, 4])
+    tf = gb.AffineTarget.max_gap(pred)
+    outs = []
+    for seed, torch_seed in ((5, 0), (5, 123), (6, 0)):
+        torch.manual_seed(torch_seed); torch.cuda.manual_seed_all(torch_seed)
+        model.set_seed(seed)
+        x, oh, nm, em = gb.sample_guidance(args, model, tf, nx, scale=0.6)
+        outs.append(x.clone())
+    assert torch.equal(outs[0], outs[1]), "same Philox seed -> same molecules, whatever torch's generator state"
+    assert not torch.equal(outs[0], outs[2])
+    model.set_seed(None)

@@ -1,7 +1,7 @@
 """GPU parity of the training step: loss and parameter gradients of the CUDA path (C ABI ops chained
 by gaudi_b200/training.py) against the reference goldens (tests/golden/train_*.npz) and the CPU oracle's autograd.
 
-Tolerances: loss max-abs <= 1e-4; every parameter gradient within 1e-4 * max(1, max|ref|) absolute AND 2e-3 relative
+Tolerances: loss max-abs <= 1e-4; every parameter gradient within 1e-4 * max(1, max|ref|) absolute AND 2e-4 relative
 in norm (fp32, different summation order: the reductions over ~60 edges/node and ~10^3 rows are re-associated).
 """
 import numpy as np
@@ -103,7 +103,7 @@ def test_training_loss_and_gradients_match_reference_golden(ds, gemm, monkeypatc
         gn = float(params[str(name)].grad.double().norm())
         rel = abs(gn - norm) / max(norm, 1e-6)
         worst_rel = max(worst_rel, rel)
-        assert rel <= 2e-3, f"{name}: |grad| {gn:.6e} vs {norm:.6e}"
+        assert rel <= 2e-4, f"{name}: |grad| {gn:.6e} vs {norm:.6e}"       # measured 4e-5 (tcgen05 3xTF32) / 2e-6 (fp32 GEMM)
     worst_abs = 0.0
     for k in g.files:
         if k.startswith("grad:"):
@@ -144,7 +144,7 @@ def test_all_parameter_gradients_match_oracle_autograd():
         assert p.grad is not None, name
         assert maxabs(p.grad, ref) <= 1e-4 * max(1.0, float(ref.abs().max())), name
         rn = float(ref.double().norm())
-        assert abs(float(p.grad.double().norm()) - rn) <= 2e-3 * max(rn, 1e-6), name
+        assert abs(float(p.grad.double().norm()) - rn) <= 2e-4 * rn + 2e-9, name          # + fp32 noise floor of ~1e-6-sized gradients
 
 
 def test_optimizer_steps_reduce_the_loss():
@@ -201,7 +201,7 @@ def test_predictor_training_step_matches_reference_golden(ds, gemm, monkeypatch)
     for name, norm in zip(g["grad_names"], g["grad_norms"]):
         gn = float(params[str(name)].grad.double().norm())
         worst = max(worst, abs(gn - norm) / max(norm, 1e-6))
-        assert abs(gn - norm) <= 2e-3 * max(norm, 1e-6), f"{name}: {gn:.6e} vs {norm:.6e}"
+        assert abs(gn - norm) <= 2e-4 * norm + 2e-9, f"{name}: {gn:.6e} vs {norm:.6e}"          # measured 9e-5 (tc) / 4e-6 (fp32)
     for k in g.files:
         if k.startswith("grad:"):
             ref = torch.from_numpy(g[k])
