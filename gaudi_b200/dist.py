@@ -46,11 +46,12 @@ def gather_padded(t: torch.Tensor, counts: Sequence[int], pad_nodes: Optional[in
 
 
 def sample_guidance_sharded(args, model, target_function, nodesxsample: torch.Tensor, scale=1.0, std=1.0,
-                            seed: int = 0, noise=None, sampler=None):
+                            seed: int = 0, noise=None, sampler=None, timing: Optional[dict] = None):
     """``sampling_edm.sample_guidance`` over all ranks: returns the FULL (x, one_hot, node_mask) on every rank.
 
     ``sampler`` defaults to ``gaudi_b200.sampling.sample_guidance``; ``noise`` (parity mode) is the injected
-    [T+2, B_total, N, D] tensor, sliced per rank.
+    [T+2, B_total, N, D] tensor, sliced per rank.  ``timing`` (optional dict) receives ``gather_ms`` (CUDA-event time of the
+    three all_gathers on this rank) and ``gather_bytes`` (payload this rank contributes).
     """
     from . import sampling
     rank, ws = world()
@@ -93,7 +94,17 @@ def sample_guidance_sharded(args, model, target_function, nodesxsample: torch.Te
         F = int(ft.item())
         if one_hot.shape[0] == 0:
             one_hot = one_hot.new_zeros(0, 1, F)
-    return (gather_padded(x, counts, pad), gather_padded(one_hot, counts, pad), gather_padded(node_mask, counts, pad))
+    if timing is not None and x.is_cuda:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    out = (gather_padded(x, counts, pad), gather_padded(one_hot, counts, pad), gather_padded(node_mask, counts, pad))
+    if timing is not None:
+        timing["gather_bytes"] = 4 * max(counts) * pad * (3 + F + 1)
+        if x.is_cuda:
+            e1.record()
+            torch.cuda.synchronize()
+            timing["gather_ms"] = e0.elapsed_time(e1)
+    return out
 
 
 def average_gradients(parameters) -> int:

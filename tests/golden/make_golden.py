@@ -207,6 +207,32 @@ def chain(dataset, nodesxsample, guided, target_name, scale, std, seed, record_e
     return rec
 
 
+def chain_frames(dataset, nodesxsample, std, seed, keep_frames):
+    """EnVariationalDiffusion.sample_chain (en_diffusion.py:1118-1174) with the SAME masks and injected noise as the unguided
+    `chain` fixture (same seed -> same generator stream), so the frames fixture does not need to store the noise again."""
+    args, model, pred, prop = build(dataset)
+    F_in = 1 if dataset == "cata" else 12
+    inner = model.module
+    T = inner.T
+    got = {}
+
+    class Fake:
+        def sample(self, bs, n_nodes, node_mask, edge_mask, std=1.0):
+            got["nm"], got["em"] = node_mask.clone(), edge_mask.clone()
+            return torch.zeros(bs, n_nodes, 3), {"categorical": torch.zeros(bs, n_nodes, 1)}
+    sampling_edm.sample_pos_edm(args, Fake(), nodesxsample)
+    nm, em = got["nm"], got["em"]
+    B, N, _ = nm.shape
+    D = 3 + F_in
+    gen = torch.Generator().manual_seed(seed)
+    noise = torch.stack([processed_noise(gen, (B, N, D), nm, std if k == 0 else 1.0) for k in range(T + 2)])
+    it = iter(noise)
+    inner.sample_combined_position_feature_noise = lambda n_s, n_n, node_mask, std=1.0: next(it)
+    frames = inner.sample_chain(B, N, nm, em, None, keep_frames=keep_frames, std=std)
+    return {"frames": frames.view(keep_frames, B, N, D).numpy(), "keep_frames": np.int64(keep_frames), "nodesxsample": nodesxsample.numpy(),
+            "noise_digest": np.frombuffer(hashlib.sha256(noise.numpy().tobytes()).digest(), dtype=np.uint8)}
+
+
 def train_step(dataset, nodesxsample, t_list, seed):
     """One training-loss evaluation + backward of the reference (train_edm.py:36-49, 71-75) with the two random draws of
     compute_loss (en_diffusion.py:657-659 t_int, :677-679 eps) pinned so that the oracle / product can be fed the same."""
@@ -342,6 +368,9 @@ def main():
         np.savez_compressed(os.path.join(HERE, "pred_train_hetro.npz"),
                             **predictor_train_step("hetro", torch.tensor([10, 8, 3]), [777, 0, 12], seed=667))
         return
+    if "--only-chain-frames" in sys.argv:   # sample_chain frames on the masks / noise of chain_cata_unguided.npz
+        np.savez_compressed(os.path.join(HERE, "chain_frames_cata.npz"), **chain_frames("cata", torch.tensor([11, 10, 8]), 0.7, 78, 8))
+        return
     if "--only-train" in sys.argv:          # add the training fixtures without regenerating the (slow) chains
         np.savez_compressed(os.path.join(HERE, "train_cata.npz"),
                             **train_step("cata", torch.tensor([11, 10, 9, 11, 7, 2]), [1000, 613, 0, 1, 250, 0], seed=555))
@@ -374,6 +403,7 @@ def main():
     rec = chain("cata", torch.tensor([11, 10, 8]), False, None, 0.0, 0.7, seed=78)
     np.savez_compressed(os.path.join(HERE, "chain_cata_unguided.npz"), **rec)
     print("chain unguided done", flush=True)
+    np.savez_compressed(os.path.join(HERE, "chain_frames_cata.npz"), **chain_frames("cata", torch.tensor([11, 10, 8]), 0.7, 78, 8))
 
     np.savez_compressed(os.path.join(HERE, "train_cata.npz"),
                         **train_step("cata", torch.tensor([11, 10, 9, 11, 7, 2]), [1000, 613, 0, 1, 250, 0], seed=555))

@@ -255,6 +255,27 @@ def test_sample_chain_frames():
         assert maxabs(chain[k], frames[k]) <= 1e-6
 
 
+def test_sample_chain_matches_reference_golden():
+    """sample_chain against the frames the UNMODIFIED reference produced (tests/golden/make_golden.py --only-chain-frames) on the
+    masks and injected noise of the unguided chain fixture: 8 frames of a 1000-step run, frame 0 = the final (x, h)."""
+    dev = _dev()
+    f, g = golden("chain_frames_cata.npz"), golden("chain_cata_unguided.npz")
+    args, model, pred, prop = build_models("cata", dev)
+    nm, em = torch.from_numpy(g["node_mask"]).to(dev), torch.from_numpy(g["edge_mask"]).to(dev)
+    noise = torch.from_numpy(g["noise"]).to(dev)
+    B, N = nm.shape[:2]
+    keep = int(f["keep_frames"])
+    chain = model.sample_chain(B, N, nm, em, None, keep_frames=keep, std=float(g["std"]), noise=noise).view(keep, B, N, -1)
+    ref = torch.from_numpy(f["frames"])
+    worst = 0.0
+    for k in range(keep):
+        rel = maxabs(chain[k], ref[k]) / max(1.0, float(ref[k].abs().max()))
+        worst = max(worst, rel)
+        assert rel <= 1e-4, (k, rel)
+    print(f"[sample_chain vs reference] worst relative frame error {worst:.2e}")
+    assert torch.equal(chain[0, :, :, 3:].cpu(), ref[0, :, :, 3:])                  # one-hot ring types of the final molecules
+
+
 def test_tensor_core_wgrad_matches_fp64():
     """gb_wgrad (tcgen05, MN-major operands, 3xTF32, split-K): C = G^T X on strided views, with accumulation, through the
     deterministic two-phase reduction (scratch) and through the atomic path (no scratch)."""

@@ -87,6 +87,17 @@ def test_free_running_chain_prefix_matches_reference():
         z = O.unguided_step(wd, dcfg, gamma, s, z, noise[k + 1], nm, em)["zs"]
     ref = torch.from_numpy(g["z_900"])
     assert maxabs(z, ref) <= 1e-5 * max(1.0, float(ref.abs().max()))
+    # the reference's sample_chain (en_diffusion.py:1118-1174) on the same masks / noise: frame k of keep_frames = 8 holds the
+    # un-normalised z after step s = 125 k, so frame 7 (s = 875) continues this very prefix
+    f = golden("chain_frames_cata.npz")
+    import hashlib
+    assert bytes(f["noise_digest"]) == hashlib.sha256(g["noise"].tobytes()).digest(), "fixtures must share their injected noise"
+    for k, s in enumerate(range(899, 874, -1)):
+        z = O.unguided_step(wd, dcfg, gamma, s, z, noise[101 + k], nm, em)["zs"]
+    frame = torch.cat([z[:, :, :3] * 3.0, z[:, :, 3:] * 4.0 * nm], dim=2)           # unnormalize_z with norm_values (3, 4, 10)
+    ref7 = torch.from_numpy(f["frames"][7])
+    assert maxabs(frame, ref7) <= 1e-5 * max(1.0, float(ref7.abs().max()))
+    assert maxabs(torch.from_numpy(f["frames"][0][:, :, :3]), torch.from_numpy(g["x"])) == 0.0    # frame 0 = the final molecules
 
 
 def test_fp64_oracle_agrees_with_fp32():
