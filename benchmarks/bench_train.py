@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE.json config 5: EDM training step (denoising loss forward + backward + AdamW) on a synthetic cc-PBH batch of 512.
 
-One JSON line: CUDA-event time per step (zero_grad, loss, backward, optimizer step, as train_edm.py:71-82), molecules/s,
+One JSON line: CUDA-event time per step (zero_grad, loss, backward, adaptive clipping + optimizer step, as train_edm.py:71-82), molecules/s,
 our kernel launches per step, and -- unless --no-cpu -- the CPU oracle's autograd step on a bounded sample beside it.
 """
 import argparse
@@ -18,6 +18,7 @@ import torch  # noqa: E402
 
 import gaudi_b200 as gb  # noqa: E402
 from gaudi_b200 import _lib  # noqa: E402
+from gaudi_b200 import train_utils as TU  # noqa: E402
 from bench_shapes import models  # noqa: E402
 
 
@@ -29,6 +30,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=32)
     ap.add_argument("--graph", action="store_true", help="capture the whole step (loss, backward, AdamW) in one CUDA graph and replay it")
+    ap.add_argument("--torch-optim", action="store_true", help="torch.optim.AdamW (no clipping) instead of the fused clip + AdamW-amsgrad step")
     ap.add_argument("--model", choices=["denoiser", "predictor"], default="denoiser",
                     help="denoiser: EDM l2 loss (train_edm.py); predictor: l1 property loss on z_t (train_cond_predictor.py)")
     args = ap.parse_args()
@@ -50,7 +52,8 @@ def main():
             p_.requires_grad_(True)
         pred.train()
         y = torch.randn(B, 5, device=dev)
-        opt = torch.optim.AdamW(pred.parameters(), lr=1e-3, amsgrad=True, weight_decay=1e-12, capturable=args.graph)
+        opt = (TU.FusedAdamWClip(pred.parameters(), lr=1e-3, weight_decay=1e-12, clip=True) if not args.torch_optim else
+               torch.optim.AdamW(pred.parameters(), lr=1e-3, amsgrad=True, weight_decay=1e-12, capturable=args.graph))
 
         def step():
             opt.zero_grad()
@@ -61,8 +64,9 @@ def main():
             opt.step()
             return loss
     else:
-        opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, amsgrad=True, weight_decay=1e-12,
-                                capturable=args.graph)
+        trainable = [p for p in model.parameters() if p.requires_grad]
+        opt = (TU.FusedAdamWClip(trainable, lr=1e-4, weight_decay=1e-12, clip=True) if not args.torch_optim else
+               torch.optim.AdamW(trainable, lr=1e-4, amsgrad=True, weight_decay=1e-12, capturable=args.graph))
 
         def step():
             opt.zero_grad()
@@ -104,7 +108,8 @@ def main():
            else "property-predictor training step (sample_edm_t + l1 loss fwd+bwd+AdamW), cc-PBH shape, synthetic batch",
            "batch": B, "edges": int(em.sum().item()), "ms_per_step": ms, "molecules_per_s": B / (ms * 1e-3),
            "gpu_launches_per_step": captured if args.graph else (_lib.lib().gb_launch_count(0) - l0) / args.steps, "loss": float(loss.detach()),
-           "cuda_graph": bool(args.graph)}
+           "cuda_graph": bool(args.graph),
+           "optimizer": "torch.optim.AdamW(amsgrad)" if args.torch_optim else "fused adaptive clip + AdamW(amsgrad) (gb_adamw_amsgrad_clip)"}
     if not args.no_cpu and args.model == "predictor":
         import gaudi_oracle as O
         cb = args.cpu_batch

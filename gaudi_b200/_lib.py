@@ -87,6 +87,9 @@ SIGNATURES = {
     "gb_pool_mean": (_I, [_P, _I, _I, _I, _P, _P]),
     "gb_pool_mean_bwd": (_I, [_P, _I, _I, _I, _P, _P]),
     "gb_train_loss": (_I, [_P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _I, _I, _I, _P, _P, _P]),
+    "gb_adamw_state_doubles": (_SZ, [_I]),
+    "gb_adamw_scratch_doubles": (_SZ, []),
+    "gb_adamw_amsgrad_clip": (_I, [_P, _P, _P, _P, _P, _SZ, _F, _F, _F, _F, _F, _P, _I, _I, _P, _P]),
 }
 
 

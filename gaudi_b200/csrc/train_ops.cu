@@ -631,3 +631,82 @@ extern "C" int gb_vlb_loss(const float* net_t, const float* eps_t, const float* 
                                                                   bias_h, B, N, F, loss, error_out);
     TR_CHECK("vlb_loss");
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused optimizer step of the training loops: adaptive global-norm clipping (edm/utils.py:51-70, Queue :31-48) + AdamW with
+// amsgrad (train_edm.py:22-24, 71-82) over ONE flat parameter / gradient bucket, with no host synchronisation:
+//   1. adamw_sqnorm_kernel      fixed-order partial sums of g^2 (one double per block)
+//   2. adamw_clip_queue_kernel  one thread: ||g||, max_norm = 1.5 mean + 2 std of the window (numpy: population std, float64),
+//                               clip coefficient of torch.nn.utils.clip_grad_norm_ (max_norm / (norm + 1e-6), capped at 1), window
+//                               update with the norm actually applied, step counter and bias corrections
+//   3. adamw_amsgrad_kernel     torch.optim.AdamW(amsgrad=True) single-tensor update order on the scaled gradient
+// state (device, double): [0] step, [1] ||g||, [2] max_norm, [3] clip coefficient, [4] window length, [5] window position,
+//                         [6] 1 - beta1^step, [7] sqrt(1 - beta2^step), [8 .. 8+window) the window.
+// ---------------------------------------------------------------------------------------------------------------------
+#define GB_ADAMW_BLOCKS 592
+__global__ void adamw_sqnorm_kernel(const float* __restrict__ g, size_t n, double* __restrict__ partial) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) { const double v = g[i]; acc += v * v; }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void adamw_clip_queue_kernel(const double* __restrict__ partial, int nblocks, double* __restrict__ st, int window, int clip,
+                                        double beta1, double beta2) {
+    double s = 0.0;
+    for (int i = 0; i < nblocks; ++i) s += partial[i];
+    const double norm = sqrt(s);
+    double coef = 1.0, max_norm = 0.0;
+    if (clip) {
+        const int len = (int)st[4];
+        double mean = 0.0, var = 0.0;
+        for (int i = 0; i < len; ++i) mean += st[8 + i];
+        mean /= (double)(len > 0 ? len : 1);
+        for (int i = 0; i < len; ++i) { const double d = st[8 + i] - mean; var += d * d; }
+        var /= (double)(len > 0 ? len : 1);
+        max_norm = 1.5 * mean + 2.0 * sqrt(var);
+        coef = fmin(max_norm / (norm + 1e-6), 1.0);
+        const double rec = norm > max_norm ? max_norm : norm;              // the window records the norm actually applied
+        int pos = (int)st[5];
+        st[8 + pos] = rec;
+        st[5] = (double)((pos + 1) % window);
+        st[4] = (double)(len < window ? len + 1 : window);
+    }
+    const double step = st[0] + 1.0;
+    st[0] = step; st[1] = norm; st[2] = max_norm; st[3] = coef;
+    st[6] = 1.0 - pow(beta1, step);
+    st[7] = sqrt(1.0 - pow(beta2, step));
+}
+__global__ void adamw_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                     float* __restrict__ vmax, size_t n, float lr, float beta1, float beta2, float eps, float wd,
+                                     const double* __restrict__ st) {
+    const float coef = (float)st[3];
+    const float step_size = (float)((double)lr / st[6]);
+    const float bc2_sqrt = (float)st[7];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * coef;                                        // clip_grad_norm_: grads.mul_(clip_coef_clamped)
+        float pi = p[i] * (1.f - lr * wd);                                   // param.mul_(1 - lr * weight_decay)
+        const float mi = m[i] + (gi - m[i]) * (1.f - beta1);                 // exp_avg.lerp_(grad, 1 - beta1)
+        const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;             // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
+        const float vm = fmaxf(vmax[i], vi);                                 // torch.maximum(max_exp_avg_sq, exp_avg_sq)
+        const float denom = sqrtf(vm) / bc2_sqrt + eps;
+        pi -= step_size * (mi / denom);                                      // param.addcdiv_(exp_avg, denom, value = -step_size)
+        p[i] = pi; m[i] = mi; v[i] = vi; vmax[i] = vm;
+    }
+}
+extern "C" size_t gb_adamw_state_doubles(int window) { return (size_t)(8 + window); }
+extern "C" size_t gb_adamw_scratch_doubles(void) { return GB_ADAMW_BLOCKS; }
+extern "C" int gb_adamw_amsgrad_clip(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, size_t n,
+                                     float lr, float beta1, float beta2, float eps, float weight_decay, double* state, int window, int clip,
+                                     double* scratch, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !max_exp_avg_sq || !state || !scratch) return gb_train_fail("adamw: null argument");
+    if (n == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    adamw_sqnorm_kernel<<<GB_ADAMW_BLOCKS, 256, 0, s>>>(grads, n, scratch);
+    adamw_clip_queue_kernel<<<1, 1, 0, s>>>(scratch, GB_ADAMW_BLOCKS, state, window, clip, (double)beta1, (double)beta2);
+    adamw_amsgrad_kernel<<<ew_blocks(n), 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, max_exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, state);
+    gb_train_launched(2);
+    TR_CHECK("adamw_amsgrad_clip");
+}

@@ -232,6 +232,19 @@ int gb_train_loss(const float* net, const float* eps, const float* zt, const flo
                   const float* t_int, const float* gamma_t, float gamma_T, float norm_h, float bias_h, int B, int N,
                   int F, float* loss, float* g_net, void* stream);
 
+/* ---- fused optimizer step of the training loops (replaces edm/utils.py:51-70 gradient_clipping + Queue :31-48 and the
+ * torch.optim.AdamW(amsgrad=True) step of train_edm.py:22-24, 71-82) over ONE flat fp32 bucket of n parameters, no host sync:
+ * global gradient norm (fixed-order double sums), max_norm = 1.5 mean + 2 std of the last `window` applied norms, clip
+ * coefficient min(1, max_norm / (norm + 1e-6)), AdamW-amsgrad update in torch's single-tensor op order.
+ * state: gb_adamw_state_doubles(window) device doubles, zero-initialised by the caller except the window entries it seeds
+ * ([4] = length, [8..] = values; the reference seeds one entry of 3000); after a call [0] = step, [1] = ||g||, [2] = max_norm,
+ * [3] = clip coefficient.  scratch: gb_adamw_scratch_doubles() device doubles.  clip = 0: plain AdamW-amsgrad. */
+size_t gb_adamw_state_doubles(int window);
+size_t gb_adamw_scratch_doubles(void);
+int gb_adamw_amsgrad_clip(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, size_t n,
+                          float lr, float beta1, float beta2, float eps, float weight_decay, double* state, int window, int clip,
+                          double* scratch, void* stream);
+
 /* ---- geometric validity of generated ring graphs -----------------------------------------------
  * gb_check_stability replaces the per-molecule Python of check_stability (analyze/analyze.py:50-100): positions2adj
  * (utils/helpers.py:172-196), minimum-distance test, connectivity (networkx), find_triplets_quads / angel3 / angel4

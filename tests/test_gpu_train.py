@@ -276,6 +276,48 @@ def test_sample_chain_matches_reference_golden():
     assert torch.equal(chain[0, :, :, 3:].cpu(), ref[0, :, :, 3:])                  # one-hot ring types of the final molecules
 
 
+def test_fused_adamw_amsgrad_clip_matches_torch():
+    """gb_adamw_amsgrad_clip vs the reference's combination: edm/utils.gradient_clipping (Queue seeded with 3000, numpy mean / std,
+    torch.nn.utils.clip_grad_norm_) followed by torch.optim.AdamW(amsgrad=True, weight_decay=1e-12) (train_edm.py:22-24, 71-82),
+    over steps whose gradient norms first fill the window and then get clipped."""
+    dev = _dev()
+    from gaudi_b200 import train_utils as TU
+    torch.manual_seed(0)
+    shapes = [(192, 386), (192,), (1, 192), (3, 5, 7)]
+    ref_p = [torch.nn.Parameter(torch.randn(*s_, device=dev) * 0.1) for s_ in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    ref_opt = torch.optim.AdamW(ref_p, lr=1e-3, weight_decay=1e-12, amsgrad=True)
+    queue = TU.Queue(max_len=5)
+    queue.add(3000)
+    holder = torch.nn.ParameterList(ref_p)
+    ours = TU.FusedAdamWClip(our_p, lr=1e-3, weight_decay=1e-12, clip=True, window=5, first_norm=3000.0)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    scales = [1.0, 1.2, 0.8, 1.1, 0.9, 1.0, 40.0, 1.0, 0.05, 25.0, 1.0, 1.0]      # steps 6 and 9 exceed 1.5 mean + 2 std -> clipped
+    for step, sc in enumerate(scales):
+        grads = [torch.randn(p.shape, device=dev, generator=gen) * sc for p in ref_p]
+        ref_opt.zero_grad(); ours.zero_grad()
+        for p, q, g_ in zip(ref_p, our_p, grads):
+            p.grad = g_.clone(); q.grad.copy_(g_)
+        max_norm = 1.5 * queue.mean() + 2 * queue.std()
+        ref_norm = float(TU.gradient_clipping(holder, queue))
+        ref_opt.step()
+        ours.step()
+        assert abs(float(ours.last_grad_norm) - ref_norm) <= 1e-5 * ref_norm, step
+        assert abs(float(ours.last_max_norm) - max_norm) <= 1e-6 * max_norm, step
+        for p, q in zip(ref_p, our_p):
+            assert maxabs(q, p) <= 2e-6 * max(1.0, float(p.abs().max())), (step, float(maxabs(q, p)))
+    assert sorted(float(v) for v in ours.state[8:8 + 5].cpu()) == pytest.approx(sorted(queue.items), rel=1e-5)
+    # plain AdamW-amsgrad (clip off) over a few more steps
+    ref2 = [torch.nn.Parameter(torch.randn(64, 64, device=dev))]
+    our2 = [torch.nn.Parameter(ref2[0].detach().clone())]
+    o_ref, o_ours = torch.optim.AdamW(ref2, lr=3e-3, weight_decay=1e-2, amsgrad=True), TU.FusedAdamWClip(our2, lr=3e-3, weight_decay=1e-2, clip=False)
+    for _ in range(5):
+        g_ = torch.randn(64, 64, device=dev, generator=gen)
+        ref2[0].grad = g_.clone(); our2[0].grad.copy_(g_)
+        o_ref.step(); o_ours.step()
+    assert maxabs(our2[0], ref2[0]) <= 2e-6
+
+
 def test_tensor_core_wgrad_matches_fp64():
     """gb_wgrad (tcgen05, MN-major operands, 3xTF32, split-K): C = G^T X on strided views, with accumulation, through the
     deterministic two-phase reduction (scratch) and through the atomic path (no scratch)."""
