@@ -451,7 +451,7 @@ def run_config4(args):
     torch.cuda.set_device(dev)
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    n, B, H = 10, args.batch or 10000, 196
+    n, B, H = 10, args.batch or 10000, args.hidden
     a, model, pred, nodes_dist, prop = bench_shapes.models("cata", dev, nf_pred=H)
     nm, em = gb.build_masks(torch.full((B,), n), n, False, device=dev)
     z = runtime.noise(nm.reshape(-1).contiguous(), B, n, 4, 1.0, 3, 0)
@@ -473,7 +473,7 @@ def run_config4(args):
     line = {"metric": "predictor forward + input-gradient molecules/sec", "value": B / (ms * 1e-3), "unit": "molecules/s", "n_gpus": 1,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[3]: EGNN predictor forward + input gradient, n = 10 rings, batch 10 000, hidden 196 x 12 layers",
+            "config": {"workload": "configs[3]: EGNN predictor forward + input gradient, n = 10 rings, batch %d, hidden %d x 12 layers" % (B, H),
                        "bench_config": 4, "precision": PRECISION, "algorithmic_tflops_achieved": fl / ms * 1e-9},
             "gpu_launches": runtime.launch_count()}
     print(json.dumps(line), flush=True)
@@ -514,6 +514,7 @@ def main():
     ap.add_argument("--full-batch", type=int, default=0, help="batch of the complete sample_guidance() call (0: batch / 5)")
     ap.add_argument("--no-full", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--hidden", type=int, default=196, help="config 4: predictor hidden width (196 = prediction_args, 192 / 256 = the sweep's widths)")
     ap.add_argument("--sweep", action="store_true", help="config 4: also print the nodes x batch x hidden sweep")
     ap.add_argument("--profile-only", action="store_true", help="few steps, no e2e / cpu legs (for ncu)")
     args = ap.parse_args()

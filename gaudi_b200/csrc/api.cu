@@ -196,9 +196,6 @@ static void parse_gemm_mode(gb_net* net) {
     net->tc_den = all || m.find("den") != std::string::npos;
     net->tc_pred = all || m.find("pred") != std::string::npos;
     if (m == "fp32") net->tc_lin = net->tc_den = net->tc_pred = 0;
-    // hidden widths above 208 (config-4 sweep, H = 256): the edge kernels' two-stage operand ring plus scratch exceeds the
-    // 227 KB shared-memory limit, so those two families stay on the FP32 engine; the node Linear still uses tcgen05.
-    if (tc_np(net->HP) > 208) net->tc_den = net->tc_pred = 0;
 }
 
 static void run_lin(const gb_net* n, LinArgs& a, cudaStream_t s) {

@@ -222,7 +222,8 @@ __host__ __device__ constexpr int geo_words(int nf) { return GEO_HDR + 128 * nf;
 // ---------------------------------------------------------------------------------------------------------------------
 template <int NP, int FMT>
 struct Rings {
-    static constexpr int SA = 2, SW = 3;
+    // NP = 256 (hidden 256): a two-slot weight ring (one hi + one mix half-atom) is what fits next to the scratch in 227 KB
+    static constexpr int SA = 2, SW = NP > 208 ? 2 : 3;
     static constexpr int A_BYTES = 128 * ATOM_ROW_BYTES;     // one hi or lo image of a [128 x 32] activation atom
     static constexpr int A_STAGE = 2 * A_BYTES;
     static constexpr int W_BYTES = NP * ATOM_ROW_BYTES;      // one hi or lo image of a [NP x 32] weight atom

@@ -43,7 +43,7 @@ struct TcEdgeCfg {
     static constexpr int SMEM = R::BYTES + 1024 + BAR_BYTES + SCRATCH;
     static constexpr int ACC_STRIDE = NP <= 64 ? 64 : 256;   // two accumulators: the MMAs of tile k+1 run during the epilogue of tile k
     static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-    static_assert(NP > 208 || SMEM <= 232448, "shared memory budget");   // NP = 256 is instantiated but never launched (api.cu)
+    static_assert(SMEM <= 232448, "shared memory budget");
 };
 
 template <int NP, int MODE>

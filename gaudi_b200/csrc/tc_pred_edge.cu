@@ -83,7 +83,7 @@ struct TcFwdCfg : TcPredCfg<NP> {
     static constexpr int NGEO = 3;
     static constexpr int SCRATCH = 6 * NP * 4 + 2 * B::NPARTS * 128 * 4 + B::NPARTS * 128 * B::EF_STRIDE * 4 + NGEO * GEO_WORDS * 4 + 128 * 3 * 4 + PS_BYTES + 64;
     static constexpr int SMEM = B::R::BYTES + 1024 + B::BAR_BYTES + SCRATCH;
-    static_assert(NP > 208 || SMEM <= 232448, "shared memory budget (forward)");
+    static_assert(SMEM <= 232448, "shared memory budget (forward)");
 };
 
 template <int NP, bool SAVE>
@@ -397,7 +397,7 @@ struct TcBwdCfg : TcPredCfg<NP> {
     static constexpr int SCRATCH = 6 * NP * 4 + 2 * B::NPARTS * 128 * 4 + SV_SLOTS * B::SV_SLOT_BYTES + (B::NWORK / 32) * STG_WARP_FLOATS * 4 +
                                    2 * GEO_WORDS * 4 + 64;
     static constexpr int SMEM = B::R::BYTES + 1024 + B::BAR_BYTES + SCRATCH;
-    static_assert(NP > 208 || SMEM <= 232448, "shared memory budget (backward)");
+    static_assert(SMEM <= 232448, "shared memory budget (backward)");
 };
 
 template <int SLOTS>

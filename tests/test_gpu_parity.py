@@ -273,7 +273,7 @@ def test_tiles_with_many_tiny_molecules_match_oracle():
 
 
 def test_hidden_256_matches_oracle():
-    """BASELINE config 4 sweeps hidden 256: node Linears on tcgen05 (NP = 256), edge kernels on the FP32 engine."""
+    """BASELINE config 4 sweeps hidden 256: every GEMM on tcgen05 (NP = 256: two-slot weight ring, tc_common.cuh)."""
     dev = _dev()
     args, model, pred, prop = build_models("cata", dev, hidden=(256, 256), layers=(2, 3))
     wd, wp = cpu_weights(model, pred)
