@@ -71,6 +71,7 @@ struct gb_net {
     int F, H, HP, L, n_sub, out_nf, attention, use_tanh;
     float coords_range, norm_constant, normf;
     int tc_lin = 0, tc_den = 0, tc_pred = 0;   // which kernel families run on tcgen05 (GAUDI_B200_GEMM)
+    int lin_fmt = 2;        // image format of the node-Linear weights: 2 = hi + bf16 mix (2 MMAs per K step), 0 = hi | lo (3xTF32; GAUDI_B200_LIN_MIX=0)
     float* buf = nullptr;
     size_t n_floats = 0;
     size_t emb_w, emb_b, out_w, out_b;      // raw (unpacked) small heads
@@ -126,8 +127,8 @@ struct Packer {
     size_t tc_block2(const float* w, int ld, int k0, int n0, int k1, int n1, int Kv, int Nv, int transpose) {
         const size_t sz = tc_size(net->HP);
         size_t o = take(2 * sz);
-        tc_at(o, w, ld, k0, n0, Kv, Nv, net->HP, transpose ? 0 : 1);
-        tc_at(o + sz, w, ld, k1, n1, Kv, Nv, net->HP, transpose ? 0 : 1);
+        tc_at(o, w, ld, k0, n0, Kv, Nv, net->HP, transpose ? 0 : 1, net->lin_fmt);
+        tc_at(o + sz, w, ld, k1, n1, Kv, Nv, net->HP, transpose ? 0 : 1, net->lin_fmt);
         return o;
     }
     size_t vec(const float* v, int n, int np) {      // zero-padded copy of a vector
@@ -163,8 +164,8 @@ struct Packer {
         wt = block(w, H, 0, 0, H, H, HP, 1);
         bias = vec(b, H, HP);
         if (nt) *nt = block(w, H, 0, 0, H, H, HP, 0);
-        if (tcw) *tcw = tc_block(w, H, 0, 0, H, H, 1, edge ? 2 : 0);
-        if (tcnt) *tcnt = tc_block(w, H, 0, 0, H, H, 0, edge ? 2 : 0);
+        if (tcw) *tcw = tc_block(w, H, 0, 0, H, H, 1, edge ? 2 : net->lin_fmt);
+        if (tcnt) *tcnt = tc_block(w, H, 0, 0, H, H, 0, edge ? 2 : net->lin_fmt);
     }
     void node_mlp(NodeMlpW& n, const float* w1, const float* b1, const float* w2, const float* b2, bool want_nt) {
         const int H = net->H, HP = net->HP;
@@ -196,9 +197,12 @@ static void parse_gemm_mode(gb_net* net) {
     net->tc_den = all || m.find("den") != std::string::npos;
     net->tc_pred = all || m.find("pred") != std::string::npos;
     if (m == "fp32") net->tc_lin = net->tc_den = net->tc_pred = 0;
+    const char* lm = getenv("GAUDI_B200_LIN_MIX");
+    net->lin_fmt = (lm && lm[0] == '0') ? 0 : 2;
 }
 
 static void run_lin(const gb_net* n, LinArgs& a, cudaStream_t s) {
+    a.mix = n->lin_fmt == 2;
     if (n->tc_lin && a.wt_tc) launch_lin_tc(n->HP, a, a.wt_tc, s);
     else launch_lin(n->HP, a, s);
 }

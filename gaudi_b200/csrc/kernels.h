@@ -50,6 +50,7 @@ struct LinArgs {
     const float* aux; int ldaux;            // EPI_MUL_DSILU: pre-activation
     int M; int ncb; int epi;
     int res_cb;                             // EPI_ADD_RES: column block that receives the residual (-1: all)
+    int mix;                                // tcgen05 path: wt_tc is a hi + bf16-mix image (TF32 MMA + one bf16 MMA per K step) instead of hi | lo
 };
 void launch_lin(int HP, const LinArgs& a, cudaStream_t s);
 // tcgen05 / 3xTF32 version (tc_lin_kernel.cu); H = row stride / hidden width of the node tensors (== HP)

@@ -147,29 +147,34 @@ void launch_lin(int HP, const LinArgs& a, cudaStream_t s) {
 // tiny-K / tiny-N heads
 // ------------------------------------------------------------------------------------------------
 __global__ void embed_in_kernel(EmbedInArgs a) {
-    // one thread per (node, output feature); K = F+1 <= 16
-    const int F = a.D - 3;
-    const long long total = (long long)a.n_nodes * a.HP;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int node = (int)(idx / a.HP), c = (int)(idx % a.HP);
+    // one thread per (node, 4 output features), one 16-byte store each (HBM-write-bound: n_nodes x HP x 4 B); K = F+1 <= 16.
+    // HP is a multiple of 4 and so is H for every supported width, but the bounds are checked per element anyway.
+    const int F = a.D - 3, q4 = a.HP >> 2;
+    const int total = a.n_nodes * q4;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int node = idx / q4, c0 = (idx - node * q4) << 2;
         const float mk = a.node_mask[node];
         const float* zr = a.z + (size_t)node * a.D;
-        float v = 0.f;
-        if (c < a.H) {
-            const float* wr = a.w + (size_t)c * (F + 1);
-            v = a.b[c];
-            for (int k = 0; k < F; ++k) v = fmaf(zr[3 + k] * mk, wr[k], v);
-            const float t = a.t_per_mol ? a.t_ptr[node / a.N] : a.t_ptr[0];
-            v = fmaf(t, wr[F], v);
+        const float t = a.t_per_mol ? a.t_ptr[node / a.N] : a.t_ptr[0];
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = c0 + e;
+            v[e] = 0.f;
+            if (c < a.H) {
+                const float* wr = a.w + (size_t)c * (F + 1);
+                float acc = a.b[c];
+                for (int k = 0; k < F; ++k) acc = fmaf(zr[3 + k] * mk, wr[k], acc);
+                v[e] = fmaf(t, wr[F], acc);
+            }
         }
-        a.h[idx] = v;
-        if (c < 3) a.x[(size_t)node * 3 + c] = zr[c] * mk;
+        *reinterpret_cast<float4*>(a.h + (size_t)node * a.HP + c0) = make_float4(v[0], v[1], v[2], v[3]);
+        if (c0 == 0) { a.x[(size_t)node * 3] = zr[0] * mk; a.x[(size_t)node * 3 + 1] = zr[1] * mk; a.x[(size_t)node * 3 + 2] = zr[2] * mk; }
     }
 }
 
 void launch_embed_in(const EmbedInArgs& a, cudaStream_t s) {
-    const long long total = (long long)a.n_nodes * a.HP;
+    const long long total = (long long)a.n_nodes * (a.HP >> 2);
     int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
     embed_in_kernel<<<blocks, 256, 0, s>>>(a);
 }
@@ -193,15 +198,20 @@ void launch_embed_plain(const float* h_in, int K, const float* w, const float* b
 }
 
 __global__ void embed_out_kernel(EmbedOutArgs a) {
-    // one warp per node, lanes stride over k; n_out <= 16
+    // one warp per node: the row of h is read once (lane l keeps columns l, l+32, ...; H <= 256), then n_out <= 16 dot products
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int node = warp; node < a.n_nodes; node += nwarps) {
         const float* hr = a.h + (size_t)node * a.HP;
         const float mk = a.node_mask[node];
+        float hv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const int k = lane + 32 * i; hv[i] = k < a.H ? hr[k] : 0.f; }
         for (int o = 0; o < a.n_out; ++o) {
+            const float* wr = a.w + (size_t)o * a.H;
             float p = 0.f;
-            for (int k = lane; k < a.H; k += 32) p = fmaf(hr[k], a.w[(size_t)o * a.H + k], p);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const int k = lane + 32 * i; if (k < a.H) p = fmaf(hv[i], wr[k], p); }
 #pragma unroll
             for (int off = 16; off; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
             if (lane == 0) a.out[(size_t)node * a.ldo + o] = (p + a.b[o]) * mk;

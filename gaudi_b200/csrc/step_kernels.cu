@@ -333,21 +333,27 @@ void launch_pool_mean(const float* hout, const float*, int B, int N, int n_out, 
 }
 
 __global__ void head_bwd_kernel(HeadBwdArgs a) {
-    const long long total = (long long)a.B * a.N * a.HP;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int node = (int)(idx / a.HP), c = (int)(idx % a.HP);
-        float v = 0.f;
-        if (c < a.H) {
-            const int b = node / a.N;
-            for (int o = 0; o < a.n_out; ++o) v = fmaf(a.g_pred[b * a.n_out + o], a.w[(size_t)o * a.H + c], v);
-            v *= a.node_mask[node] / (float)a.N;
+    // one thread per (node, 4 columns), one 16-byte store each
+    const int q4 = a.HP >> 2, total = a.B * a.N * q4;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int node = idx / q4, c0 = (idx - node * q4) << 2;
+        const int b = node / a.N;
+        const float sc = a.node_mask[node] / (float)a.N;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = c0 + e;
+            float acc = 0.f;
+            if (c < a.H)
+                for (int o = 0; o < a.n_out; ++o) acc = fmaf(a.g_pred[b * a.n_out + o], a.w[(size_t)o * a.H + c], acc);
+            v[e] = c < a.H ? acc * sc : 0.f;
         }
-        a.gh[idx] = v;
+        *reinterpret_cast<float4*>(a.gh + (size_t)node * a.HP + c0) = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
 
 void launch_head_bwd(const HeadBwdArgs& a, cudaStream_t s) {
-    const long long total = (long long)a.B * a.N * a.HP;
+    const long long total = (long long)a.B * a.N * (a.HP >> 2);
     head_bwd_kernel<<<(int)min((long long)148 * 16, (total + 255) / 256), 256, 0, s>>>(a);
 }
 

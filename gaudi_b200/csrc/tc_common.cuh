@@ -201,6 +201,19 @@ __device__ __forceinline__ void store_kstep_mix(unsigned char* atom_hi, unsigned
     *reinterpret_cast<uint4*>(atom_mix + o1) = make_uint4(pack16<FMT>(ha.x, ha.y), pack16<FMT>(hb.x, hb.y), pack16<FMT>(hc.x, hc.y), pack16<FMT>(hd.x, hd.y));
 }
 
+// One 16-byte chunk c (4 consecutive k) of row r in the hi + mix format, for builders that own 4 floats per row instead of a whole
+// K step: the hi image gets the TF32 parts; of the K step's mix chunks (2q: residuals, 2q + 1: TF32 parts, q = c / 2) this thread
+// writes the 8 bytes that belong to its four k (the lower half for even c, the upper half for odd c).
+template <int FMT>
+__device__ __forceinline__ void store_chunk_mix(unsigned char* atom_hi, unsigned char* atom_mix, int r, int c, float4 x) {
+    const f2 ha = make_float2(tf32_hi(x.x), tf32_hi(x.y)), hb = make_float2(tf32_hi(x.z), tf32_hi(x.w));
+    const f2 la = fma2(ha, f2s(-1.f), lo2(x)), lb = fma2(hb, f2s(-1.f), hi2(x));
+    *reinterpret_cast<float4*>(atom_hi + swz_offset(r, c)) = cat2(ha, hb);
+    const int c0 = c & ~1, sub = (c & 1) << 3;
+    *reinterpret_cast<uint2*>(atom_mix + swz_offset(r, c0) + sub) = make_uint2(pack16<FMT>(la.x, la.y), pack16<FMT>(lb.x, lb.y));
+    *reinterpret_cast<uint2*>(atom_mix + swz_offset(r, c0 + 1) + sub) = make_uint2(pack16<FMT>(ha.x, ha.y), pack16<FMT>(hb.x, hb.y));
+}
+
 // named barriers of the worker warps: ids 1-4 = the four warps sharing a TMEM lane quadrant (one per part; they exchange
 // per-row partial sums), 5-12 = the four warps of one part (they cover the 128 rows of a chunk), 13 = all workers
 __device__ __forceinline__ void bar_named(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }

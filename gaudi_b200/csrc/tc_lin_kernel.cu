@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, GB_LIN_CTAS) tc_lin_ker
     const int na1 = (a.K1 + ATOM_K - 1) / ATOM_K, na2 = (a.K2 + ATOM_K - 1) / ATOM_K, na = na1 + na2;
     const size_t atom_floats = (size_t)2 * NP * ATOM_K;
     const float* wcb = wimg + (size_t)cb * na * atom_floats;
-    constexpr uint32_t idesc = instr_desc_tf32(NP);
+    constexpr uint32_t idesc = instr_desc_tf32(NP), idesc_mix = instr_desc_mix(NP, MIX_BF16);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -114,11 +114,19 @@ __global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, GB_LIN_CTAS) tc_lin_ker
                     fence_after_sync();
                     const uint32_t a_hi = smem_u32(base + s * CF::STAGE_BYTES), a_lo = a_hi + CF::A_BYTES;
                     const uint32_t w_hi = a_hi + 2 * CF::A_BYTES, w_lo = w_hi + CF::W_BYTES;
-                    for (int kk = 0; kk < ksteps; ++kk) {
-                        const uint32_t ko = kk * 32;
-                        mma_tf32(d_tmem, smem_desc(a_lo + ko), smem_desc(w_hi + ko), idesc, (j | kk) != 0);
-                        mma_tf32(d_tmem, smem_desc(a_hi + ko), smem_desc(w_lo + ko), idesc, 1);
-                        mma_tf32(d_tmem, smem_desc(a_hi + ko), smem_desc(w_hi + ko), idesc, 1);
+                    if (a.mix) {                                   // TF32 product + both correction terms as one bf16 MMA (tc_common.cuh)
+                        for (int kk = 0; kk < ksteps; ++kk) {
+                            const uint32_t ko = kk * 32;
+                            mma_tf32(d_tmem, smem_desc(a_hi + ko), smem_desc(w_hi + ko), idesc, (j | kk) != 0);
+                            mma_f16(d_tmem, smem_desc(a_lo + ko), smem_desc(w_lo + ko), idesc_mix, 1);
+                        }
+                    } else {
+                        for (int kk = 0; kk < ksteps; ++kk) {
+                            const uint32_t ko = kk * 32;
+                            mma_tf32(d_tmem, smem_desc(a_lo + ko), smem_desc(w_hi + ko), idesc, (j | kk) != 0);
+                            mma_tf32(d_tmem, smem_desc(a_hi + ko), smem_desc(w_lo + ko), idesc, 1);
+                            mma_tf32(d_tmem, smem_desc(a_hi + ko), smem_desc(w_hi + ko), idesc, 1);
+                        }
                     }
                     mma_commit(&empty[s]);
                 }
@@ -162,7 +170,11 @@ __global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, GB_LIN_CTAS) tc_lin_ker
             if (rr > 0) mbar_wait(&empty[s], (rr - 1) & 1);
             unsigned char* a_hi = base + s * CF::STAGE_BYTES;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { const int f = bt + 256 * i; store_split(a_hi, a_hi + CF::A_BYTES, f >> 3, f & 7, x[i]); }
+            for (int i = 0; i < 4; ++i) {
+                const int f = bt + 256 * i;
+                if (a.mix) store_chunk_mix<MIX_BF16>(a_hi, a_hi + CF::A_BYTES, f >> 3, f & 7, x[i]);
+                else store_split(a_hi, a_hi + CF::A_BYTES, f >> 3, f & 7, x[i]);
+            }
             fence_proxy_async();
             mbar_arrive(&full_a[s]);
             if (tid == 64) TL(0, q, 200 + q);
