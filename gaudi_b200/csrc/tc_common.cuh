@@ -233,10 +233,10 @@ __host__ __device__ constexpr int geo_words(int nf) { return GEO_HDR + 128 * nf;
 // that read w_hi first, releases that slot, then the 16-bit products that read w_mix: three slots (instead of two stages of
 // hi + mix) keep one half-atom in flight ahead of the tensor pipe and free NP x 128 B of shared memory for the staged P rows.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int NP, int FMT>
+template <int NP, int FMT, int SW_ = (NP > 208 ? 2 : 3)>
 struct Rings {
     // NP = 256 (hidden 256): a two-slot weight ring (one hi + one mix half-atom) is what fits next to the scratch in 227 KB
-    static constexpr int SA = 2, SW = NP > 208 ? 2 : 3;
+    static constexpr int SA = 2, SW = SW_;
     static constexpr int A_BYTES = 128 * ATOM_ROW_BYTES;     // one hi or lo image of a [128 x 32] activation atom
     static constexpr int A_STAGE = 2 * A_BYTES;
     static constexpr int W_BYTES = NP * ATOM_ROW_BYTES;      // one hi or lo image of a [NP x 32] weight atom

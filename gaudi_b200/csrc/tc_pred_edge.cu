@@ -11,6 +11,10 @@
 #ifndef GB_PRED_NPARTS
 #define GB_PRED_NPARTS 4
 #endif
+#ifndef GB_BWD_SW
+#define GB_BWD_SW 3         // backward: weight half-atom slots
+#define GB_BWD_SVS 6        // backward: saved-activation ring slots (8 KB each)
+#endif
 
 namespace gb {
 using namespace tc;
@@ -33,7 +37,7 @@ struct TcPredCfg {
     // gradients of the backward and it overflows on the forward too (random-init trajectories reach |x| ~ 1e3, i.e. squared
     // distances and pre-activations beyond 65504: the 1000-step chain test diverged with fp16)
     using R = Rings<NP, MIX_BF16>;
-    using RB = Rings<NP, MIX_BF16>;
+    using RB = Rings<NP, MIX_BF16, (NP > 208 ? 2 : GB_BWD_SW)>;
     static constexpr int A_BYTES = R::A_BYTES;
     static constexpr int A_STAGE = R::A_STAGE;
     static constexpr int NPARTS = GB_PRED_NPARTS;                          // worker parts of 4 warps; part p owns 16-column chunks ch == p (mod 4)
@@ -392,11 +396,11 @@ struct TcBwdCfg : TcPredCfg<NP> {
     static constexpr int THREADS = B::THREADS + 64;
     static constexpr int GEO_NF = 8;                                       // local row node, g_phi, d (3), g_u (3)
     static constexpr int GEO_WORDS = geo_words(GEO_NF);
-    static constexpr int SV_SLOTS = 6;                                     // saved-activation ring: 6 x 8 KB
+    static constexpr int SV_SLOTS = NP > 208 ? 6 : GB_BWD_SVS;             // saved-activation ring: slots of 8 KB
     static constexpr int STG_WARP_FLOATS = 32 * 8;                         // per-warp transpose block of epilogue 2: 32 rows x 8 columns
     static constexpr int SCRATCH = 6 * NP * 4 + 2 * B::NPARTS * 128 * 4 + SV_SLOTS * B::SV_SLOT_BYTES + (B::NWORK / 32) * STG_WARP_FLOATS * 4 +
                                    2 * GEO_WORDS * 4 + 64;
-    static constexpr int SMEM = B::R::BYTES + 1024 + B::BAR_BYTES + SCRATCH;
+    static constexpr int SMEM = B::RB::BYTES + 1024 + B::BAR_BYTES + SCRATCH;
     static_assert(SMEM <= 232448, "shared memory budget (backward)");
 };
 
@@ -434,14 +438,14 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
     // 1024-byte alignment by pointer arithmetic on the __shared__ array: the compiler keeps the address space (LDS / STS
     // instead of generic LD / ST for every staging and operand access)
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::R::BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::RB::BYTES);
     typename CF::RB rg; rg.carve(base, bars);
-    uint64_t* d1_full = bars + CF::R::NBARS; uint64_t* d2_full = d1_full + 1; uint64_t* d1_empty = d2_full + 1; uint64_t* d2_empty = d1_empty + 1;
+    uint64_t* d1_full = bars + CF::RB::NBARS; uint64_t* d2_full = d1_full + 1; uint64_t* d1_empty = d2_full + 1; uint64_t* d2_empty = d1_empty + 1;
     uint64_t* sv_full = d2_empty + 1; uint64_t* sv_empty = sv_full + SVS;
     uint64_t* geo_full = sv_empty + SVS; uint64_t* geo_empty = geo_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(geo_empty + 2);
-    volatile uint32_t* sv_round = reinterpret_cast<volatile uint32_t*>(base + CF::R::BYTES + 384);     // [SV_SLOTS], inside the barrier block
-    float* vec_s = reinterpret_cast<float*>(base + CF::R::BYTES + CF::BAR_BYTES);     // [6][NP]: w_r, w_a, -, att_w, -, wc_last
+    volatile uint32_t* sv_round = reinterpret_cast<volatile uint32_t*>(base + CF::RB::BYTES + 384);     // [SV_SLOTS], inside the barrier block
+    float* vec_s = reinterpret_cast<float*>(base + CF::RB::BYTES + CF::BAR_BYTES);     // [6][NP]: w_r, w_a, -, att_w, -, wc_last
     float* red_s = vec_s + 6 * NP;                                                       // [2][NPARTS][128]
     unsigned char* sv_buf = reinterpret_cast<unsigned char*>(red_s + 2 * CF::NPARTS * 128);   // saved-activation ring
     float* stg_s = reinterpret_cast<float*>(sv_buf + SVS * CF::SV_SLOT_BYTES);           // [16 warps][32][8]

@@ -13,7 +13,7 @@ from typing import Dict, List, Optional, Tuple
 
 import torch
 
-from . import _lib
+from . import _lib, ops
 from .graph import Topology, build_topology
 
 _VP = C.c_void_p
@@ -253,12 +253,9 @@ def denoiser_forward(dyn, t, xh: torch.Tensor, node_mask: torch.Tensor, edge_mas
     g = graph_for(node_mask, edge_mask, B, N)
     z = _f32c(xh)
     tt, per_mol = _time_tensor(t, B, xh.device)
-    eps = torch.empty_like(z)
     nbytes = _lib.lib().gb_denoiser_workspace_bytes(net.handle, g.handle)
     ws = workspace("den", xh.device).get(nbytes, xh.device)
-    _lib.check(_lib.lib().gb_denoiser_forward(net.handle, g.handle, _ptr(z), _ptr(tt), per_mol, _ptr(eps),
-                                              int(scrub_all), _ptr(stats), _ptr(ws), ws.numel(), _stream()))
-    return eps
+    return ops.denoiser_forward(net.handle.value, g.handle.value, z, tt, per_mol, bool(scrub_all), stats, ws)
 
 
 class _PredictorFn(torch.autograd.Function):
@@ -272,12 +269,10 @@ class _PredictorFn(torch.autograd.Function):
         z = _f32c(xh)
         tt, per_mol = _time_tensor(t, B, xh.device)
         need_grad = bool(ctx.needs_input_grad[0])
-        out = torch.empty(B, pred_module.hyper["out_nf"], dtype=torch.float32, device=xh.device)
         nbytes = _lib.lib().gb_predictor_workspace_bytes(net.handle, g.handle, int(need_grad))
         wsp = workspace("pred_grad" if need_grad else "pred", xh.device)
         ws = wsp.get(nbytes, xh.device)
-        _lib.check(_lib.lib().gb_predictor_forward(net.handle, g.handle, _ptr(z), _ptr(tt), per_mol, _ptr(out),
-                                                   int(need_grad), _ptr(ws), ws.numel(), _stream()))
+        out = ops.predictor_forward(net.handle.value, g.handle.value, z, tt, per_mol, pred_module.hyper["out_nf"], need_grad, ws)
         if need_grad:
             wsp.generation += 1
             ctx.gen = wsp.generation
@@ -293,10 +288,7 @@ class _PredictorFn(torch.autograd.Function):
         B, N, D = ctx.shape
         gp = _f32c(g_pred)
         with torch.cuda.device(gp.device):
-            gz = torch.empty(B, N, D, dtype=torch.float32, device=gp.device)
-            ws = wsp.buf
-            _lib.check(_lib.lib().gb_predictor_input_grad(ctx.net.handle, ctx.g.handle, _ptr(gp), 0, _ptr(gz), _ptr(ws),
-                                                          ws.numel(), _stream()))
+            gz = ops.predictor_input_grad(ctx.net.handle.value, ctx.g.handle.value, gp, False, B, N, D, wsp.buf)
         return gz, None, None, None, None
 
 
@@ -316,17 +308,13 @@ def predictor_value_and_grad(pred_module, xh, node_mask, edge_mask, t, g_pred_ro
     g = graph_for(node_mask, edge_mask, B, N)
     z = _f32c(xh)
     tt, per_mol = _time_tensor(t, B, xh.device)
-    out = torch.empty(B, pred_module.hyper["out_nf"], dtype=torch.float32, device=xh.device)
     nbytes = _lib.lib().gb_predictor_workspace_bytes(net.handle, g.handle, 1)
     wsp = workspace("pred_grad", xh.device)
     ws = wsp.get(nbytes, xh.device)
     wsp.generation += 1
-    L = _lib.lib()
-    _lib.check(L.gb_predictor_forward(net.handle, g.handle, _ptr(z), _ptr(tt), per_mol, _ptr(out), 1, _ptr(ws),
-                                      ws.numel(), _stream()))
-    gz = torch.empty_like(z)
+    out = ops.predictor_forward(net.handle.value, g.handle.value, z, tt, per_mol, pred_module.hyper["out_nf"], True, ws)
     w = _f32c(g_pred_row).reshape(-1)
-    _lib.check(L.gb_predictor_input_grad(net.handle, g.handle, _ptr(w), 1, _ptr(gz), _ptr(ws), ws.numel(), _stream()))
+    gz = ops.predictor_input_grad(net.handle.value, g.handle.value, w, True, B, N, D, ws)
     return out, gz
 
 

@@ -348,3 +348,15 @@ def test_bench_reference_arm_contract():
         assert k in line, k
     assert line["impl"] == "reference" and line["unit"] == "molecules/s" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] in ("port", "reference")
+
+
+def test_torch_library_ops_registered_with_fake_kernels_and_no_cpu_kernel():
+    """north_star: the module forwards reach the C ABI through ``torch.ops.gaudi_b200.*`` custom ops (gaudi_b200/ops.py).  On a
+    CPU-only host they must exist, propagate shapes on meta tensors and refuse real CPU tensors (no fallback)."""
+    import gaudi_b200.ops  # noqa: F401
+    z, t, ws = torch.empty(4, 11, 4, device="meta"), torch.empty(1, device="meta"), torch.empty(16, device="meta")
+    assert torch.ops.gaudi_b200.denoiser_forward(0, 0, z, t, 0, False, None, ws).shape == (4, 11, 4)
+    assert torch.ops.gaudi_b200.predictor_forward(0, 0, z, t, 0, 5, True, ws).shape == (4, 5)
+    assert torch.ops.gaudi_b200.predictor_input_grad(0, 0, torch.empty(5, device="meta"), True, 4, 11, 4, ws).shape == (4, 11, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        torch.ops.gaudi_b200.denoiser_forward(0, 0, torch.zeros(4, 11, 4), torch.zeros(1), 0, False, None, torch.zeros(16))
