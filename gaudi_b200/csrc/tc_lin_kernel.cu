@@ -40,7 +40,12 @@ struct TcLinCfg {
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
     static constexpr int TMEM_COLS = 512;                 // two accumulators at columns 0 and 256
     static constexpr int NBUILD = 256;                    // warps 2-9
-    static constexpr int EPARTS = 2;                      // warps 10-17
+#ifndef GB_LIN_EPARTS
+#define GB_LIN_EPARTS 2
+#endif
+    // epilogue parts of 4 warps (a part covers the 128 TMEM lanes).  Four parts (26 warps, 72 registers) were measured in round 2:
+    // 0.098 -> 0.195 ms per launch -- the kernel is bound by the L1 / shared-memory data pipe (93 % busy), not by epilogue warps
+    static constexpr int EPARTS = NP > 208 ? 2 : GB_LIN_EPARTS;   // warps 10-17
     static constexpr int NEPI = 128 * EPARTS;
     static constexpr int THREADS = 64 + NBUILD + NEPI;
     static constexpr int STG_PITCH = 20;                  // floats per staged row: conflict-free float4 writes by row
