@@ -419,7 +419,7 @@ struct PredWs {
     float* x;        // [(L+1)][nn][3]
     float* pre4;     // [L][nn][HP]
     float *sv_d1, *sv_pre2, *sv_d3, *sv_tau;   // per layer strides below
-    size_t sv_stride, tau_stride;
+    size_t sv_stride, sv_stride_p, tau_stride;
     float *gh, *gh2, *gcat, *gpre4, *gPa, *gPb, *gx, *gx2, *gattr, *gpre1, *gd;
 };
 void carve_pred(Bump& b, const gb_net* n, const Graph& g, bool grad, PredWs& w) {
@@ -427,11 +427,14 @@ void carve_pred(Bump& b, const gb_net* n, const Graph& g, bool grad, PredWs& w) 
     w.h = b.get<float>(nn * HP); w.h2 = b.get<float>(nn * HP); w.s = b.get<float>(nn * HP);
     w.agg = b.get<float>(nn * HP); w.P = b.get<float>(nn * 2 * HP); w.hout = b.get<float>(nn * n->out_nf);
     w.x = b.get<float>((L + 1) * nn * 3);
-    w.sv_stride = (size_t)g.n_tiles * HP * GB_TM_HOST;
+    // saved activations per layer and tensor, in floats: the tensor-core kernels keep the two SiLU derivatives as 16-bit codes in
+    // planes of 8 columns ([tile][(H + 7) / 8][128 rows][8 codes], tc_common.cuh), the FP32 engine as fp32 [tile][HP][128]
+    w.sv_stride = n->tc_pred ? (size_t)g.n_tiles * ((n->H + 7) / 8) * (GB_TM_HOST * 16 / 4) : (size_t)g.n_tiles * HP * GB_TM_HOST;
+    w.sv_stride_p = (size_t)g.n_tiles * HP * GB_TM_HOST;        // pre2: fp32 in both engines
     w.tau_stride = (size_t)g.n_edges;
     if (grad) {
         w.pre4 = b.get<float>(L * nn * HP);
-        w.sv_d1 = b.get<float>(L * w.sv_stride); w.sv_pre2 = b.get<float>(L * w.sv_stride);
+        w.sv_d1 = b.get<float>(L * w.sv_stride); w.sv_pre2 = b.get<float>(L * w.sv_stride_p);
         w.sv_d3 = b.get<float>(L * w.sv_stride); w.sv_tau = b.get<float>(L * w.tau_stride + 1);
         w.gh = b.get<float>(nn * HP); w.gh2 = b.get<float>(nn * HP); w.gcat = b.get<float>(nn * 2 * HP);
         w.gpre4 = b.get<float>(nn * HP); w.gPa = b.get<float>(nn * HP); w.gPb = b.get<float>(nn * HP);
@@ -554,7 +557,7 @@ static PredEdgeArgs pred_edge_args(const gb_net* n, const PredLayer& Lr, const G
     a.x0 = w.x;
     if (grad) {
         a.x = w.x + (size_t)l * nn * 3; a.x_out = w.x + (size_t)(l + 1) * nn * 3;
-        a.sv_d1 = w.sv_d1 + l * w.sv_stride; a.sv_pre2 = w.sv_pre2 + l * w.sv_stride;
+        a.sv_d1 = w.sv_d1 + l * w.sv_stride; a.sv_pre2 = w.sv_pre2 + l * w.sv_stride_p;
         a.sv_d3 = w.sv_d3 + l * w.sv_stride; a.sv_tau = w.sv_tau + l * w.tau_stride;
     } else {                                  // inference: ping-pong between slots 1 and 2, slot 0 keeps x0
         a.x = l == 0 ? w.x : w.x + (size_t)(1 + ((l - 1) & 1)) * nn * 3;

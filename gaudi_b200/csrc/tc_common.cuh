@@ -214,6 +214,62 @@ __device__ __forceinline__ void store_chunk_mix(unsigned char* atom_hi, unsigned
     *reinterpret_cast<uint2*>(atom_mix + swz_offset(r, c0 + 1) + sub) = make_uint2(pack16<FMT>(ha.x, ha.y), pack16<FMT>(hb.x, hb.y));
 }
 
+// Saved activations of the predictor's input-gradient pass (round 2d): 8 instead of 12 bytes per edge, column and layer.
+// SiLU'(pre1) and SiLU'(pre3) of a tile are stored as 16-bit codes in planes [tile][k / 8][128 rows][8 codes] (16 bytes per row and
+// plane; a 16-column chunk = two planes = 4 KB contiguous, one bulk-TMA copy in the backward); pre2 stays fp32
+// ([tile][k / 4][128 rows][4], 8 KB per chunk).  The formats were chosen with an oracle error model (tests/sv_code_error_model.py:
+// autograd with quantised saved tensors on the reference goldens) and then measured on the GPU -- raw gradient max-abs error on
+// |g| ~ 2e-2 / relative drift of the guided 1000-step chain (bound 5e-3), whose diverging random-init molecules have clipped
+// gradients and therefore feel the RELATIVE error of pre2:
+//     fp32 everything (round 2c)        6e-8 / 6.6e-4
+//     fp16 derivatives + fp16 pre2    1.1e-6 / 1.1e-2        fixed-point derivatives + fp16 pre2    2.4e-7 / 9.4e-3
+//     fixed-point + bf16 pre2         1.9e-6 / 4.0e-2        fixed-point derivatives + 24-bit pre2  7e-8 .. 1e-7 / 1.4e-3 .. 5.3e-3
+//                                                            (three encoders of equal nominal accuracy: the chain is chaotic)
+//     fixed-point derivatives + fp32 pre2: this file.
+constexpr int SV_PLANE_BYTES = 128 * 16;
+__host__ __device__ constexpr int sv_planes(int H) { return (H + 7) / 8; }
+// 16-bit codes.  SV_FX (the SiLU derivatives, which lie in [-0.0998, 1.0998]): fixed point, n = round(d * 52428 + 6554) -- built
+// without integer conversions as the low mantissa bits of  y = fma(d, 52428, 2^23 + 6554)  and decoded as (y - (2^23 + 6554)) / 52428,
+// exact for d = 0.  Max error 9.5e-6 everywhere; fp16 has an ulp of 9.8e-4 for d in [1, 1.1) and 4.9e-4 in [0.5, 1), where most of the
+// gradient flows.  A NaN derivative (pre1 = -inf) is not representable and decodes to a finite value; the NaN of such a molecule
+// still reaches its gradient through pre2 and the forward values, which keep NaN / inf.
+// SV_H / SV_H_SAT / SV_BF: fp16, fp16 saturated to +-65504, bf16 (the experiments of the table above).
+enum SvFmt { SV_H = 0, SV_H_SAT = 1, SV_BF = 2, SV_FX = 3 };
+constexpr float SV_FX_SCALE = 52428.f, SV_FX_BIAS = 8388608.f + 6554.f, SV_FX_INV = 1.f / 52428.f;
+template <int FMT>
+__device__ __forceinline__ uint32_t sv_pack2(float lo, float hi) {
+    if (FMT == SV_H) { const __half2 v = __floats2half2_rn(lo, hi); return *reinterpret_cast<const uint32_t*>(&v); }
+    if (FMT == SV_BF) { const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<const uint32_t*>(&v); }
+    if (FMT == SV_H_SAT) {
+        uint32_t d;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+        return d;
+    }
+    const float a = fmaf(lo, SV_FX_SCALE, SV_FX_BIAS), b = fmaf(hi, SV_FX_SCALE, SV_FX_BIAS);
+    return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x5410);
+}
+template <int FMT>
+__device__ __forceinline__ f2 sv_unpack2(uint32_t v) {
+    if (FMT == SV_H || FMT == SV_H_SAT) return __half22float2(*reinterpret_cast<const __half2*>(&v));
+    if (FMT == SV_BF) return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+    const uint32_t m = __float_as_uint(8388608.f);
+    const f2 y = make_float2(__uint_as_float(__byte_perm(v, m, 0x7610)), __uint_as_float(__byte_perm(v, m, 0x7632)));
+    return mul2(add2(y, f2s(-SV_FX_BIAS)), f2s(SV_FX_INV));
+}
+template <int FMT>
+__device__ __forceinline__ void sv_store8(float* base, int tile, int npl, int plane, int r, const float (&v)[8]) {
+    const uint4 u = make_uint4(sv_pack2<FMT>(v[0], v[1]), sv_pack2<FMT>(v[2], v[3]), sv_pack2<FMT>(v[4], v[5]), sv_pack2<FMT>(v[6], v[7]));
+    *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(base) + (((size_t)tile * npl + plane) * 128 + r) * 16) = u;
+}
+// plane p of the chunk staged at `slot_r` (already offset to this thread's row); planes beyond the hidden width read as zeros
+template <int FMT>
+__device__ __forceinline__ void sv_load8(const uint4* slot_r, int p, bool exists, f2* o) {
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (FMT == SV_FX) u.x = u.y = u.z = u.w = 6554u * 0x10001u;        // the code of 0
+    if (exists) u = slot_r[p * 128];
+    o[0] = sv_unpack2<FMT>(u.x); o[1] = sv_unpack2<FMT>(u.y); o[2] = sv_unpack2<FMT>(u.z); o[3] = sv_unpack2<FMT>(u.w);
+}
+
 // named barriers of the worker warps: ids 1-4 = the four warps sharing a TMEM lane quadrant (one per part; they exchange
 // per-row partial sums), 5-12 = the four warps of one part (they cover the 128 rows of a chunk), 13 = all workers
 __device__ __forceinline__ void bar_named(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -233,10 +289,10 @@ __host__ __device__ constexpr int geo_words(int nf) { return GEO_HDR + 128 * nf;
 // that read w_hi first, releases that slot, then the 16-bit products that read w_mix: three slots (instead of two stages of
 // hi + mix) keep one half-atom in flight ahead of the tensor pipe and free NP x 128 B of shared memory for the staged P rows.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int NP, int FMT, int SW_ = (NP > 208 ? 2 : 3)>
+template <int NP, int FMT, int SW_ = (NP > 208 ? 2 : 3), int SA_ = 2>
 struct Rings {
     // NP = 256 (hidden 256): a two-slot weight ring (one hi + one mix half-atom) is what fits next to the scratch in 227 KB
-    static constexpr int SA = 2, SW = SW_;
+    static constexpr int SA = SA_, SW = SW_;
     static constexpr int A_BYTES = 128 * ATOM_ROW_BYTES;     // one hi or lo image of a [128 x 32] activation atom
     static constexpr int A_STAGE = 2 * A_BYTES;
     static constexpr int W_BYTES = NP * ATOM_ROW_BYTES;      // one hi or lo image of a [NP x 32] weight atom
@@ -258,9 +314,21 @@ struct Rings {
     // count and an odd na the pairs swap stages from one GEMM to the next; a pair that had not touched a stage for a whole GEMM
     // could then be two phases behind its `empty` barrier, which a parity wait cannot distinguish from "ready": a real,
     // timing-dependent deadlock of the software-pipelined kernels.)
+    //
+    // SA >= 3: stage = running atom count modulo SA.  That is safe exactly when consecutive atoms of one builder pair are at most
+    // SA apart in the running count: before it waits for the consumption of atom q - SA the pair has already seen the consumption
+    // of atom q' - SA of its previous atom q' >= q - SA, and the MMA lane consumes in order, so every atom up to q - 2 SA is
+    // consumed and the stage's `empty` barrier is exactly in the phase the wait names.  The largest gap is 3 (the odd pair going
+    // from atom na - 2 of one GEMM to atom 1 of the next when na is odd), so three stages are the minimum for this form.
     static __device__ __forceinline__ void slot(uint32_t g, int j, int na, uint32_t& s, uint32_t& round) {
-        s = (uint32_t)j & 1u;
-        round = g * (uint32_t)((na + 1 - (int)s) >> 1) + ((uint32_t)j >> 1);
+        if (SA == 2) {
+            s = (uint32_t)j & 1u;
+            round = g * (uint32_t)((na + 1 - (int)s) >> 1) + ((uint32_t)j >> 1);
+        } else {
+            const uint32_t q = g * (uint32_t)na + (uint32_t)j;
+            s = q % (uint32_t)SA;
+            round = q / (uint32_t)SA;
+        }
     }
     // TMA warp (one lane): the 2*na half-atoms of one GEMM; wq = running half-atom counter of this CTA
     __device__ __forceinline__ void tma_gemm(uint32_t& wq, int na, const float* wimg) const {

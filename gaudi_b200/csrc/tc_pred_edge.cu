@@ -12,8 +12,16 @@
 #define GB_PRED_NPARTS 4
 #endif
 #ifndef GB_BWD_SW
-#define GB_BWD_SW 3         // backward: weight half-atom slots
-#define GB_BWD_SVS 6        // backward: saved-activation ring slots (8 KB each)
+#define GB_BWD_SW 2         // backward: weight half-atom slots
+#endif
+#ifndef GB_BWD_SVS
+#define GB_BWD_SVS 5        // backward: saved-activation ring slots (8 KB each)
+#endif
+#ifndef GB_SV_D
+#define GB_SV_D SV_FX       // 16-bit code of the saved SiLU derivatives (tc_common.cuh)
+#endif
+#ifndef GB_BWD_SA
+#define GB_BWD_SA 3         // backward: activation (A operand) ring stages
 #endif
 
 namespace gb {
@@ -37,7 +45,7 @@ struct TcPredCfg {
     // gradients of the backward and it overflows on the forward too (random-init trajectories reach |x| ~ 1e3, i.e. squared
     // distances and pre-activations beyond 65504: the 1000-step chain test diverged with fp16)
     using R = Rings<NP, MIX_BF16>;
-    using RB = Rings<NP, MIX_BF16, (NP > 208 ? 2 : GB_BWD_SW)>;
+    using RB = Rings<NP, MIX_BF16, (NP > 208 ? 2 : GB_BWD_SW), (NP > 208 ? 2 : GB_BWD_SA)>;    // NP = 256: two + two is what fits
     static constexpr int A_BYTES = R::A_BYTES;
     static constexpr int A_STAGE = R::A_STAGE;
     static constexpr int NPARTS = GB_PRED_NPARTS;                          // worker parts of 4 warps; part p owns 16-column chunks ch == p (mod 4)
@@ -48,10 +56,11 @@ struct TcPredCfg {
     static constexpr int EF_STRIDE = 17;
     static constexpr int BAR_BYTES = 512;                                  // up to 64 mbarriers + the TMEM address slot
     static constexpr int D2_COL = 256;
-    // backward only: one extra producer warp streams the saved activations (16-column chunks of the float4 "Q layout",
-    // 4 planes x 128 rows x 16 B = 8 KB, contiguous in HBM) through an 8-slot ring (two chunks per worker part in flight: with
-    // one slot per part the HBM latency of every chunk was exposed -- ~1.5 us on each of the 13 chunk steps of a part and tile)
-    static constexpr int SV_SLOT_BYTES = 4 * 128 * 16;                     // one 16-column chunk of a tile: 4 planes x 128 rows x 16 B
+    // backward only: one extra producer warp streams the saved activations (16-column chunks of the plane layouts of
+    // tc_common.cuh: 2 planes x 128 rows x 16 B = 4 KB for the 16-bit derivative codes, 4 planes = 8 KB for the fp32 pre2,
+    // contiguous in HBM) through a ring of 8 KB slots (more than one chunk per worker part in flight: with one slot per part the
+    // HBM latency of every chunk was exposed -- ~1.5 us on each of the 13 chunk steps of a part and tile)
+    static constexpr int SV_SLOT_BYTES = 4 * SV_PLANE_BYTES;
 };
 
 // saved-activation ring.  `round[s]` = number of the round (q / slots) whose chunk the producer last started to load into slot s.
@@ -131,6 +140,8 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
     const uint32_t tmem_base = *tmem_slot;
     const Graph& g = a.g;
     const int na = (H + ATOM_K - 1) / ATOM_K;
+    const int npl = sv_planes(H);                                // 8-column planes of the 16-bit saved activations
+    (void)npl;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -225,21 +236,28 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
                 const float* pst = ps.acquire(k, j, na);
                 float4 x[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int k0 = j * ATOM_K + 16 * half + 4 * c;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), dv = v;
-                    if (valid && k0 < H) {
-                        const float4 pa = *reinterpret_cast<const float4*>(pst + pa_off + 4 * c);
-                        const float4 pb = *reinterpret_cast<const float4*>(pst + pb_off + 4 * c);
-                        const float4 wr = *reinterpret_cast<const float4*>(vec_s + k0);
-                        const float4 wa = *reinterpret_cast<const float4*>(vec_s + NP + k0);
-                        silu_both(pa.x + pb.x + wr.x * rad + wa.x * a0, v.x, dv.x);
-                        silu_both(pa.y + pb.y + wr.y * rad + wa.y * a0, v.y, dv.y);
-                        silu_both(pa.z + pb.z + wr.z * rad + wa.z * a0, v.z, dv.z);
-                        silu_both(pa.w + pb.w + wr.w * rad + wa.w * a0, v.w, dv.w);
+                for (int pp = 0; pp < 2; ++pp) {                    // one 8-column plane of the saved SiLU'(pre1) per pass
+                    float dv8[8];
+#pragma unroll
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        const int c = 2 * pp + c2;
+                        const int k0 = j * ATOM_K + 16 * half + 4 * c;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f), dv = v;
+                        if (valid && k0 < H) {
+                            const float4 pa = *reinterpret_cast<const float4*>(pst + pa_off + 4 * c);
+                            const float4 pb = *reinterpret_cast<const float4*>(pst + pb_off + 4 * c);
+                            const float4 wr = *reinterpret_cast<const float4*>(vec_s + k0);
+                            const float4 wa = *reinterpret_cast<const float4*>(vec_s + NP + k0);
+                            silu_both(pa.x + pb.x + wr.x * rad + wa.x * a0, v.x, dv.x);
+                            silu_both(pa.y + pb.y + wr.y * rad + wa.y * a0, v.y, dv.y);
+                            silu_both(pa.z + pb.z + wr.z * rad + wa.z * a0, v.z, dv.z);
+                            silu_both(pa.w + pb.w + wr.w * rad + wa.w * a0, v.w, dv.w);
+                        }
+                        x[c] = v;
+                        dv8[4 * c2] = dv.x; dv8[4 * c2 + 1] = dv.y; dv8[4 * c2 + 2] = dv.z; dv8[4 * c2 + 3] = dv.w;
                     }
-                    x[c] = v;
-                    if (SAVE && k0 < H) *reinterpret_cast<float4*>(a.sv_d1 + (((size_t)tile * (H / 4) + (k0 >> 2)) * 128 + r) * 4) = dv;
+                    const int plane = 4 * j + 2 * half + pp;
+                    if (SAVE && plane < npl) sv_store8<GB_SV_D>(a.sv_d1, tile, npl, plane, r, dv8);
                 }
                 ps.release(k, j, na);
                 TLW(20 + j);
@@ -280,7 +298,7 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
                             q[ci][4 * c4 + e] = v;
                             psum = fmaf(vec_s[3 * NP + c0 + e], v, psum);
                         }
-                        if (SAVE && c0 < H)
+                        if (SAVE && c0 < H)          // pre2 stays fp32: [tile][k / 4][128 rows][4]
                             *reinterpret_cast<float4*>(a.sv_pre2 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4) = make_float4(pre[0], pre[1], pre[2], pre[3]);
                     }
                 }
@@ -336,17 +354,16 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
                 float v[16];
                 tmem_ld16(lane_addr + CF::D2_COL + ch * 16, v);
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    const int c0 = ch * 16 + 4 * c4;
-                    float d3[4];
+                for (int pp = 0; pp < 2; ++pp) {
+                    const int c0 = ch * 16 + 8 * pp;
+                    float d3[8];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
+                    for (int e = 0; e < 8; ++e) {
                         float s3;
-                        silu_both(v[4 * c4 + e] + vec_s[4 * NP + c0 + e], s3, d3[e]);
+                        silu_both(v[8 * pp + e] + vec_s[4 * NP + c0 + e], s3, d3[e]);
                         phi_part = fmaf(vec_s[5 * NP + c0 + e], s3, phi_part);
                     }
-                    if (SAVE && c0 < H)
-                        *reinterpret_cast<float4*>(a.sv_d3 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4) = make_float4(d3[0], d3[1], d3[2], d3[3]);
+                    if (SAVE && 2 * ch + pp < npl) sv_store8<GB_SV_D>(a.sv_d3, tile, npl, 2 * ch + pp, r, d3);
                 }
             }
             fence_before_sync();
@@ -405,7 +422,7 @@ struct TcBwdCfg : TcPredCfg<NP> {
 };
 
 template <int SLOTS>
-__device__ __forceinline__ const float4* svq_acquire(const SvRing& sv, uint32_t q, int r) {
+__device__ __forceinline__ const uint4* svq_acquire(const SvRing& sv, uint32_t q, int r) {
     const uint32_t s = q % SLOTS, rr = q / SLOTS;
 #ifdef GB_DEBUG_HANG
     for (long long spin = 0; sv.round[s] != rr; ++spin) {
@@ -424,7 +441,7 @@ __device__ __forceinline__ const float4* svq_acquire(const SvRing& sv, uint32_t 
     while (sv.round[s] != rr) { }
 #endif
     mbar_wait(&sv.full[s], rr & 1);
-    return reinterpret_cast<const float4*>(sv.buf + s * 8192) + r;
+    return reinterpret_cast<const uint4*>(sv.buf + s * (4 * SV_PLANE_BYTES)) + r;
 }
 template <int SLOTS>
 __device__ __forceinline__ void svq_release(const SvRing& sv, uint32_t q) { mbar_arrive(&sv.empty[q % SLOTS]); }
@@ -466,10 +483,8 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
         vec_s[i] = v ? a.ext[i] : 0.f; vec_s[NP + i] = v ? a.ext[H + i] : 0.f;
         vec_s[3 * NP + i] = v ? a.att_w[i] : 0.f; vec_s[5 * NP + i] = v ? a.wc_last[i] : 0.f;
     }
-    // the last 16-column chunk of a tile is only partly filled by the producer (H / 4 planes): the remaining planes are read as
-    // they are and multiplied by zero-padded weights, so they must hold finite values from the start
-    for (int i = tid; i < SVS * CF::SV_SLOT_BYTES / 16; i += blockDim.x) reinterpret_cast<float4*>(sv_buf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    fence_proxy_async();
+    // (the last 16-column chunk of a tile may hold one plane only: sv_load8 reads the missing plane as zeros instead of the slot's
+    // previous occupant, so a NaN saved for another tile can never leak into this one through a zero-padded weight)
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -477,6 +492,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
     const Graph& g = a.g;
     const int na = (H + ATOM_K - 1) / ATOM_K;
     const int my_tiles = (int)blockIdx.x < g.n_tiles ? (g.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int npl = sv_planes(H);                                // 8-column planes of the 16-bit saved activations
 
     if (warp == 0) {
         if (lane == 0 && my_tiles > 0) {
@@ -511,26 +527,28 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
         // saved-activation producer, in the order the worker parts consume the 16-column chunks:
         //   d3(0);  for k: pre2(k) [epilogue 1], pre2(k) [GEMM-2 operand], d3(k+1) [GEMM-1 operand of the next tile], d1(k) [epilogue 2]
         if (lane == 0 && my_tiles > 0) {
-            const int nchunks = (H + 15) / 16, planes = H / 4;
+            const int nchunks = (H + 15) / 16, planes = sv_planes(H);
             uint32_t q = 0;
-            auto stream = [&](const float* src) {
+            auto stream = [&](const float* src, bool p32) {     // 16-bit derivative planes (8 columns each) or fp32 pre2 planes (4 columns each)
                 for (int ch = 0; ch < nchunks; ++ch, ++q) {
                     const uint32_t s = q % SVS, rr = q / SVS;
-                    const uint32_t bytes = (uint32_t)min(4, planes - 4 * ch) * 2048u;
+                    const uint32_t bytes = (uint32_t)(p32 ? min(4, H / 4 - 4 * ch) : min(2, planes - 2 * ch)) * (uint32_t)SV_PLANE_BYTES;
+                    const size_t off = (size_t)ch * (p32 ? 4 : 2) * (SV_PLANE_BYTES / 4);
                     if (rr > 0) mbar_wait(&sv_empty[s], (rr - 1) & 1);
                     sv_round[s] = rr;                        // full[s] is in phase rr from here on (see SvRing)
                     mbar_arrive_expect_tx(&sv_full[s], bytes);
-                    bulk_g2s(sv.buf + s * CF::SV_SLOT_BYTES, src + (size_t)ch * 2048, bytes, &sv_full[s]);
+                    bulk_g2s(sv.buf + s * CF::SV_SLOT_BYTES, src + off, bytes, &sv_full[s]);
                 }
             };
-            const size_t tstride = (size_t)planes * 512;
-            stream(a.sv_d3 + (size_t)blockIdx.x * tstride);
+            const size_t tstride = (size_t)planes * (SV_PLANE_BYTES / 4);          // floats per tile: derivative codes
+            const size_t tstride_p = (size_t)(H / 4) * (SV_PLANE_BYTES / 4);       //                  pre2
+            stream(a.sv_d3 + (size_t)blockIdx.x * tstride, false);
             int tile = blockIdx.x;
             for (int k = 0; k < my_tiles; ++k, tile += gridDim.x) {
-                stream(a.sv_pre2 + (size_t)tile * tstride);
-                stream(a.sv_pre2 + (size_t)tile * tstride);
-                if (k + 1 < my_tiles) stream(a.sv_d3 + (size_t)(tile + gridDim.x) * tstride);
-                stream(a.sv_d1 + (size_t)tile * tstride);
+                stream(a.sv_pre2 + (size_t)tile * tstride_p, true);
+                stream(a.sv_pre2 + (size_t)tile * tstride_p, true);
+                if (k + 1 < my_tiles) stream(a.sv_d3 + (size_t)(tile + gridDim.x) * tstride, false);
+                stream(a.sv_d1 + (size_t)tile * tstride, false);
             }
         }
     } else if (warp == CF::GEO_WARP) {
@@ -594,14 +612,19 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                 f2 x[8];
                 const int ch = 2 * j + half;
                 if (ch < nchunks) {
-                    const float4* d3p = svq_acquire<SVS>(sv, sq + ch, r);
+                    const uint4* d3p = svq_acquire<SVS>(sv, sq + ch, r);
                     TLW(100 + j);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float4 d3 = d3p[c * 128];
-                        const float4 wl = *reinterpret_cast<const float4*>(vec_s + 5 * NP + ch * 16 + 4 * c);
-                        x[2 * c] = mul2(mul2(gphi2, lo2(wl)), lo2(d3));
-                        x[2 * c + 1] = mul2(mul2(gphi2, hi2(wl)), hi2(d3));
+                    for (int pp = 0; pp < 2; ++pp) {
+                        f2 d3[4];
+                        sv_load8<GB_SV_D>(d3p, pp, 2 * ch + pp < npl, d3);
+#pragma unroll
+                        for (int c2 = 0; c2 < 2; ++c2) {
+                            const int c = 2 * pp + c2;
+                            const float4 wl = *reinterpret_cast<const float4*>(vec_s + 5 * NP + ch * 16 + 4 * c);
+                            x[2 * c] = mul2(mul2(gphi2, lo2(wl)), d3[2 * c2]);
+                            x[2 * c + 1] = mul2(mul2(gphi2, hi2(wl)), d3[2 * c2 + 1]);
+                        }
                     }
                     svq_release<SVS>(sv, sq + ch);
                 } else {
@@ -630,7 +653,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
             // the tile's rows of g_agg (one per row node, shared by its ~9 edges) are copied once, coalesced, into the A ring: every
             // operand atom stored so far (GEMM 1 of this tile was the last) has been consumed, and nothing is stored before build2
             constexpr int GA_ROWS = CF::A_STAGE / (NP * 4);                // rows per ring stage (A hi + A lo)
-            const bool ga_staged = nn <= 2 * GA_ROWS;
+            const bool ga_staged = nn <= CF::RB::SA * GA_ROWS;
             if (ga_staged) {
                 const int h4 = H >> 2;
                 for (int idx = (warp - 2) * 32 + lane; idx < nn * h4; idx += CF::NWORK) {
@@ -656,15 +679,14 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                 for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
                     tmem_ld_wait16(v);
                     TLW(200 + ch);
-                    const float4* p2p = svq_acquire<SVS>(sv, sq + ch, r);
+                    const float4* p2p = reinterpret_cast<const float4*>(svq_acquire<SVS>(sv, sq + ch, r));
                     TLW(220 + ch);
                     float w[16];
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         const int c0 = ch * 16 + 4 * c4;
-                        float4 ga = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (c0 < H) ga = *reinterpret_cast<const float4*>(ga_row + c0);     // (the staged copy only holds the H real columns)
-                        const float4 p2 = p2p[c4 * 128];
+                        float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), p2 = ga;               // planes beyond H: zeros, not the slot's previous occupant
+                        if (c0 < H) { ga = *reinterpret_cast<const float4*>(ga_row + c0); p2 = p2p[c4 * 128]; }     // (the staged copy only holds the H real columns)
                         const float4 wq = *reinterpret_cast<const float4*>(vec_s + 3 * NP + c0);
                         const f2 qa = silu2(lo2(p2)), qb = silu2(hi2(p2));
                         const f2 ga_ = add2(make_float2(v[4 * c4], v[4 * c4 + 1]), lo2(ga));
@@ -700,12 +722,13 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                     f2 x[8];
                     if (ch < nchunks) {
                         tmem_ld_wait16(v);
-                        const float4* p2p = svq_acquire<SVS>(sv, sq + ch, r);
+                        const float4* p2p = reinterpret_cast<const float4*>(svq_acquire<SVS>(sv, sq + ch, r));
                         TLW(300 + ch);
 #pragma unroll
                         for (int c4 = 0; c4 < 4; ++c4) {
                             const int c0 = ch * 16 + 4 * c4;
-                            const float4 p2 = p2p[c4 * 128];
+                            float4 p2 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (c0 < H) p2 = p2p[c4 * 128];
                             const float4 wq = *reinterpret_cast<const float4*>(vec_s + 3 * NP + c0);
                             const f2 ta = fma2(kap2, lo2(wq), mul2(make_float2(v[4 * c4], v[4 * c4 + 1]), gate2));
                             const f2 tb = fma2(kap2, hi2(wq), mul2(make_float2(v[4 * c4 + 2], v[4 * c4 + 3]), gate2));
@@ -750,17 +773,18 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                 for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
                     tmem_ld_wait16(v);
                     TLW(400 + ch);
-                    const float4* d1p = svq_acquire<SVS>(sv, sq + ch, r);
+                    const uint4* d1p = svq_acquire<SVS>(sv, sq + ch, r);
                     TLW(420 + ch);
-                    f2 gp[8];
+                    f2 gp[8], d1v[8];
+                    sv_load8<GB_SV_D>(d1p, 0, true, d1v);
+                    sv_load8<GB_SV_D>(d1p, 1, 2 * ch + 1 < npl, d1v + 4);
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         const int c0 = ch * 16 + 4 * c4;
-                        const float4 d1 = d1p[c4 * 128];
                         const float4 wr = *reinterpret_cast<const float4*>(vec_s + c0);
                         const float4 wa = *reinterpret_cast<const float4*>(vec_s + NP + c0);
-                        gp[2 * c4] = mul2(make_float2(v[4 * c4], v[4 * c4 + 1]), lo2(d1));
-                        gp[2 * c4 + 1] = mul2(make_float2(v[4 * c4 + 2], v[4 * c4 + 3]), hi2(d1));
+                        gp[2 * c4] = mul2(make_float2(v[4 * c4], v[4 * c4 + 1]), d1v[2 * c4]);
+                        gp[2 * c4 + 1] = mul2(make_float2(v[4 * c4 + 2], v[4 * c4 + 3]), d1v[2 * c4 + 1]);
                         pr2 = fma2(lo2(wr), gp[2 * c4], pr2); pr2 = fma2(hi2(wr), gp[2 * c4 + 1], pr2);
                         pa2 = fma2(lo2(wa), gp[2 * c4], pa2); pa2 = fma2(hi2(wa), gp[2 * c4 + 1], pa2);
                     }

@@ -23,6 +23,7 @@ from __future__ import annotations
 
 from typing import Callable, Optional
 
+import os
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -409,8 +410,10 @@ class EnVariationalDiffusion(torch.nn.Module):
         self._check_stats(stats)
         return self._finish(z, node_mask, edge_mask, fix_noise, last)
 
-    # ---- batch chunking: the input-gradient pass keeps 3 x hidden floats per edge and layer (25 GB per 10k cc-PBH
-    #      molecules); batches whose workspace would not fit the free HBM are sampled in sequential chunks ----
+    # ---- batch chunking: the input-gradient pass keeps SiLU'(pre1), pre2, SiLU'(pre3) per edge, column and layer -- 2 + 4 + 2
+    #      bytes on the tensor-core engine (16-bit derivative codes, fp32 pre2: 16.9 GB per 10k cc-PBH molecules; 12 bytes
+    #      = 25.4 GB on the FP32 engine and up to round 2c); batches whose workspace would not fit the free HBM are sampled
+    #      in sequential chunks ----
     memory_fraction = 0.7
 
     def _max_chunk(self, node_mask, edge_mask, predictor, guided=False) -> int:
@@ -424,7 +427,9 @@ class EnVariationalDiffusion(torch.nn.Module):
         if predictor is not None or guided:
             hyper = getattr(getattr(predictor, "module", predictor), "hyper", None) or {"hidden_nf": 256, "n_layers": 12}
             hp, lp = hyper["hidden_nf"], hyper["n_layers"]
-            per_mol += 4.0 * (3 * lp * hp * edges_per_mol * 1.1 + n * hp * (lp + 12))
+            eng = os.environ.get("GAUDI_B200_GEMM", "tc")
+            sv_bytes = 8.0 if (eng == "tc" or "pred" in eng) else 12.0
+            per_mol += (sv_bytes * lp + 4.0) * hp * edges_per_mol * 1.1 + 4.0 * n * hp * (lp + 12)     # + g_pre1 [edges, hp]
         free, _ = torch.cuda.mem_get_info(node_mask.device)
         reusable = sum(w.buf.numel() for w in runtime._ws.values() if w.buf is not None)
         return max(1, int(self.memory_fraction * (free + reusable) / per_mol))
