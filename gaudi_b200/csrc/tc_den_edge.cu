@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(TcEdgeCfg<NP>::THREADS, 1) tc_den_edge_kernel(
                         for (int nl = ht >> 4; nl < nn; nl += 8) {
                             const int col = ht & 15, c = ch * 16 + col;
                             float sum = 0.f;
-                            for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += my_ef[mm * CF::EF_STRIDE + col];
+                            for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += my_ef[mm * CF::EF_STRIDE + col];   // (a 4-way unrolled form with batched loads measured 4-6 % slower)
                             if (c < H) a.agg[(size_t)(node_lo + nl) * H + c] = sum / a.normf;
                         }
                         bar_named(BAR_PART + part, 128);

@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
                     for (int nl = r >> 4; nl < nn; nl += 8) {
                         const int col = r & 15, c = ch * 16 + col;
                         float sum = 0.f;
-                        for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += my_ef[mm * CF::EF_STRIDE + col];
+                        for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += my_ef[mm * CF::EF_STRIDE + col];   // (a 4-way unrolled form with batched loads measured 4-6 % slower)
                         if (c < H) a.agg[(size_t)(node_lo + nl) * H + c] = sum;
                     }
                     bar_named(BAR_PART + part, 128);
@@ -877,42 +877,60 @@ void launch_pred_edge_bwd_tc(int H, const PredEdgeArgs& a, const float* wcimg_nt
     }
 }
 
-// Node-parallel reductions of the backward (one warp per node, lanes along the feature dimension):
+// Node-parallel reductions of the backward:
 //   g_Pa[i] = sum over the row segment of i,  g_Pb[i] = sum over the edges whose column is i (CSC order),
 //   g_x[i]  = g_xout[i]*mask_i + sum_row g_d - sum_col g_d.          Fixed order -> bit-reproducible.
-__global__ void pred_bwd_reduce_kernel(PredEdgeArgs a, int H) {
+// One thread per (node, float4 column): a block of 256 threads covers 256 / (H / 4) nodes (5 at H = 196: 245 busy threads; the
+// first version gave a whole warp to a node and ran its second pass over the 49 float4 columns with 17 of 32 lanes).  The row and
+// column loops issue four independent 16-byte loads before they add, in the same order as a plain loop.
+__global__ void __launch_bounds__(256) pred_bwd_reduce_kernel(PredEdgeArgs a, int H) {
     const Graph& g = a.g;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int nq = H >> 2;                                       // float4 columns
-    for (int node = warp; node < g.n_nodes; node += nwarps) {
-        const int r0 = g.rowptr[node], r1 = g.rowptr[node + 1];
-        const int c0 = g.colptr[node], c1 = g.colptr[node + 1];
-        for (int q = lane; q < nq; q += 32) {
+    const int npb = 256 / nq;                                    // nodes per block and pass
+    const int nl = threadIdx.x / nq, q = threadIdx.x - nl * nq;
+    for (int base = blockIdx.x * npb; base < g.n_nodes; base += gridDim.x * npb) {
+        const int node = base + nl;
+        if (nl < npb && node < g.n_nodes) {
+            const int r0 = g.rowptr[node], r1 = g.rowptr[node + 1];
+            const int c0 = g.colptr[node], c1 = g.colptr[node + 1];
+            const float4* src = reinterpret_cast<const float4*>(a.g_pre1) + q;
             float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
-            for (int e = r0; e < r1; ++e) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(a.g_pre1 + (size_t)e * H) + q);
-                sa.x += v.x; sa.y += v.y; sa.z += v.z; sa.w += v.w;
+            int e = r0;
+            for (; e + 4 <= r1; e += 4) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = __ldg(src + (size_t)(e + u) * nq);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { sa.x += v[u].x; sa.y += v[u].y; sa.z += v[u].z; sa.w += v[u].w; }
             }
-            for (int p = c0; p < c1; ++p) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(a.g_pre1 + (size_t)__ldg(g.cedge + p) * H) + q);
-                sb.x += v.x; sb.y += v.y; sb.z += v.z; sb.w += v.w;
+            for (; e < r1; ++e) { const float4 v = __ldg(src + (size_t)e * nq); sa.x += v.x; sa.y += v.y; sa.z += v.z; sa.w += v.w; }
+            int p = c0;
+            for (; p + 4 <= c1; p += 4) {
+                int ce[4]; float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) ce[u] = __ldg(g.cedge + p + u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = __ldg(src + (size_t)ce[u] * nq);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { sb.x += v[u].x; sb.y += v[u].y; sb.z += v[u].z; sb.w += v[u].w; }
             }
+            for (; p < c1; ++p) { const float4 v = __ldg(src + (size_t)__ldg(g.cedge + p) * nq); sb.x += v.x; sb.y += v.y; sb.z += v.z; sb.w += v.w; }
             reinterpret_cast<float4*>(a.g_Pa + (size_t)node * H)[q] = sa;
             reinterpret_cast<float4*>(a.g_Pb + (size_t)node * H)[q] = sb;
-        }
-        if (lane < 3) {
-            float sum = a.g_xout[3 * node + lane] * g.node_mask[node];
-            for (int e = r0; e < r1; ++e) sum += a.g_d[(size_t)e * 3 + lane];
-            for (int p = c0; p < c1; ++p) sum -= a.g_d[(size_t)g.cedge[p] * 3 + lane];
-            a.g_x[3 * node + lane] = sum;
+            if (q < 3) {                                         // coordinate gradient: three threads of the node
+                float sum = a.g_xout[3 * node + q] * g.node_mask[node];
+                for (int ee = r0; ee < r1; ++ee) sum += a.g_d[(size_t)ee * 3 + q];
+                for (int pp = c0; pp < c1; ++pp) sum -= a.g_d[(size_t)g.cedge[pp] * 3 + q];
+                a.g_x[3 * node + q] = sum;
+            }
         }
     }
 }
 
 void launch_pred_bwd_reduce(int H, const PredEdgeArgs& a, cudaStream_t s) {
     if (a.g.n_nodes <= 0) return;
-    const int blocks = min(148 * 8, (a.g.n_nodes + 7) / 8);
+    const int npb = 256 / (H >> 2);
+    const int blocks = min(148 * 16, (a.g.n_nodes + npb - 1) / npb);
     pred_bwd_reduce_kernel<<<blocks, 256, 0, s>>>(a, H);
 }
 
