@@ -77,6 +77,26 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand from TENSOR MEMORY (the ".ts" form; cute SM100_MMA_TF32_TS / SM100_MMA_F16BF16_TS): lane = row, the K elements of one
+// MMA in 8 consecutive 32-bit columns (tf32: one per column; 16-bit kinds: two per column, the lower k in the low half), K-major only.
+// The worker warps then write their operand rows with tcgen05.st (thread = row, no swizzle arithmetic, no fence.proxy.async, nothing
+// on the shared-memory data pipe) and the MMA reads only the weights from shared memory (208 of 336 operand rows per instruction).
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -164,6 +184,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
         "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
         ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
           "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16_u(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -289,19 +317,25 @@ __host__ __device__ constexpr int geo_words(int nf) { return GEO_HDR + 128 * nf;
 // that read w_hi first, releases that slot, then the 16-bit products that read w_mix: three slots (instead of two stages of
 // hi + mix) keep one half-atom in flight ahead of the tensor pipe and free NP x 128 B of shared memory for the staged P rows.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int NP, int FMT, int SW_ = (NP > 208 ? 2 : 3), int SA_ = 2>
+template <int NP, int FMT, int SW_ = (NP > 208 ? 2 : 3), int SA_ = 2, bool AT_ = false>
 struct Rings {
+    // AT: the activation stages live in tensor memory (64 columns per stage: [hi : 32 tf32][mix : 4 K steps x 8 columns of 16-bit
+    // pairs]) instead of shared memory; same barriers, same stage / round bookkeeping.  Needs 64 free TMEM columns per stage next
+    // to the accumulators (set_tmem), which the denoiser kernels have at NP = 192 (2 x 192 + 2 x 64 = 512).
+    static constexpr bool AT = AT_;
     // NP = 256 (hidden 256): a two-slot weight ring (one hi + one mix half-atom) is what fits next to the scratch in 227 KB
     static constexpr int SA = SA_, SW = SW_;
     static constexpr int A_BYTES = 128 * ATOM_ROW_BYTES;     // one hi or lo image of a [128 x 32] activation atom
     static constexpr int A_STAGE = 2 * A_BYTES;
     static constexpr int W_BYTES = NP * ATOM_ROW_BYTES;      // one hi or lo image of a [NP x 32] weight atom
-    static constexpr int BYTES = SA * A_STAGE + SW * W_BYTES;
+    static constexpr int BYTES = (AT ? 0 : SA * A_STAGE) + SW * W_BYTES;
     static constexpr int NBARS = 2 * SA + 2 * SW;
     unsigned char* a_base; unsigned char* w_base;
     uint64_t *full_a, *empty_a, *full_w, *empty_w;
+    uint32_t a_tm[SA];                                        // AT: TMEM address (lane 0) of each activation stage
+    __device__ __forceinline__ void set_tmem(uint32_t s, uint32_t taddr) { a_tm[s] = taddr; }
     __device__ __forceinline__ void carve(unsigned char* base, uint64_t* bars) {
-        a_base = base; w_base = base + SA * A_STAGE;
+        a_base = base; w_base = base + (AT ? 0 : SA * A_STAGE);
         full_a = bars; empty_a = bars + SA; full_w = bars + 2 * SA; empty_w = full_w + SW;
     }
     __device__ __forceinline__ void init(int a_arrivals) {   // one thread
@@ -347,14 +381,15 @@ struct Rings {
             slot(g, j, na, sa, ra);
             const int kvalid = H - j * ATOM_K;
             const int ksteps = kvalid >= ATOM_K ? 4 : (kvalid + 7) / 8;
-            const uint32_t a_hi = smem_u32(a_base + sa * A_STAGE), a_mix = a_hi + A_BYTES;
+            const uint32_t a_hi = AT ? 0u : smem_u32(a_base + sa * A_STAGE), a_mix = a_hi + A_BYTES;
             mbar_wait(&full_a[sa], ra & 1 GB_TAG((int)(g * 16 + j)));
             {
                 const uint32_t s = wq % SW, r = wq / SW;
                 mbar_wait(&full_w[s], r & 1);
                 fence_after_sync();
                 const uint32_t w_hi = smem_u32(w_base + s * W_BYTES);
-                for (int kk = 0; kk < ksteps; ++kk) mma_tf32(d_tmem, smem_desc(a_hi + kk * 32), smem_desc(w_hi + kk * 32), idesc, (j | kk) != 0);
+                if (AT) { for (int kk = 0; kk < ksteps; ++kk) mma_tf32_ts(d_tmem, a_tm[sa] + kk * 8, smem_desc(w_hi + kk * 32), idesc, (j | kk) != 0); }
+                else for (int kk = 0; kk < ksteps; ++kk) mma_tf32(d_tmem, smem_desc(a_hi + kk * 32), smem_desc(w_hi + kk * 32), idesc, (j | kk) != 0);
                 mma_commit(&empty_w[s]);
                 ++wq;
             }
@@ -363,13 +398,42 @@ struct Rings {
                 mbar_wait(&full_w[s], r & 1);
                 fence_after_sync();
                 const uint32_t w_mix = smem_u32(w_base + s * W_BYTES);
-                for (int kk = 0; kk < ksteps; ++kk) mma_f16(d_tmem, smem_desc(a_mix + kk * 32), smem_desc(w_mix + kk * 32), idesc_mix, 1);
+                if (AT) { for (int kk = 0; kk < ksteps; ++kk) mma_f16_ts(d_tmem, a_tm[sa] + 32 + kk * 8, smem_desc(w_mix + kk * 32), idesc_mix, 1); }
+                else for (int kk = 0; kk < ksteps; ++kk) mma_f16(d_tmem, smem_desc(a_mix + kk * 32), smem_desc(w_mix + kk * 32), idesc_mix, 1);
                 mma_commit(&empty_w[s]);
                 ++wq;
             }
             mma_commit(&empty_a[sa]);
         }
         ++g;
+    }
+    // worker, AT form: this thread's 16 columns (two K steps) of atom j go to its own TMEM lane (lane_off = (32 * (warp & 3)) << 16):
+    // 16 columns of TF32 parts, and per K step [4 columns of residual pairs | 4 columns of TF32-part pairs] as 16-bit values
+    __device__ __forceinline__ void put_chunk_t(uint32_t g, int j, int na, uint32_t lane_off, int half, const float4 (&x)[4]) const {
+        uint32_t s, rr;
+        slot(g, j, na, s, rr);
+        float hi[16]; uint32_t mix[16];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {                        // K step q of this half: x[2q], x[2q + 1]
+            const f2 a = lo2(x[2 * q]), b = hi2(x[2 * q]), c = lo2(x[2 * q + 1]), d = hi2(x[2 * q + 1]);
+            const f2 ha = make_float2(tf32_hi(a.x), tf32_hi(a.y)), hb = make_float2(tf32_hi(b.x), tf32_hi(b.y));
+            const f2 hc = make_float2(tf32_hi(c.x), tf32_hi(c.y)), hd = make_float2(tf32_hi(d.x), tf32_hi(d.y));
+            const f2 la = fma2(ha, f2s(-1.f), a), lb = fma2(hb, f2s(-1.f), b), lc = fma2(hc, f2s(-1.f), c), ld = fma2(hd, f2s(-1.f), d);
+            hi[8 * q] = ha.x; hi[8 * q + 1] = ha.y; hi[8 * q + 2] = hb.x; hi[8 * q + 3] = hb.y;
+            hi[8 * q + 4] = hc.x; hi[8 * q + 5] = hc.y; hi[8 * q + 6] = hd.x; hi[8 * q + 7] = hd.y;
+            mix[8 * q] = pack16<FMT>(la.x, la.y); mix[8 * q + 1] = pack16<FMT>(lb.x, lb.y);
+            mix[8 * q + 2] = pack16<FMT>(lc.x, lc.y); mix[8 * q + 3] = pack16<FMT>(ld.x, ld.y);
+            mix[8 * q + 4] = pack16<FMT>(ha.x, ha.y); mix[8 * q + 5] = pack16<FMT>(hb.x, hb.y);
+            mix[8 * q + 6] = pack16<FMT>(hc.x, hc.y); mix[8 * q + 7] = pack16<FMT>(hd.x, hd.y);
+        }
+        if (rr > 0) mbar_wait(&empty_a[s], (rr - 1) & 1);
+        fence_after_sync();
+        const uint32_t t = a_tm[s] + lane_off + 16 * half;
+        tmem_st16(t, hi);
+        tmem_st16_u(t + 32, mix);
+        tmem_st_wait();
+        fence_before_sync();
+        mbar_arrive(&full_a[s]);
     }
     // worker, packed form: x[2c], x[2c+1] = the two halves of 16-byte chunk c
     __device__ __forceinline__ void put_chunk2(uint32_t g, int j, int na, int r, int half, const f2 (&x)[8]) const {

@@ -24,7 +24,14 @@ __device__ unsigned int gb_tl_den_n[5];
 
 template <int NP>
 struct TcEdgeCfg {
-    using R = Rings<NP, MIX_BF16>;
+    static constexpr int ACC_STRIDE = NP <= 64 ? 64 : 256;   // two accumulators: the MMAs of tile k+1 run during the epilogue of tile k
+    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+#ifndef GB_DEN_AT
+#define GB_DEN_AT 1
+#endif
+    // activation operand in tensor memory when 64 columns are free behind each accumulator (hidden 192: 2 x (192 + 64) = 512)
+    static constexpr bool AT = GB_DEN_AT && ACC_STRIDE - NP >= 64;
+    using R = Rings<NP, MIX_BF16, (NP > 208 ? 2 : 3), 2, AT>;
     static constexpr int NPARTS = 4;                         // worker parts of 4 warps; part p owns 16-column chunks ch == p (mod 4)
     static constexpr int NWORK = 128 * NPARTS;
     // two auxiliary warps stage the P rows of every K-atom (even / odd atoms); the first one also prepares the edge geometry
@@ -34,15 +41,13 @@ struct TcEdgeCfg {
     static constexpr int THREADS = 64 + NWORK + 64;
     static constexpr int MAXCH = (NP + 15) / 16;             // 16-column chunks
     static constexpr int MYCH = (MAXCH + NPARTS - 1) / NPARTS;
-    static constexpr int EF_STRIDE = 17;
+    static constexpr int EF_STRIDE = 17;                     // (a 20-float pitch with 16-byte stores and two buffers per part = one barrier per chunk: no gain)
     static constexpr int GEO_NF = 7;                         // P-stage row of the row node / of the col node, radial, d0, unit vector (3)
     static constexpr int GEO_WORDS = geo_words(GEO_NF);
     static constexpr int BAR_BYTES = 256;
     static constexpr int NGEO = 3;                           // tile k builds while tile k-1 is in its epilogue and k+1 is being prepared
     static constexpr int SCRATCH = 4 * NP * 4 + 2 * NPARTS * 128 * 4 + NPARTS * 128 * EF_STRIDE * 4 + NGEO * GEO_WORDS * 4 + 2 * 128 * 3 * 4 + PS_BYTES + 64;
     static constexpr int SMEM = R::BYTES + 1024 + BAR_BYTES + SCRATCH;
-    static constexpr int ACC_STRIDE = NP <= 64 ? 64 : 256;   // two accumulators: the MMAs of tile k+1 run during the epilogue of tile k
-    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
     static_assert(SMEM <= 232448, "shared memory budget");
 };
 
@@ -84,6 +89,7 @@ __global__ void __launch_bounds__(TcEdgeCfg<NP>::THREADS, 1) tc_den_edge_kernel(
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    if (CF::AT) { rg.set_tmem(0, tmem_base + NP); rg.set_tmem(1, tmem_base + CF::ACC_STRIDE + NP); }
     const Graph& g = a.g;
     const int na = (H + ATOM_K - 1) / ATOM_K;
 
@@ -201,7 +207,8 @@ __global__ void __launch_bounds__(TcEdgeCfg<NP>::THREADS, 1) tc_den_edge_kernel(
                 }
                 ps.release(k, j, na);                            // P slice consumed (the loads above fed the arithmetic)
                 if (tlr >= 0) TLD(tlr, 30 + j);
-                rg.put_chunk(k, j, na, r, half, x);
+                if (CF::AT) rg.put_chunk_t(k, j, na, (uint32_t)(group * 32) << 16, half, x);
+                else rg.put_chunk(k, j, na, r, half, x);
                 if (tlr >= 0) TLD(tlr, 40 + j);
             }
         };
