@@ -143,7 +143,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         }
     }
 #endif
+    // try_wait suspends the thread until the phase completes or a time limit passes; without the hint operand the limit is short and a
+    // waiting warp keeps re-issuing SYNCS + BRA + YIELD (25 % of the executed warp-instructions of the round-2c edge kernels were such
+    // polls, competing with the worker warps for issue slots).  GB_MBAR_HINT_NS = 0 restores the plain form.
+#ifndef GB_MBAR_HINT_NS
+#define GB_MBAR_HINT_NS 1000000
+#endif
     do {
+#if GB_MBAR_HINT_NS > 0
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(GB_MBAR_HINT_NS)
+            : "memory");
+#else
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -151,6 +166,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(done)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
+#endif
     } while (!done);
 }
 // 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP); completes `bytes` on `bar`.
