@@ -4,7 +4,7 @@
 #   gpurun -- 'bash tools/ncu_kernels.sh r2a'
 tag=${1:-r2}
 mkdir -p gpurun_out
-for spec in "bwd:tc_pred_edge_bwd_kernel" "fwd:tc_pred_edge_fwd_kernel" "den:tc_den_edge_kernel" "lin:tc_lin_kernel"; do
+for spec in "bwd:tc_pred_edge_bwd_kernel" "fwd:tc_pred_edge_fwd_kernel" "den:tc_den_edge_kernel" "lin:tc_lin_kernel" "red:pred_bwd_reduce_kernel"; do
     name=${spec%%:*}; kern=${spec##*:}
     cnt=1; [ "$name" = "den" ] && cnt=2
     timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$kern" -s 20 -c $cnt -f -o gpurun_out/prof_${tag}_${name} \
