@@ -460,6 +460,114 @@ struct Rings {
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Operand ring with the ACTIVATIONS IN TENSOR MEMORY, in half-atom stages (the predictor kernels at NP <= 208: the two accumulators
+// leave 96 of the 512 TMEM columns, i.e. three stages of 32 columns = [hi : 2 K steps x 8 tf32][mix : 2 K steps x 8 columns of
+// 16-bit pairs]).  A stage is one 16-column chunk of a GEMM's K dimension, written by the ONE worker part that owns the chunk
+// (128 arrivals) with two tcgen05.st per thread; the MMA lane consumes the chunks in order (TF32 then 16-bit MMAs of the chunk's
+// K steps) and releases the stage with a commit.  Stage = running chunk count modulo 3.  A part's consecutive chunks are 4-5 apart
+// in that count, more than the ring is deep, so a part can reach its wait for round r of a stage before round r-1 of that stage
+// has even been built -- and a parity wait cannot tell "round r-1 consumed" from "round r-3 consumed".  `built[s]` (last round
+// whose builder passed its own wait) closes that hole exactly like SvRing::round does.
+// The weight half-atoms stream through shared memory as in Rings; both halves of a 32-wide atom stay until its two chunks are done,
+// so four slots (the shared memory freed by the activation ring) keep the next atom's two halves in flight.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NP, int FMT, int SW_ = 4>
+struct RingsH {
+    static constexpr int SA = 3, SW = SW_;
+    static constexpr int STAGE_COLS = 32;
+    static constexpr int TMEM_COLS = SA * STAGE_COLS;
+    static constexpr int W_BYTES = NP * ATOM_ROW_BYTES;
+    static constexpr int BYTES = SW * W_BYTES;
+    static constexpr int NBARS = 2 * SA + 2 * SW;
+    unsigned char* w_base;
+    uint64_t *full_a, *empty_a, *full_w, *empty_w;
+    volatile uint32_t* built;                                  // [SA]
+    uint32_t a_tm0;                                            // TMEM address (lane 0) of stage 0
+    __device__ __forceinline__ void carve(unsigned char* base, uint64_t* bars, volatile uint32_t* built_) {
+        w_base = base;
+        full_a = bars; empty_a = bars + SA; full_w = bars + 2 * SA; empty_w = full_w + SW;
+        built = built_;
+    }
+    __device__ __forceinline__ void init() {                  // one thread
+        for (int s = 0; s < SA; ++s) { mbar_init(&full_a[s], 128); mbar_init(&empty_a[s], 1); built[s] = 0xffffffffu; }
+        for (int s = 0; s < SW; ++s) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], 1); }
+    }
+    // TMA warp (one lane): the 2*na half-atoms of one GEMM; wq = running half-atom counter of this CTA
+    __device__ __forceinline__ void tma_gemm(uint32_t& wq, int na, const float* wimg) const {
+        for (int h = 0; h < 2 * na; ++h, ++wq) {
+            const uint32_t s = wq % SW, r = wq / SW;
+            if (r > 0) mbar_wait(&empty_w[s], (r - 1) & 1);
+            mbar_arrive_expect_tx(&full_w[s], W_BYTES);
+            bulk_g2s(w_base + s * W_BYTES, wimg + (size_t)h * NP * ATOM_K, W_BYTES, &full_w[s]);
+        }
+    }
+    // MMA warp (one lane): the ceil(H / 16) chunks of one GEMM into accumulator d_tmem; g = running GEMM counter, wq as above
+    __device__ __forceinline__ void mma_gemm(uint32_t& g, uint32_t& wq, int na, int H, uint32_t d_tmem) const {
+        constexpr uint32_t idesc = instr_desc_tf32(NP), idesc_mix = instr_desc_mix(NP, FMT);
+        const int nch = (H + 15) >> 4;
+        (void)na;
+        uint32_t w_hi = 0, w_mix = 0;
+        for (int c = 0; c < nch; ++c) {
+            const uint32_t q = g * (uint32_t)nch + (uint32_t)c, s = q % SA, r = q / SA;
+            if ((c & 1) == 0) {                                // first chunk of a 32-wide atom: both weight halves
+                const uint32_t sh = wq % SW, rh = wq / SW, sm = (wq + 1) % SW, rm = (wq + 1) / SW;
+                mbar_wait(&full_w[sh], rh & 1);
+                mbar_wait(&full_w[sm], rm & 1);
+                w_hi = smem_u32(w_base + sh * W_BYTES); w_mix = smem_u32(w_base + sm * W_BYTES);
+            }
+            mbar_wait(&full_a[s], r & 1 GB_TAG((int)(g * 16 + c)));
+            fence_after_sync();
+            const int kvalid = H - 16 * c;
+            const int ksteps = kvalid >= 16 ? 2 : (kvalid + 7) / 8;
+            const uint32_t a_t = a_tm0 + s * STAGE_COLS, kb = 2u * (uint32_t)(c & 1);
+            for (int kk = 0; kk < ksteps; ++kk) mma_tf32_ts(d_tmem, a_t + kk * 8, smem_desc(w_hi + (kb + kk) * 32), idesc, (c | kk) != 0);
+            for (int kk = 0; kk < ksteps; ++kk) mma_f16_ts(d_tmem, a_t + 16 + kk * 8, smem_desc(w_mix + (kb + kk) * 32), idesc_mix, 1);
+            mma_commit(&empty_a[s]);
+            if ((c & 1) || c == nch - 1) {
+                mma_commit(&empty_w[wq % SW]);
+                mma_commit(&empty_w[(wq + 1) % SW]);
+                wq += 2;
+            }
+        }
+        ++g;
+    }
+    // worker: this thread's row of chunk c (16 K columns as 8 pairs) of the CTA's g-th GEMM; lane_off = (32 * (warp & 3)) << 16;
+    // `leader` = one thread of the part (it publishes the round)
+    __device__ __forceinline__ void put(uint32_t g, int c, int nch, uint32_t lane_off, bool leader, const f2 (&x)[8]) const {
+        const uint32_t q = g * (uint32_t)nch + (uint32_t)c, s = q % SA, r = q / SA;
+        float hi[16]; uint32_t mix[16];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {                        // K step k of the chunk: x[4k .. 4k + 3]
+            f2 h[4], l[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                h[i] = make_float2(tf32_hi(x[4 * k + i].x), tf32_hi(x[4 * k + i].y));
+                l[i] = fma2(h[i], f2s(-1.f), x[4 * k + i]);
+                hi[8 * k + 2 * i] = h[i].x; hi[8 * k + 2 * i + 1] = h[i].y;
+                mix[8 * k + i] = pack16<FMT>(l[i].x, l[i].y);
+                mix[8 * k + 4 + i] = pack16<FMT>(h[i].x, h[i].y);
+            }
+        }
+        if (r > 0) {
+            while ((int)built[s] < (int)r - 1) { }            // (the leader of this part may already have published r)
+            mbar_wait(&empty_a[s], (r - 1) & 1 GB_TAG((int)(g * 16 + c)));
+        }
+        if (leader) built[s] = r;
+        fence_after_sync();
+        const uint32_t t = a_tm0 + s * STAGE_COLS + lane_off;
+        tmem_st16(t, hi);
+        tmem_st16_u(t + 16, mix);
+        tmem_st_wait();
+        fence_before_sync();
+        mbar_arrive(&full_a[s]);
+    }
+    __device__ __forceinline__ void put(uint32_t g, int c, int nch, uint32_t lane_off, bool leader, const float4 (&x)[4]) const {
+        const f2 y[8] = {lo2(x[0]), hi2(x[0]), lo2(x[1]), hi2(x[1]), lo2(x[2]), hi2(x[2]), lo2(x[3]), hi2(x[3])};
+        put(g, c, nch, lane_off, leader, y);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Staged node projections.  The first edge Linear is factorised per node (P = h [W_a | W_b] + b, kernels.h), so the operand
 // build needs Pa[row] + Pb[col] per edge: ~10 edges share every row.  Instead of 2 x 16-byte L2 gathers per edge and
 // 4 columns (5x the unique bytes, on the same L2->SM path that streams the weights), two loader warps copy the 32-column

@@ -24,8 +24,11 @@ __device__ unsigned int gb_tl_den_n[5];
 
 template <int NP>
 struct TcEdgeCfg {
-    static constexpr int ACC_STRIDE = NP <= 64 ? 64 : 256;   // two accumulators: the MMAs of tile k+1 run during the epilogue of tile k
-    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+#ifndef GB_DEN_ACC_STRIDE
+#define GB_DEN_ACC_STRIDE 256
+#endif
+    static constexpr int ACC_STRIDE = NP <= 64 ? 64 : GB_DEN_ACC_STRIDE;   // two accumulators: the MMAs of tile k+1 run during the epilogue of tile k
+    static constexpr int TMEM_COLS = NP <= 64 ? 128 : 512;
 #ifndef GB_DEN_AT
 #define GB_DEN_AT 1
 #endif

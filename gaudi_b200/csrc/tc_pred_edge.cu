@@ -5,6 +5,7 @@
 // A K-atoms (chunk ch = 16-byte chunks 4(ch&1)..+3 of atom ch/2) and in the epilogues, so every atom is built by two
 // parts (256 threads).  Two accumulators live in TMEM (columns [0,NP) and [256,256+NP)): the epilogue of GEMM 1 produces the A
 // atoms of GEMM 2 on the fly, chunk by chunk, while the MMA warp consumes them.
+#include <type_traits>
 #include "tc_common.cuh"
 #include "kernels.h"
 
@@ -19,6 +20,12 @@
 #endif
 #ifndef GB_SV_D
 #define GB_SV_D SV_FX       // 16-bit code of the saved SiLU derivatives (tc_common.cuh)
+#endif
+#ifndef GB_FWD_AT
+#define GB_FWD_AT 1         // forward: activation operands in tensor memory (half-atom stages)
+#endif
+#ifndef GB_BWD_AT
+#define GB_BWD_AT 0         // backward: shared-memory activation ring (see TcPredCfg)
 #endif
 #ifndef GB_BWD_SA
 #define GB_BWD_SA 3         // backward: activation (A operand) ring stages
@@ -39,15 +46,22 @@ __device__ unsigned int gb_tl_pred_n[5];
 #define TLW(code) do {} while (0)
 #endif
 
-template <int NP>
+template <int NP, bool AT_WANTED>
 struct TcPredCfg {
     // bf16 correction terms in both directions: fp16 would be 3x more accurate for O(1) activations, but it has no range for the
     // gradients of the backward and it overflows on the forward too (random-init trajectories reach |x| ~ 1e3, i.e. squared
     // distances and pre-activations beyond 65504: the 1000-step chain test diverged with fp16)
-    using R = Rings<NP, MIX_BF16>;
-    using RB = Rings<NP, MIX_BF16, (NP > 208 ? 2 : GB_BWD_SW), (NP > 208 ? 2 : GB_BWD_SA)>;    // NP = 256: two + two is what fits
-    static constexpr int A_BYTES = R::A_BYTES;
-    static constexpr int A_STAGE = R::A_STAGE;
+    // activation operands in tensor memory (RingsH, tc_common.cuh) when the two accumulators leave 96 TMEM columns: NP <= 208.
+    // Hidden 256 (2 x 256 = 512 columns) keeps the shared-memory activation ring.  Measured at the bench shape: forward 1.113 ->
+    // 1.074 ms; backward 1.143 -> 1.210 ms -- its operand builds are fast enough to be paced by the tensor pipe, and three
+    // half-atom stages let the four worker parts run only 1.5 atoms ahead instead of 3, so the backward keeps the shared-memory
+    // ring (GB_BWD_AT=1 selects the tested tensor-memory form).
+    static constexpr bool AT = AT_WANTED && 2 * NP + 96 <= 512;
+    using RS = Rings<NP, MIX_BF16>;
+    using RSB = Rings<NP, MIX_BF16, (NP > 208 ? 2 : GB_BWD_SW), (NP > 208 ? 2 : GB_BWD_SA)>;    // NP = 256: two + two is what fits
+    using RH = RingsH<NP, MIX_BF16>;
+    using R = typename std::conditional<AT, RH, RS>::type;
+    using RB = typename std::conditional<AT, RH, RSB>::type;
     static constexpr int NPARTS = GB_PRED_NPARTS;                          // worker parts of 4 warps; part p owns 16-column chunks ch == p (mod 4)
     static constexpr int NWORK = 128 * NPARTS;
     static constexpr int THREADS = 64 + NWORK;
@@ -55,7 +69,7 @@ struct TcPredCfg {
     static constexpr int MYCH = (MAXCH + NPARTS - 1) / NPARTS;
     static constexpr int EF_STRIDE = 17;
     static constexpr int BAR_BYTES = 512;                                  // up to 64 mbarriers + the TMEM address slot
-    static constexpr int D2_COL = 256;
+    static constexpr int D2_COL = AT ? NP + RH::TMEM_COLS : 256;             // accumulator 2 (AT: behind the three activation stages)
     // backward only: one extra producer warp streams the saved activations (16-column chunks of the plane layouts of
     // tc_common.cuh: 2 planes x 128 rows x 16 B = 4 KB for the 16-bit derivative codes, 4 planes = 8 KB for the fp32 pre2,
     // contiguous in HBM) through a ring of 8 KB slots (more than one chunk per worker part in flight: with one slot per part the
@@ -87,8 +101,8 @@ __device__ __forceinline__ float psum_parts(const float* red, int r) {
 // so that GEMM 1 of tile k+1 runs on the tensor pipe while the workers are in epilogue 2 of tile k, and GEMM 2 of tile k while they
 // build tile k+1 (accumulator 1 is free again once epilogue 1 has read it, accumulator 2 once epilogue 2 has).
 template <int NP>
-struct TcFwdCfg : TcPredCfg<NP> {
-    using B = TcPredCfg<NP>;
+struct TcFwdCfg : TcPredCfg<NP, GB_FWD_AT != 0> {
+    using B = TcPredCfg<NP, GB_FWD_AT != 0>;
     static constexpr int AUX_WARP = 2 + 4 * B::NPARTS;
     static constexpr int THREADS = B::THREADS + 64;
     static constexpr int GEO_NF = 6;                                       // P-stage rows (row | col << 16), radial, edge_attr, unit vector (3)
@@ -108,7 +122,9 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
     // instead of generic LD / ST for every staging and operand access)
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::R::BYTES);
-    typename CF::R rg; rg.carve(base, bars);
+    typename CF::R rg;
+    if constexpr (CF::AT) rg.carve(base, bars, reinterpret_cast<volatile uint32_t*>(base + CF::R::BYTES + 448));   // built[3], inside the barrier block
+    else rg.carve(base, bars);
     uint64_t* d1_full = bars + CF::R::NBARS; uint64_t* d2_full = d1_full + 1; uint64_t* d1_empty = d2_full + 1; uint64_t* d2_empty = d1_empty + 1;
     uint64_t* geo_full = d2_empty + 1; uint64_t* geo_empty = geo_full + CF::NGEO;
     uint64_t* ps_full = geo_empty + CF::NGEO; uint64_t* ps_empty = ps_full + 4;
@@ -122,7 +138,7 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        rg.init(256);
+        if constexpr (CF::AT) rg.init(); else rg.init(256);
         mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d1_empty, CF::NWORK); mbar_init(d2_empty, CF::NWORK);
         for (int b = 0; b < CF::NGEO; ++b) { mbar_init(&geo_full[b], 1); mbar_init(&geo_empty[b], CF::NWORK); }
         ps.init();
@@ -138,6 +154,7 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    if constexpr (CF::AT) rg.a_tm0 = tmem_base + NP;
     const Graph& g = a.g;
     const int na = (H + ATOM_K - 1) / ATOM_K;
     const int npl = sv_planes(H);                                // 8-column planes of the 16-bit saved activations
@@ -216,6 +233,9 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
         const int r = group * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(group * 32) << 16);
         const int nchunks = (H + 15) / 16;
+        const uint32_t lane_off = (uint32_t)(group * 32) << 16;
+        const bool leader = group == 0 && lane == 0;
+        (void)lane_off; (void)leader;
         float* my_ef = ef_s + part * 128 * CF::EF_STRIDE;
         float* red1 = red_s; float* red2 = red_s + CF::NPARTS * 128;
         const int tlr = (lane == 0 && group == 0) ? (part == 0 ? 0 : (part == 3 ? 1 : -1)) : -1;
@@ -261,7 +281,8 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
                 }
                 ps.release(k, j, na);
                 TLW(20 + j);
-                rg.put_chunk(2 * k, j, na, r, half, x);
+                if constexpr (CF::AT) { if (2 * j + half < nchunks) rg.put(2 * k, 2 * j + half, nchunks, lane_off, leader, x); }
+                else rg.put_chunk(2 * k, j, na, r, half, x);
                 TLW(30 + j);
             }
         };
@@ -325,7 +346,8 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
                         my_ef[r * CF::EF_STRIDE + 4 * c] = x[c].x; my_ef[r * CF::EF_STRIDE + 4 * c + 1] = x[c].y;
                         my_ef[r * CF::EF_STRIDE + 4 * c + 2] = x[c].z; my_ef[r * CF::EF_STRIDE + 4 * c + 3] = x[c].w;
                     }
-                    rg.put_chunk(2 * k + 1, ch >> 1, na, r, half, x);
+                    if constexpr (CF::AT) rg.put(2 * k + 1, ch, nchunks, lane_off, leader, x);
+                    else rg.put_chunk(2 * k + 1, ch >> 1, na, r, half, x);
                     bar_named(BAR_PART + part, 128);
                     for (int nl = r >> 4; nl < nn; nl += 8) {
                         const int col = r & 15, c = ch * 16 + col;
@@ -334,10 +356,11 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
                         if (c < H) a.agg[(size_t)(node_lo + nl) * H + c] = sum;
                     }
                     bar_named(BAR_PART + part, 128);
-                } else if (ch < 2 * na) {
+                } else if (!CF::AT && ch < 2 * na) {
                     // chunk beyond the hidden width but inside the last atom: publish zeros so the atom completes
+                    // (the half-atom stages of the AT form have no such chunk)
                     float4 x[4] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-                    rg.put_chunk(2 * k + 1, ch >> 1, na, r, half, x);
+                    if constexpr (!CF::AT) rg.put_chunk(2 * k + 1, ch >> 1, na, r, half, x);
                 }
             }
             // ---- GEMM 1 operand of the next tile (its MMAs overlap epilogue 2 below) ----
@@ -407,16 +430,17 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
 // GEMM 1 of tile k+1 runs while the workers are in epilogue 2 of tile k; accumulator 1 (which also parks g_ef between epilogue 1
 // and build2) is released after build2(k), accumulator 2 after epilogue2(k).
 template <int NP>
-struct TcBwdCfg : TcPredCfg<NP> {
-    using B = TcPredCfg<NP>;
+struct TcBwdCfg : TcPredCfg<NP, GB_BWD_AT != 0> {
+    using B = TcPredCfg<NP, GB_BWD_AT != 0>;
     static constexpr int SV_WARP = 2 + 4 * B::NPARTS, GEO_WARP = SV_WARP + 1;
     static constexpr int THREADS = B::THREADS + 64;
     static constexpr int GEO_NF = 8;                                       // local row node, g_phi, d (3), g_u (3)
     static constexpr int GEO_WORDS = geo_words(GEO_NF);
-    static constexpr int SV_SLOTS = NP > 208 ? 6 : GB_BWD_SVS;             // saved-activation ring: slots of 8 KB
+    static constexpr int SV_SLOTS = B::AT ? 7 : (NP > 208 ? 6 : GB_BWD_SVS);  // saved-activation ring: slots of 8 KB
     static constexpr int STG_WARP_FLOATS = 32 * 8;                         // per-warp transpose block of epilogue 2: 32 rows x 8 columns
+    static constexpr int GA_SCRATCH_ROWS = B::AT ? 32 : 0;                 // AT form: staged g_agg rows of a tile (else they borrow the A ring)
     static constexpr int SCRATCH = 6 * NP * 4 + 2 * B::NPARTS * 128 * 4 + SV_SLOTS * B::SV_SLOT_BYTES + (B::NWORK / 32) * STG_WARP_FLOATS * 4 +
-                                   2 * GEO_WORDS * 4 + 64;
+                                   2 * GEO_WORDS * 4 + GA_SCRATCH_ROWS * NP * 4 + 64;
     static constexpr int SMEM = B::RB::BYTES + 1024 + B::BAR_BYTES + SCRATCH;
     static_assert(SMEM <= 232448, "shared memory budget (backward)");
 };
@@ -456,7 +480,9 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
     // instead of generic LD / ST for every staging and operand access)
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + CF::RB::BYTES);
-    typename CF::RB rg; rg.carve(base, bars);
+    typename CF::RB rg;
+    if constexpr (CF::AT) rg.carve(base, bars, reinterpret_cast<volatile uint32_t*>(base + CF::RB::BYTES + 448));   // built[3], inside the barrier block
+    else rg.carve(base, bars);
     uint64_t* d1_full = bars + CF::RB::NBARS; uint64_t* d2_full = d1_full + 1; uint64_t* d1_empty = d2_full + 1; uint64_t* d2_empty = d1_empty + 1;
     uint64_t* sv_full = d2_empty + 1; uint64_t* sv_empty = sv_full + SVS;
     uint64_t* geo_full = sv_empty + SVS; uint64_t* geo_empty = geo_full + 2;
@@ -468,10 +494,13 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
     float* stg_s = reinterpret_cast<float*>(sv_buf + SVS * CF::SV_SLOT_BYTES);           // [16 warps][32][8]
     int* geo_s = reinterpret_cast<int*>(stg_s + (CF::NWORK / 32) * CF::STG_WARP_FLOATS);  // [2][GEO_WORDS]
     const SvRing sv{sv_buf, sv_full, sv_empty, sv_round};
+    unsigned char* ga_scratch;
+    if constexpr (CF::AT) ga_scratch = reinterpret_cast<unsigned char*>(geo_s + 2 * CF::GEO_WORDS);
+    else ga_scratch = rg.a_base;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        rg.init(256);
+        if constexpr (CF::AT) rg.init(); else rg.init(256);
         mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d1_empty, CF::NWORK); mbar_init(d2_empty, CF::NWORK);
         for (int s = 0; s < SVS; ++s) { mbar_init(&sv_full[s], 1); mbar_init(&sv_empty[s], 128); sv_round[s] = 0xffffffffu; }
         for (int b = 0; b < 2; ++b) { mbar_init(&geo_full[b], 1); mbar_init(&geo_empty[b], CF::NWORK); }
@@ -489,6 +518,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    if constexpr (CF::AT) rg.a_tm0 = tmem_base + NP;
     const Graph& g = a.g;
     const int na = (H + ATOM_K - 1) / ATOM_K;
     const int my_tiles = (int)blockIdx.x < g.n_tiles ? (g.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -598,6 +628,9 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
         const int nchunks = (H + 15) / 16;
         const int tlr = (lane == 0 && group == 0) ? (part == 0 ? 0 : (part == 3 ? 1 : -1)) : -1;
         (void)tlr;
+        const uint32_t lane_off = (uint32_t)(group * 32) << 16;
+        const bool leader = group == 0 && lane == 0;
+        (void)lane_off; (void)leader;
         float* stg = stg_s + (warp - 2) * CF::STG_WARP_FLOATS;
         uint32_t sq = 0;                                             // first saved-activation chunk of the current stream
         // ---- GEMM 1 operand of the CTA's k-th tile: g_pre3 = g_phi * w_c * SiLU'(pre3) ----
@@ -632,7 +665,8 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                     for (int c = 0; c < 8; ++c) x[c] = f2s(0.f);
                 }
                 TLW(110 + j);
-                rg.put_chunk2(2 * k, j, na, r, half, x);
+                if constexpr (CF::AT) { if (ch < nchunks) rg.put(2 * k, ch, nchunks, lane_off, leader, x); }
+                else rg.put_chunk2(2 * k, j, na, r, half, x);
                 TLW(120 + j);
             }
             sq += nchunks;
@@ -652,13 +686,16 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
             fence_after_sync();
             // the tile's rows of g_agg (one per row node, shared by its ~9 edges) are copied once, coalesced, into the A ring: every
             // operand atom stored so far (GEMM 1 of this tile was the last) has been consumed, and nothing is stored before build2
-            constexpr int GA_ROWS = CF::A_STAGE / (NP * 4);                // rows per ring stage (A hi + A lo)
-            const bool ga_staged = nn <= CF::RB::SA * GA_ROWS;
+            // (AT form: there is no activation ring in shared memory; a dedicated block of GA_SCRATCH_ROWS rows takes its place)
+            constexpr int GA_STAGE_BYTES = CF::AT ? CF::GA_SCRATCH_ROWS * NP * 4 : CF::RSB::A_STAGE;
+            constexpr int GA_ROWS = GA_STAGE_BYTES / (NP * 4);             // rows per ring stage (A hi + A lo)
+            unsigned char* ga_base = ga_scratch;
+            const bool ga_staged = nn <= (CF::AT ? 1 : CF::RSB::SA) * GA_ROWS;
             if (ga_staged) {
                 const int h4 = H >> 2;
                 for (int idx = (warp - 2) * 32 + lane; idx < nn * h4; idx += CF::NWORK) {
                     const int nl = idx / h4, k4 = idx - nl * h4;
-                    float* dst = reinterpret_cast<float*>(rg.a_base + (nl / GA_ROWS) * CF::A_STAGE) + (nl % GA_ROWS) * NP + 4 * k4;
+                    float* dst = reinterpret_cast<float*>(ga_base + (nl / GA_ROWS) * GA_STAGE_BYTES) + (nl % GA_ROWS) * NP + 4 * k4;
                     *reinterpret_cast<float4*>(dst) = __ldg(reinterpret_cast<const float4*>(a.g_agg + (size_t)(node_lo + nl) * a.ld_gagg + 4 * k4));
                 }
             }
@@ -667,7 +704,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
             TLW(43);
             f2 plog2 = f2s(0.f), pdot2 = f2s(0.f);
             const int rloc = gi[GEO_HDR + r];
-            const float* ga_row = ga_staged ? reinterpret_cast<const float*>(rg.a_base + (rloc / GA_ROWS) * CF::A_STAGE) + (rloc % GA_ROWS) * NP
+            const float* ga_row = ga_staged ? reinterpret_cast<const float*>(ga_base + (rloc / GA_ROWS) * GA_STAGE_BYTES) + (rloc % GA_ROWS) * NP
                                             : a.g_agg + (size_t)(node_lo + rloc) * a.ld_gagg;
             // chunk-streaming: g_ef = accumulator 1 + g_agg[row] goes BACK to tensor memory (same columns) instead of waiting in 64
             // registers for the row-wide attention reduction; the operand build of GEMM 2 reads it again.  The TMEM read of the
@@ -718,7 +755,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                 float v[16];
                 if (part < nchunks) tmem_ld16_issue_f(lane_addr + part * 16, v);
 #pragma unroll 1
-                for (int ch = part; ch < 2 * na; ch += CF::NPARTS) {
+                for (int ch = part; ch < (CF::AT ? nchunks : 2 * na); ch += CF::NPARTS) {
                     f2 x[8];
                     if (ch < nchunks) {
                         tmem_ld_wait16(v);
@@ -742,7 +779,8 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                         for (int c = 0; c < 8; ++c) x[c] = f2s(0.f);
                     }
                     TLW(320 + ch);
-                    rg.put_chunk2(2 * k + 1, ch >> 1, na, r, half, x);
+                    if constexpr (CF::AT) rg.put(2 * k + 1, ch, nchunks, lane_off, leader, x);
+                    else rg.put_chunk2(2 * k + 1, ch >> 1, na, r, half, x);
                     TLW(340 + ch);
                 }
             }
@@ -854,7 +892,6 @@ extern "C" int gb_debug_timeline_pred(unsigned long long* out, unsigned int* n, 
 
 template <int NP>
 static void launch_bwd_t(const PredEdgeArgs& a, const float* wcimg_nt, const float* w2img_nt, int H, cudaStream_t s) {
-    using CF = TcPredCfg<NP>;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(tc_pred_edge_bwd_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcBwdCfg<NP>::SMEM);
@@ -936,7 +973,6 @@ void launch_pred_bwd_reduce(int H, const PredEdgeArgs& a, cudaStream_t s) {
 
 template <int NP>
 static void launch_fwd_t(bool save, const PredEdgeArgs& a, const float* w2img, const float* wcimg, int H, cudaStream_t s) {
-    using CF = TcPredCfg<NP>;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(tc_pred_edge_fwd_kernel<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcFwdCfg<NP>::SMEM);
