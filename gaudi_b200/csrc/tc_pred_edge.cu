@@ -27,8 +27,11 @@
 #ifndef GB_BWD_AT
 #define GB_BWD_AT 0         // backward: shared-memory activation ring (see TcPredCfg)
 #endif
+#ifndef GB_BWD_GA_TMA
+#define GB_BWD_GA_TMA 1     // backward: the tile's g_agg rows arrive by bulk TMA one tile ahead (two blocks of 16 rows) instead of a staging loop
+#endif
 #ifndef GB_BWD_SA
-#define GB_BWD_SA 3         // backward: activation (A operand) ring stages
+#define GB_BWD_SA (GB_BWD_GA_TMA ? 2 : 3)         // backward: activation (A operand) ring stages (the third one gave 1 %; the g_agg blocks need its room)
 #endif
 
 namespace gb {
@@ -439,8 +442,12 @@ struct TcBwdCfg : TcPredCfg<NP, GB_BWD_AT != 0> {
     static constexpr int SV_SLOTS = B::AT ? 7 : (NP > 208 ? 6 : GB_BWD_SVS);  // saved-activation ring: slots of 8 KB
     static constexpr int STG_WARP_FLOATS = 32 * 8;                         // per-warp transpose block of epilogue 2: 32 rows x 8 columns
     static constexpr int GA_SCRATCH_ROWS = B::AT ? 32 : 0;                 // AT form: staged g_agg rows of a tile (else they borrow the A ring)
+    // g_agg rows of the coming tile by bulk TMA (SV warp) into one of two blocks: tiles with more row nodes read g_agg from L2
+    static constexpr bool GA_TMA = GB_BWD_GA_TMA && !B::AT && NP <= 208;
+    static constexpr int GA_TMA_ROWS = 16;
+    static constexpr int GA_BLOCK_BYTES = GA_TMA_ROWS * NP * 4;
     static constexpr int SCRATCH = 6 * NP * 4 + 2 * B::NPARTS * 128 * 4 + SV_SLOTS * B::SV_SLOT_BYTES + (B::NWORK / 32) * STG_WARP_FLOATS * 4 +
-                                   2 * GEO_WORDS * 4 + GA_SCRATCH_ROWS * NP * 4 + 64;
+                                   2 * GEO_WORDS * 4 + GA_SCRATCH_ROWS * NP * 4 + (GA_TMA ? 2 * GA_BLOCK_BYTES : 0) + 64;
     static constexpr int SMEM = B::RB::BYTES + 1024 + B::BAR_BYTES + SCRATCH;
     static_assert(SMEM <= 232448, "shared memory budget (backward)");
 };
@@ -486,7 +493,8 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
     uint64_t* d1_full = bars + CF::RB::NBARS; uint64_t* d2_full = d1_full + 1; uint64_t* d1_empty = d2_full + 1; uint64_t* d2_empty = d1_empty + 1;
     uint64_t* sv_full = d2_empty + 1; uint64_t* sv_empty = sv_full + SVS;
     uint64_t* geo_full = sv_empty + SVS; uint64_t* geo_empty = geo_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(geo_empty + 2);
+    uint64_t* ga_full = geo_empty + 2; uint64_t* ga_empty = ga_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ga_empty + 2);
     volatile uint32_t* sv_round = reinterpret_cast<volatile uint32_t*>(base + CF::RB::BYTES + 384);     // [SV_SLOTS], inside the barrier block
     float* vec_s = reinterpret_cast<float*>(base + CF::RB::BYTES + CF::BAR_BYTES);     // [6][NP]: w_r, w_a, -, att_w, -, wc_last
     float* red_s = vec_s + 6 * NP;                                                       // [2][NPARTS][128]
@@ -495,7 +503,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
     int* geo_s = reinterpret_cast<int*>(stg_s + (CF::NWORK / 32) * CF::STG_WARP_FLOATS);  // [2][GEO_WORDS]
     const SvRing sv{sv_buf, sv_full, sv_empty, sv_round};
     unsigned char* ga_scratch;
-    if constexpr (CF::AT) ga_scratch = reinterpret_cast<unsigned char*>(geo_s + 2 * CF::GEO_WORDS);
+    if constexpr (CF::AT || CF::GA_TMA) ga_scratch = reinterpret_cast<unsigned char*>(geo_s + 2 * CF::GEO_WORDS);
     else ga_scratch = rg.a_base;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -504,6 +512,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
         mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d1_empty, CF::NWORK); mbar_init(d2_empty, CF::NWORK);
         for (int s = 0; s < SVS; ++s) { mbar_init(&sv_full[s], 1); mbar_init(&sv_empty[s], 128); sv_round[s] = 0xffffffffu; }
         for (int b = 0; b < 2; ++b) { mbar_init(&geo_full[b], 1); mbar_init(&geo_empty[b], CF::NWORK); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&ga_full[b], 1); mbar_init(&ga_empty[b], CF::NWORK); }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -570,12 +579,29 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                     bulk_g2s(sv.buf + s * CF::SV_SLOT_BYTES, src + off, bytes, &sv_full[s]);
                 }
             };
+            // g_agg rows (one per row node, shared by its ~9 edges) of the CTA's kk-th tile -> block kk & 1, one bulk copy per row
+            auto ga_load = [&](int tile_, uint32_t kk) {
+                if constexpr (CF::GA_TMA) {
+                    const uint32_t b = kk & 1, use = kk >> 1;
+                    if (use > 0) mbar_wait(&ga_empty[b], (use - 1) & 1);
+                    const int4 ti = __ldg(g.tile_info + tile_);
+                    if (ti.y <= CF::GA_TMA_ROWS) {
+                        mbar_arrive_expect_tx(&ga_full[b], (uint32_t)(ti.y * H * 4));
+                        for (int nl = 0; nl < ti.y; ++nl)
+                            bulk_g2s(ga_scratch + b * CF::GA_BLOCK_BYTES + nl * NP * 4, a.g_agg + (size_t)(ti.x + nl) * a.ld_gagg, (uint32_t)(H * 4), &ga_full[b]);
+                    } else {
+                        mbar_arrive(&ga_full[b]);                // too many row nodes: the workers read g_agg from L2
+                    }
+                }
+            };
             const size_t tstride = (size_t)planes * (SV_PLANE_BYTES / 4);          // floats per tile: derivative codes
             const size_t tstride_p = (size_t)(H / 4) * (SV_PLANE_BYTES / 4);       //                  pre2
+            ga_load(blockIdx.x, 0);
             stream(a.sv_d3 + (size_t)blockIdx.x * tstride, false);
             int tile = blockIdx.x;
             for (int k = 0; k < my_tiles; ++k, tile += gridDim.x) {
                 stream(a.sv_pre2 + (size_t)tile * tstride_p, true);
+                if (k + 1 < my_tiles) ga_load(tile + gridDim.x, (uint32_t)k + 1);
                 stream(a.sv_pre2 + (size_t)tile * tstride_p, true);
                 if (k + 1 < my_tiles) stream(a.sv_d3 + (size_t)(tile + gridDim.x) * tstride, false);
                 stream(a.sv_d1 + (size_t)tile * tstride, false);
@@ -687,11 +713,13 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
             // the tile's rows of g_agg (one per row node, shared by its ~9 edges) are copied once, coalesced, into the A ring: every
             // operand atom stored so far (GEMM 1 of this tile was the last) has been consumed, and nothing is stored before build2
             // (AT form: there is no activation ring in shared memory; a dedicated block of GA_SCRATCH_ROWS rows takes its place)
-            constexpr int GA_STAGE_BYTES = CF::AT ? CF::GA_SCRATCH_ROWS * NP * 4 : CF::RSB::A_STAGE;
+            // (GA_TMA form: the rows were copied by the SV warp's bulk TMA one tile ahead into block k & 1 -- no staging loop here)
+            constexpr int GA_STAGE_BYTES = CF::GA_TMA ? CF::GA_BLOCK_BYTES : (CF::AT ? CF::GA_SCRATCH_ROWS * NP * 4 : CF::RSB::A_STAGE);
             constexpr int GA_ROWS = GA_STAGE_BYTES / (NP * 4);             // rows per ring stage (A hi + A lo)
-            unsigned char* ga_base = ga_scratch;
-            const bool ga_staged = nn <= (CF::AT ? 1 : CF::RSB::SA) * GA_ROWS;
-            if (ga_staged) {
+            unsigned char* ga_base = ga_scratch + (CF::GA_TMA ? (k & 1) * CF::GA_BLOCK_BYTES : 0);
+            const bool ga_staged = nn <= (CF::AT || CF::GA_TMA ? 1 : CF::RSB::SA) * GA_ROWS;
+            if constexpr (CF::GA_TMA) mbar_wait(&ga_full[k & 1], (k >> 1) & 1);
+            if (!CF::GA_TMA && ga_staged) {
                 const int h4 = H >> 2;
                 for (int idx = (warp - 2) * 32 + lane; idx < nn * h4; idx += CF::NWORK) {
                     const int nl = idx / h4, k4 = idx - nl * h4;
@@ -738,6 +766,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                 }
                 tmem_st_wait();
             }
+            if constexpr (CF::GA_TMA) mbar_arrive(&ga_empty[k & 1]);      // this tile's g_agg block may be overwritten (two tiles from now)
             sq += nchunks;
             red_s[part * 128 + r] = plog2.x + plog2.y;
             red_s[CF::NPARTS * 128 + part * 128 + r] = pdot2.x + pdot2.y;
