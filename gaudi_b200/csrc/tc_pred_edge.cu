@@ -109,7 +109,8 @@ struct TcFwdCfg : TcPredCfg<NP, GB_FWD_AT != 0> {
     static constexpr int AUX_WARP = 2 + 4 * B::NPARTS;
     static constexpr int THREADS = B::THREADS + 64;
     static constexpr int GEO_NF = 6;                                       // P-stage rows (row | col << 16), radial, edge_attr, unit vector (3)
-    static constexpr int GEO_WORDS = geo_words(GEO_NF);
+    static constexpr int GEO_NODE = geo_words(GEO_NF);                     // then per row node (up to 128): x (3), node mask -- read on the tile's tail
+    static constexpr int GEO_WORDS = GEO_NODE + 4 * 128;
     static constexpr int NGEO = 3;
     static constexpr int SCRATCH = 6 * NP * 4 + 2 * B::NPARTS * 128 * 4 + B::NPARTS * 128 * B::EF_STRIDE * 4 + NGEO * GEO_WORDS * 4 + 128 * 3 * 4 + PS_BYTES + 64;
     static constexpr int SMEM = B::R::BYTES + 1024 + B::BAR_BYTES + SCRATCH;
@@ -195,6 +196,11 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
             float* gf = reinterpret_cast<float*>(gi);
             if (lane == 0) { gi[0] = m.node_lo; gi[1] = m.nn; gi[2] = m.e_lo; gi[3] = m.ne; }
             for (int i = lane; i <= m.nn; i += 32) gi[4 + i] = __ldg(g.rowptr + m.node_lo + i) - m.e_lo;
+            for (int i = lane; i < m.nn; i += 32) {
+                const int node = m.node_lo + i;
+                gf[CF::GEO_NODE + 4 * i] = a.x[3 * node]; gf[CF::GEO_NODE + 4 * i + 1] = a.x[3 * node + 1]; gf[CF::GEO_NODE + 4 * i + 2] = a.x[3 * node + 2];
+                gf[CF::GEO_NODE + 4 * i + 3] = g.node_mask[node];
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int r = lane + 32 * q;
@@ -413,7 +419,7 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
                 float sum = 0.f;
                 for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += tr_s[3 * mm + d];
                 const int node = node_lo + nl;
-                a.x_out[3 * node + d] = (a.x[3 * node + d] + sum) * g.node_mask[node];
+                a.x_out[3 * node + d] = (gf[CF::GEO_NODE + 4 * nl + d] + sum) * gf[CF::GEO_NODE + 4 * nl + 3];     // x and mask came with the geometry block
             }
             mbar_arrive(&geo_empty[gb_]);
             TLW(70);
@@ -437,7 +443,7 @@ struct TcBwdCfg : TcPredCfg<NP, GB_BWD_AT != 0> {
     using B = TcPredCfg<NP, GB_BWD_AT != 0>;
     static constexpr int SV_WARP = 2 + 4 * B::NPARTS, GEO_WARP = SV_WARP + 1;
     static constexpr int THREADS = B::THREADS + 64;
-    static constexpr int GEO_NF = 8;                                       // local row node, g_phi, d (3), g_u (3)
+    static constexpr int GEO_NF = 9;                                       // local row node, g_phi, d (3), g_u (3), g_attr so far
     static constexpr int GEO_WORDS = geo_words(GEO_NF);
     static constexpr int SV_SLOTS = B::AT ? 7 : (NP > 208 ? 6 : GB_BWD_SVS);  // saved-activation ring: slots of 8 KB
     static constexpr int STG_WARP_FLOATS = 32 * 8;                         // per-warp transpose block of epilogue 2: 32 rows x 8 columns
@@ -620,9 +626,10 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
             for (int q = 0; q < 4; ++q) {
                 const int r = lane + 32 * q;
                 int rloc = 0;
-                float gphi = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, gux = 0.f, guy = 0.f, guz = 0.f;
+                float gphi = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, gux = 0.f, guy = 0.f, guz = 0.f, gat = 0.f;
                 if (r < m.ne) {
                     const int e = m.e_lo + r, rown = m.row[q], coln = m.col[q];
+                    gat = a.g_attr[e];                       // sum of the later layers (every edge is updated once per launch, by its own tile)
                     rloc = rown - m.node_lo;
                     dx = a.x[3 * rown] - a.x[3 * coln]; dy = a.x[3 * rown + 1] - a.x[3 * coln + 1]; dz = a.x[3 * rown + 2] - a.x[3 * coln + 2];
                     const float nrm = sqrtf(dx * dx + dy * dy + dz * dz + 1e-8f);
@@ -637,6 +644,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                 gi[GEO_HDR + r] = rloc; gf[GEO_HDR + 128 + r] = gphi;
                 gf[GEO_HDR + 256 + r] = dx; gf[GEO_HDR + 384 + r] = dy; gf[GEO_HDR + 512 + r] = dz;
                 gf[GEO_HDR + 640 + r] = gux; gf[GEO_HDR + 768 + r] = guy; gf[GEO_HDR + 896 + r] = guz;
+                gf[GEO_HDR + 1024 + r] = gat;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&geo_full[gb_]);
@@ -885,7 +893,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
             if (part == 0 && valid) {
                 const float g_r = psum_parts<CF::NPARTS>(red_s, r);
                 const float g_a = psum_parts<CF::NPARTS>(red_s + CF::NPARTS * 128, r);
-                a.g_attr[e_lo + r] += g_a;
+                a.g_attr[e_lo + r] = gf[GEO_HDR + 1024 + r] + g_a;         // (the old value came with the geometry block: no load on the tile's tail)
                 const float dx = gf[GEO_HDR + 256 + r], dy = gf[GEO_HDR + 384 + r], dz = gf[GEO_HDR + 512 + r];
                 const float gux = gf[GEO_HDR + 640 + r], guy = gf[GEO_HDR + 768 + r], guz = gf[GEO_HDR + 896 + r];
                 const float nrm = sqrtf(dx * dx + dy * dy + dz * dz + 1e-8f);
