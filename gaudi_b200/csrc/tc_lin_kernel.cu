@@ -26,6 +26,7 @@ using namespace tc;
 
 // Optional per-tile timeline (make EXTRA=-DGB_TIMELINE; tools/lin_timeline.py): clock64 marks of CTA 0 per role.
 #ifdef GB_TIMELINE
+__device__ unsigned long long gb_tl_dur[512];             // per CTA: clock64 from kernel entry to exit
 __device__ unsigned long long gb_tl[3][1024];
 #define TL(role, idx, code) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (idx) < 512) { gb_tl[role][2 * (idx)] = (code); gb_tl[role][2 * (idx) + 1] = clock64(); } } while (0)
 #else
@@ -71,6 +72,9 @@ __global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, GB_LIN_CTAS) tc_lin_ker
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cb = blockIdx.y;
+#ifdef GB_TIMELINE
+    const long long tl_t0 = clock64();
+#endif
     if (tid == 0) {
         for (int s = 0; s < CF::S; ++s) { mbar_init(&full_a[s], CF::NBUILD); mbar_init(&full_w[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&d_full[b], 1); mbar_init(&d_empty[b], CF::NEPI); }
@@ -206,9 +210,33 @@ __global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, GB_LIN_CTAS) tc_lin_ker
             mbar_wait(&d_full[buf], (tcnt >> 1) & 1);
             if (tid == 320) TL(2, 2 * tcnt, 300 + tcnt);
             fence_after_sync();
-            // the TMEM read of the next chunk is in flight while this one is processed
+            // the TMEM read AND the side-input loads (residual / mask / saved pre-activation) of the next chunk are in flight while
+            // this one is processed: with the loads issued and consumed inside one chunk step every step exposed a full L2 / HBM
+            // latency -- the epilogue then took ~11 us per tile instead of ~6.5 and paced every launch that has a side input
+            // (RES_MASK 77 us where the same GEMM without side input takes 45; launch list of round 2e)
             uint32_t vr[16];
+            float4 sd_n[4];
+            float mk_n[4];
+            auto load_side = [&](int ch, float4 (&sd)[4], float (&mk)[4]) {
+                const int c0 = ch * 16 + 4 * piece;
+                const size_t col = (size_t)cb * H + c0;
+                const int row0 = tile * 128 + group * 32 + rsub;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = row0 + 8 * i;
+                    sd[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    mk[i] = 1.f;
+                    if (ch < nchunks && c0 < H && row < a.M) {
+                        if (a.epi == EPI_MUL_DSILU) sd[i] = __ldg(reinterpret_cast<const float4*>(a.aux + (size_t)row * a.ldaux + col));
+                        else if (use_res) {
+                            sd[i] = __ldg(reinterpret_cast<const float4*>(a.res + (size_t)row * a.ldr + col));
+                            if (a.epi == EPI_RES_MASK || a.mask) mk[i] = __ldg(a.mask + row);
+                        }
+                    }
+                }
+            };
             if (part < nchunks) tmem_ld16_issue(lane_addr + buf * 256 + part * 16, vr);
+            load_side(part, sd_n, mk_n);
             for (int ch = part; ch < nchunks; ch += CF::EPARTS) {
                 tmem_ld_wait();
 #pragma unroll
@@ -216,26 +244,16 @@ __global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, GB_LIN_CTAS) tc_lin_ker
                     *reinterpret_cast<uint4*>(stg + lane * CF::STG_PITCH + 4 * q) = make_uint4(vr[4 * q], vr[4 * q + 1], vr[4 * q + 2], vr[4 * q + 3]);
                 __syncwarp();
                 if (ch + CF::EPARTS < nchunks) tmem_ld16_issue(lane_addr + buf * 256 + (ch + CF::EPARTS) * 16, vr);
+                float4 sd[4];
+                float mk[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { sd[i] = sd_n[i]; mk[i] = mk_n[i]; }
+                load_side(ch + CF::EPARTS, sd_n, mk_n);
                 const int c0 = ch * 16 + 4 * piece;
                 if (c0 < H) {
                     const size_t col = (size_t)cb * H + c0;      // column blocks are H wide in the node tensors
                     const float4 b = *reinterpret_cast<const float4*>(bias_s + c0);
                     const int row0 = tile * 128 + group * 32 + rsub;
-                    float4 sd[4];
-                    float mk[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {                 // side inputs first: four independent loads in flight
-                        const int row = row0 + 8 * i;
-                        sd[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        mk[i] = 1.f;
-                        if (row < a.M) {
-                            if (a.epi == EPI_MUL_DSILU) sd[i] = __ldg(reinterpret_cast<const float4*>(a.aux + (size_t)row * a.ldaux + col));
-                            else if (use_res) {
-                                sd[i] = __ldg(reinterpret_cast<const float4*>(a.res + (size_t)row * a.ldr + col));
-                                if (a.epi == EPI_RES_MASK || a.mask) mk[i] = __ldg(a.mask + row);
-                            }
-                        }
-                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int rl = rsub + 8 * i;
@@ -266,10 +284,14 @@ __global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, GB_LIN_CTAS) tc_lin_ker
     fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc<CF::TMEM_COLS>(tmem_base);
+#ifdef GB_TIMELINE
+    if (tid == 0 && blockIdx.y * gridDim.x + blockIdx.x < 512) gb_tl_dur[blockIdx.y * gridDim.x + blockIdx.x] = (unsigned long long)(clock64() - tl_t0);
+#endif
 }
 
 #ifdef GB_TIMELINE
 extern "C" int gb_debug_timeline(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, gb_tl, sizeof(gb_tl)); }
+extern "C" int gb_debug_timeline_dur(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, gb_tl_dur, sizeof(gb_tl_dur)); }
 #endif
 
 template <int NP>

@@ -11,11 +11,18 @@ for _ in range(3):
     y = training._linear(A, W, K, N, b, epi=1)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); y = training._linear(A, W, K, N, b, epi=1); e1.record(); torch.cuda.synchronize()
-print("ms incl pack", e0.elapsed_time(e1))
+e0.record()
+for _ in range(10): y = training._linear(A, W, K, N, b, epi=1)
+e1.record(); torch.cuda.synchronize()
+print("ms per call incl pack (10 calls)", e0.elapsed_time(e1) / 10)
 buf = np.zeros((3, 1024), dtype=np.uint64)
 lib = _lib.lib(); lib.gb_debug_timeline.argtypes = [C.c_void_p]; lib.gb_debug_timeline.restype = C.c_int
 print("rc", lib.gb_debug_timeline(buf.ctypes.data_as(C.c_void_p)))
+dur = np.zeros(512, dtype=np.uint64)
+lib.gb_debug_timeline_dur.argtypes = [C.c_void_p]; lib.gb_debug_timeline_dur.restype = C.c_int
+lib.gb_debug_timeline_dur(dur.ctypes.data_as(C.c_void_p))
+d = np.sort(dur[dur > 0].astype(np.float64)) / 1.9e3
+print(f"per-CTA entry-to-exit: n={len(d)} min {d[0]:.1f} median {d[len(d)//2]:.1f} max {d[-1]:.1f} us")
 ev = []
 for role in range(3):
     for i in range(512):
