@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
         const int group = warp & 3, part = (warp - 2) >> 2, half = part & 1;
         const int r = group * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(group * 32) << 16);
-        const int nchunks = (H + 15) / 16;
+        const int nchunks = (H + 15) / 16, nfull = H >> 4;       // all chunks / chunks whose 16 columns are all real
         const uint32_t lane_off = (uint32_t)(group * 32) << 16;
         const bool leader = group == 0 && lane == 0;
         (void)lane_off; (void)leader;
@@ -312,26 +312,38 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
             fence_after_sync();
             float q[CF::MYCH][16];
             float psum = 0.f;
+            // Two code paths per chunk: a chunk whose 16 columns are all real runs without per-column tests; the last chunk of a
+            // hidden width that is not a multiple of 16 (4 real columns of 16 at H = 196) only touches its real 4-column groups.
+            // The part that owns that extra chunk is the critical path of every chunk phase (4 chunks against 3), and runtime tests
+            // inside ALL chunks cost more than they save (+7 % when tried: they break the scheduling of the unrolled loops).
+            auto e1_chunk = [&](auto tail_t, float (&qr)[16], int ch) {
+                constexpr bool TAIL = decltype(tail_t)::value;
+                tmem_ld16(lane_addr + ch * 16, qr);
 #pragma unroll
-            for (int ci = 0; ci < CF::MYCH; ++ci) {
-                const int ch = part + CF::NPARTS * ci;
-                if (ch < nchunks) {
-                    tmem_ld16(lane_addr + ch * 16, q[ci]);
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {
-                        const int c0 = ch * 16 + 4 * c4;
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const int c0 = ch * 16 + 4 * c4;
+                    if (!TAIL || c0 < H) {
                         float pre[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            pre[e] = q[ci][4 * c4 + e] + vec_s[2 * NP + c0 + e];
+                            pre[e] = qr[4 * c4 + e] + vec_s[2 * NP + c0 + e];
                             const float v = silu_f(pre[e]);
-                            q[ci][4 * c4 + e] = v;
+                            qr[4 * c4 + e] = v;
                             psum = fmaf(vec_s[3 * NP + c0 + e], v, psum);
                         }
-                        if (SAVE && c0 < H)          // pre2 stays fp32: [tile][k / 4][128 rows][4]
+                        if (SAVE)                    // pre2 stays fp32: [tile][k / 4][128 rows][4]
                             *reinterpret_cast<float4*>(a.sv_pre2 + (((size_t)tile * (H / 4) + (c0 >> 2)) * 128 + r) * 4) = make_float4(pre[0], pre[1], pre[2], pre[3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) qr[4 * c4 + e] = 0.f;
                     }
                 }
+            };
+#pragma unroll
+            for (int ci = 0; ci < CF::MYCH; ++ci) {
+                const int ch = part + CF::NPARTS * ci;
+                if (ch < nfull) e1_chunk(std::false_type{}, q[ci], ch);
+                else if (ch < nchunks) e1_chunk(std::true_type{}, q[ci], ch);
             }
             fence_before_sync();
             mbar_arrive(d1_empty);                              // accumulator 1 is in registers: GEMM 1 of the next tile may start
@@ -343,29 +355,38 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
             TLW(43);
             const float gate = a.attention ? sigmoid_f(psum_parts<CF::NPARTS>(red1, r) + a.att_b) : 1.f;
             // ---- gated edge feature: segment sums -> agg, and operand atoms of GEMM 2 ----
+            auto g_chunk = [&](auto tail_t, const float (&qr)[16], int ch) {
+                constexpr bool TAIL = decltype(tail_t)::value;
+                float4 x[4];
 #pragma unroll
-            for (int ci = 0; ci < CF::MYCH; ++ci) {
-                const int ch = part + CF::NPARTS * ci;
-                if (ch < nchunks) {
-                    float4 x[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        x[c] = make_float4(q[ci][4 * c] * gate, q[ci][4 * c + 1] * gate, q[ci][4 * c + 2] * gate, q[ci][4 * c + 3] * gate);
+                for (int c = 0; c < 4; ++c) {
+                    x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!TAIL || ch * 16 + 4 * c < H) {
+                        x[c] = make_float4(qr[4 * c] * gate, qr[4 * c + 1] * gate, qr[4 * c + 2] * gate, qr[4 * c + 3] * gate);
                         if (!valid) x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
                         my_ef[r * CF::EF_STRIDE + 4 * c] = x[c].x; my_ef[r * CF::EF_STRIDE + 4 * c + 1] = x[c].y;
                         my_ef[r * CF::EF_STRIDE + 4 * c + 2] = x[c].z; my_ef[r * CF::EF_STRIDE + 4 * c + 3] = x[c].w;
                     }
-                    if constexpr (CF::AT) rg.put(2 * k + 1, ch, nchunks, lane_off, leader, x);
-                    else rg.put_chunk(2 * k + 1, ch >> 1, na, r, half, x);
-                    bar_named(BAR_PART + part, 128);
+                }
+                if constexpr (CF::AT) rg.put(2 * k + 1, ch, nchunks, lane_off, leader, x);
+                else rg.put_chunk(2 * k + 1, ch >> 1, na, r, half, x);
+                bar_named(BAR_PART + part, 128);
+                if (!TAIL || ch * 16 + (r & 15) < H) {
                     for (int nl = r >> 4; nl < nn; nl += 8) {
                         const int col = r & 15, c = ch * 16 + col;
                         float sum = 0.f;
                         for (int mm = seg_s[nl]; mm < seg_s[nl + 1]; ++mm) sum += my_ef[mm * CF::EF_STRIDE + col];   // (a 4-way unrolled form with batched loads measured 4-6 % slower)
-                        if (c < H) a.agg[(size_t)(node_lo + nl) * H + c] = sum;
+                        a.agg[(size_t)(node_lo + nl) * H + c] = sum;
                     }
-                    bar_named(BAR_PART + part, 128);
-                } else if (!CF::AT && ch < 2 * na) {
+                }
+                bar_named(BAR_PART + part, 128);
+            };
+#pragma unroll
+            for (int ci = 0; ci < CF::MYCH; ++ci) {
+                const int ch = part + CF::NPARTS * ci;
+                if (ch < nfull) g_chunk(std::false_type{}, q[ci], ch);
+                else if (ch < nchunks) g_chunk(std::true_type{}, q[ci], ch);
+                else if (!CF::AT && ch < 2 * na) {
                     // chunk beyond the hidden width but inside the last atom: publish zeros so the atom completes
                     // (the half-atom stages of the AT form have no such chunk)
                     float4 x[4] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
@@ -381,23 +402,35 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
             TLW(61);
             fence_after_sync();
             float phi_part = 0.f;
-#pragma unroll 1
-            for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
+            auto e2_chunk = [&](auto tail_t, int ch) {
+                constexpr bool TAIL = decltype(tail_t)::value;
                 float v[16];
                 tmem_ld16(lane_addr + CF::D2_COL + ch * 16, v);
 #pragma unroll
                 for (int pp = 0; pp < 2; ++pp) {
                     const int c0 = ch * 16 + 8 * pp;
+                    if (TAIL && c0 >= H) break;
                     float d3[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        float s3;
-                        silu_both(v[8 * pp + e] + vec_s[4 * NP + c0 + e], s3, d3[e]);
-                        phi_part = fmaf(vec_s[5 * NP + c0 + e], s3, phi_part);
+                    for (int hq = 0; hq < 2; ++hq) {
+                        if (!TAIL || c0 + 4 * hq < H) {
+#pragma unroll
+                            for (int e = 4 * hq; e < 4 * hq + 4; ++e) {
+                                float s3;
+                                silu_both(v[8 * pp + e] + vec_s[4 * NP + c0 + e], s3, d3[e]);
+                                phi_part = fmaf(vec_s[5 * NP + c0 + e], s3, phi_part);
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 4 * hq; e < 4 * hq + 4; ++e) d3[e] = 0.f;
+                        }
                     }
-                    if (SAVE && 2 * ch + pp < npl) sv_store8<GB_SV_D>(a.sv_d3, tile, npl, 2 * ch + pp, r, d3);
+                    if (SAVE) sv_store8<GB_SV_D>(a.sv_d3, tile, npl, 2 * ch + pp, r, d3);
                 }
-            }
+            };
+#pragma unroll 1
+            for (int ch = part; ch < nfull; ch += CF::NPARTS) e2_chunk(std::false_type{}, ch);
+            if (nfull < nchunks && part == (nfull & (CF::NPARTS - 1))) e2_chunk(std::true_type{}, nfull);
             fence_before_sync();
             mbar_arrive(d2_empty);
             red2[part * 128 + r] = phi_part;
