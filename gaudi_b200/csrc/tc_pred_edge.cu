@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
         const int group = warp & 3, part = (warp - 2) >> 2, half = part & 1;
         const int r = group * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(group * 32) << 16);
-        const int nchunks = (H + 15) / 16;
+        const int nchunks = (H + 15) / 16, nfull = H >> 4;       // all chunks / chunks whose 16 columns are all real
         const int tlr = (lane == 0 && group == 0) ? (part == 0 ? 0 : (part == 3 ? 1 : -1)) : -1;
         (void)tlr;
         const uint32_t lane_off = (uint32_t)(group * 32) << 16;
@@ -778,11 +778,13 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
             // chunk-streaming: g_ef = accumulator 1 + g_agg[row] goes BACK to tensor memory (same columns) instead of waiting in 64
             // registers for the row-wide attention reduction; the operand build of GEMM 2 reads it again.  The TMEM read of the
             // next chunk is in flight while the current one is processed.
+            // (two code paths per chunk, as in the forward kernel: chunks whose 16 columns are all real carry no per-column tests; the
+            //  last, partly filled chunk of a hidden width that is not a multiple of 16 only touches its real 4-column groups)
             {
                 float v[16];
                 if (part < nchunks) tmem_ld16_issue_f(lane_addr + part * 16, v);
-#pragma unroll 1
-                for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
+                auto e1_chunk = [&](auto tail_t, int ch) {
+                    constexpr bool TAIL = decltype(tail_t)::value;
                     tmem_ld_wait16(v);
                     TLW(200 + ch);
                     const float4* p2p = reinterpret_cast<const float4*>(svq_acquire<SVS>(sv, sq + ch, r));
@@ -791,20 +793,27 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         const int c0 = ch * 16 + 4 * c4;
-                        float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), p2 = ga;               // planes beyond H: zeros, not the slot's previous occupant
-                        if (c0 < H) { ga = *reinterpret_cast<const float4*>(ga_row + c0); p2 = p2p[c4 * 128]; }     // (the staged copy only holds the H real columns)
-                        const float4 wq = *reinterpret_cast<const float4*>(vec_s + 3 * NP + c0);
-                        const f2 qa = silu2(lo2(p2)), qb = silu2(hi2(p2));
-                        const f2 ga_ = add2(make_float2(v[4 * c4], v[4 * c4 + 1]), lo2(ga));
-                        const f2 gb2 = add2(make_float2(v[4 * c4 + 2], v[4 * c4 + 3]), hi2(ga));
-                        w[4 * c4] = ga_.x; w[4 * c4 + 1] = ga_.y; w[4 * c4 + 2] = gb2.x; w[4 * c4 + 3] = gb2.y;
-                        plog2 = fma2(lo2(wq), qa, plog2); plog2 = fma2(hi2(wq), qb, plog2);
-                        pdot2 = fma2(ga_, qa, pdot2); pdot2 = fma2(gb2, qb, pdot2);
+                        if (!TAIL || c0 < H) {                      // (the staged g_agg copy only holds the H real columns; planes beyond H
+                            const float4 ga = *reinterpret_cast<const float4*>(ga_row + c0);       //  would be the slot's previous occupant)
+                            const float4 p2 = p2p[c4 * 128];
+                            const float4 wq = *reinterpret_cast<const float4*>(vec_s + 3 * NP + c0);
+                            const f2 qa = silu2(lo2(p2)), qb = silu2(hi2(p2));
+                            const f2 ga_ = add2(make_float2(v[4 * c4], v[4 * c4 + 1]), lo2(ga));
+                            const f2 gb2 = add2(make_float2(v[4 * c4 + 2], v[4 * c4 + 3]), hi2(ga));
+                            w[4 * c4] = ga_.x; w[4 * c4 + 1] = ga_.y; w[4 * c4 + 2] = gb2.x; w[4 * c4 + 3] = gb2.y;
+                            plog2 = fma2(lo2(wq), qa, plog2); plog2 = fma2(hi2(wq), qb, plog2);
+                            pdot2 = fma2(ga_, qa, pdot2); pdot2 = fma2(gb2, qb, pdot2);
+                        } else {
+                            w[4 * c4] = 0.f; w[4 * c4 + 1] = 0.f; w[4 * c4 + 2] = 0.f; w[4 * c4 + 3] = 0.f;
+                        }
                     }
                     svq_release<SVS>(sv, sq + ch);
                     if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + (ch + CF::NPARTS) * 16, v);
                     tmem_st16(lane_addr + ch * 16, w);
-                }
+                };
+#pragma unroll 1
+                for (int ch = part; ch < nfull; ch += CF::NPARTS) e1_chunk(std::false_type{}, ch);
+                if (nfull < nchunks && part == (nfull & (CF::NPARTS - 1))) e1_chunk(std::true_type{}, nfull);
                 tmem_st_wait();
             }
             if constexpr (CF::GA_TMA) mbar_arrive(&ga_empty[k & 1]);      // this tile's g_agg block may be overwritten (two tiles from now)
@@ -824,34 +833,44 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                 const f2 gate2 = f2s(gate), kap2 = f2s(kap);
                 float v[16];
                 if (part < nchunks) tmem_ld16_issue_f(lane_addr + part * 16, v);
-#pragma unroll 1
-                for (int ch = part; ch < (CF::AT ? nchunks : 2 * na); ch += CF::NPARTS) {
+                auto b2_chunk = [&](auto tail_t, int ch) {
+                    constexpr bool TAIL = decltype(tail_t)::value;
                     f2 x[8];
-                    if (ch < nchunks) {
-                        tmem_ld_wait16(v);
-                        const float4* p2p = reinterpret_cast<const float4*>(svq_acquire<SVS>(sv, sq + ch, r));
-                        TLW(300 + ch);
+                    tmem_ld_wait16(v);
+                    const float4* p2p = reinterpret_cast<const float4*>(svq_acquire<SVS>(sv, sq + ch, r));
+                    TLW(300 + ch);
 #pragma unroll
-                        for (int c4 = 0; c4 < 4; ++c4) {
-                            const int c0 = ch * 16 + 4 * c4;
-                            float4 p2 = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (c0 < H) p2 = p2p[c4 * 128];
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const int c0 = ch * 16 + 4 * c4;
+                        if (!TAIL || c0 < H) {
+                            const float4 p2 = p2p[c4 * 128];
                             const float4 wq = *reinterpret_cast<const float4*>(vec_s + 3 * NP + c0);
                             const f2 ta = fma2(kap2, lo2(wq), mul2(make_float2(v[4 * c4], v[4 * c4 + 1]), gate2));
                             const f2 tb = fma2(kap2, hi2(wq), mul2(make_float2(v[4 * c4 + 2], v[4 * c4 + 3]), gate2));
                             x[2 * c4] = mul2(ta, dsilu2(lo2(p2)));
                             x[2 * c4 + 1] = mul2(tb, dsilu2(hi2(p2)));
+                        } else {
+                            x[2 * c4] = f2s(0.f); x[2 * c4 + 1] = f2s(0.f);
                         }
-                        svq_release<SVS>(sv, sq + ch);
-                        if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + (ch + CF::NPARTS) * 16, v);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) x[c] = f2s(0.f);
                     }
+                    svq_release<SVS>(sv, sq + ch);
+                    if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + (ch + CF::NPARTS) * 16, v);
                     TLW(320 + ch);
                     if constexpr (CF::AT) rg.put(2 * k + 1, ch, nchunks, lane_off, leader, x);
                     else rg.put_chunk2(2 * k + 1, ch >> 1, na, r, half, x);
                     TLW(340 + ch);
+                };
+#pragma unroll 1
+                for (int ch = part; ch < nfull; ch += CF::NPARTS) b2_chunk(std::false_type{}, ch);
+                if (nfull < nchunks && part == (nfull & (CF::NPARTS - 1))) b2_chunk(std::true_type{}, nfull);
+                if constexpr (!CF::AT) {         // chunks beyond the hidden width but inside the last atom: zeros, so that the atom completes
+                    for (int ch = nchunks; ch < 2 * na; ++ch)
+                        if ((ch & (CF::NPARTS - 1)) == part) {
+                            f2 x[8];
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) x[c] = f2s(0.f);
+                            rg.put_chunk2(2 * k + 1, ch >> 1, na, r, half, x);
+                        }
                 }
             }
             sq += nchunks;
@@ -877,15 +896,15 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                 const int wsw = (lane >> 2) & 1;
                 float v[16];
                 if (part < nchunks) tmem_ld16_issue_f(lane_addr + CF::D2_COL + part * 16, v);
-#pragma unroll 1
-                for (int ch = part; ch < nchunks; ch += CF::NPARTS) {
+                auto e2_chunk = [&](auto tail_t, int ch) {
+                    constexpr bool TAIL = decltype(tail_t)::value;
                     tmem_ld_wait16(v);
                     TLW(400 + ch);
                     const uint4* d1p = svq_acquire<SVS>(sv, sq + ch, r);
                     TLW(420 + ch);
                     f2 gp[8], d1v[8];
                     sv_load8<GB_SV_D>(d1p, 0, true, d1v);
-                    sv_load8<GB_SV_D>(d1p, 1, 2 * ch + 1 < npl, d1v + 4);
+                    sv_load8<GB_SV_D>(d1p, 1, !TAIL || 2 * ch + 1 < npl, d1v + 4);
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         const int c0 = ch * 16 + 4 * c4;
@@ -900,11 +919,12 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                     if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + CF::D2_COL + (ch + CF::NPARTS) * 16, v);   // next chunk in flight during the stores
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
+                        if (TAIL && ch * 16 + 8 * hh >= H) break;      // (uniform: the partly filled chunk's halves beyond the hidden width)
                         *reinterpret_cast<float4*>(stg + lane * 8 + 4 * (0 ^ wsw)) = cat2(gp[4 * hh], gp[4 * hh + 1]);
                         *reinterpret_cast<float4*>(stg + lane * 8 + 4 * (1 ^ wsw)) = cat2(gp[4 * hh + 2], gp[4 * hh + 3]);
                         __syncwarp();
                         const int c = ch * 16 + 8 * hh + 4 * piece;
-                        if (c < H) {
+                        if (!TAIL || c < H) {
 #pragma unroll
                             for (int i = 0; i < 2; ++i) {
                                 const int rw = rsub + 16 * i, rl = group * 32 + rw;
@@ -913,7 +933,10 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                         }
                         __syncwarp();
                     }
-                }
+                };
+#pragma unroll 1
+                for (int ch = part; ch < nfull; ch += CF::NPARTS) e2_chunk(std::false_type{}, ch);
+                if (nfull < nchunks && part == (nfull & (CF::NPARTS - 1))) e2_chunk(std::true_type{}, nfull);
             }
             sq += nchunks;
             fence_before_sync();
