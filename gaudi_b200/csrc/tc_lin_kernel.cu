@@ -16,6 +16,9 @@
 #include "tc_common.cuh"
 #include "kernels.h"
 
+#ifndef GB_LIN_SPLIT_LD
+#define GB_LIN_SPLIT_LD 0     // 1: TMEM read of the next chunk in flight across a chunk step (unsafe: see tc_pred_edge.cu, GB_BWD_SPLIT_LD)
+#endif
 #ifndef GB_LIN_S
 #define GB_LIN_S 2          // operand ring stages
 #define GB_LIN_CTAS 1       // CTAs per SM
@@ -235,15 +238,16 @@ __global__ void __launch_bounds__(TcLinCfg<NP>::THREADS, GB_LIN_CTAS) tc_lin_ker
                     }
                 }
             };
-            if (part < nchunks) tmem_ld16_issue(lane_addr + buf * 256 + part * 16, vr);
+            if (GB_LIN_SPLIT_LD && part < nchunks) tmem_ld16_issue(lane_addr + buf * 256 + part * 16, vr);
             load_side(part, sd_n, mk_n);
             for (int ch = part; ch < nchunks; ch += CF::EPARTS) {
-                tmem_ld_wait();
+                if (GB_LIN_SPLIT_LD) tmem_ld_wait();
+                else tmem_ld16u(lane_addr + buf * 256 + ch * 16, vr);
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     *reinterpret_cast<uint4*>(stg + lane * CF::STG_PITCH + 4 * q) = make_uint4(vr[4 * q], vr[4 * q + 1], vr[4 * q + 2], vr[4 * q + 3]);
                 __syncwarp();
-                if (ch + CF::EPARTS < nchunks) tmem_ld16_issue(lane_addr + buf * 256 + (ch + CF::EPARTS) * 16, vr);
+                if (GB_LIN_SPLIT_LD && ch + CF::EPARTS < nchunks) tmem_ld16_issue(lane_addr + buf * 256 + (ch + CF::EPARTS) * 16, vr);
                 float4 sd[4];
                 float mk[4];
 #pragma unroll

@@ -27,6 +27,13 @@
 #ifndef GB_BWD_AT
 #define GB_BWD_AT 0         // backward: shared-memory activation ring (see TcPredCfg)
 #endif
+#ifndef GB_BWD_SPLIT_LD
+// backward: 1 = the TMEM read of the next chunk is issued one chunk ahead and waited for at the top of the next step (rounds 2a-2e).
+// That form is UNSAFE and off: between the issue and the wait the destination registers are in flight, but the compiler does not
+// know it and may copy or spill them (it did once register pressure rose in round 2f: 2-7 of 24 000 molecules per run came out
+// 1e-5 .. 1e-4 off, different ones each run -- found by the replica test).  Loading and waiting together is also 6 % FASTER here.
+#define GB_BWD_SPLIT_LD 0
+#endif
 #ifndef GB_BWD_GA_TMA
 #define GB_BWD_GA_TMA 1     // backward: the tile's g_agg rows arrive by bulk TMA one tile ahead (two blocks of 16 rows) instead of a staging loop
 #endif
@@ -782,10 +789,10 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
             //  last, partly filled chunk of a hidden width that is not a multiple of 16 only touches its real 4-column groups)
             {
                 float v[16];
-                if (part < nchunks) tmem_ld16_issue_f(lane_addr + part * 16, v);
+                if (GB_BWD_SPLIT_LD && part < nchunks) tmem_ld16_issue_f(lane_addr + part * 16, v);
                 auto e1_chunk = [&](auto tail_t, int ch) {
                     constexpr bool TAIL = decltype(tail_t)::value;
-                    tmem_ld_wait16(v);
+                    if (GB_BWD_SPLIT_LD) tmem_ld_wait16(v); else tmem_ld16(lane_addr + ch * 16, v);
                     TLW(200 + ch);
                     const float4* p2p = reinterpret_cast<const float4*>(svq_acquire<SVS>(sv, sq + ch, r));
                     TLW(220 + ch);
@@ -808,7 +815,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                         }
                     }
                     svq_release<SVS>(sv, sq + ch);
-                    if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + (ch + CF::NPARTS) * 16, v);
+                    if (GB_BWD_SPLIT_LD && ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + (ch + CF::NPARTS) * 16, v);
                     tmem_st16(lane_addr + ch * 16, w);
                 };
 #pragma unroll 1
@@ -832,11 +839,11 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
             {
                 const f2 gate2 = f2s(gate), kap2 = f2s(kap);
                 float v[16];
-                if (part < nchunks) tmem_ld16_issue_f(lane_addr + part * 16, v);
+                if (GB_BWD_SPLIT_LD && part < nchunks) tmem_ld16_issue_f(lane_addr + part * 16, v);
                 auto b2_chunk = [&](auto tail_t, int ch) {
                     constexpr bool TAIL = decltype(tail_t)::value;
                     f2 x[8];
-                    tmem_ld_wait16(v);
+                    if (GB_BWD_SPLIT_LD) tmem_ld_wait16(v); else tmem_ld16(lane_addr + ch * 16, v);
                     const float4* p2p = reinterpret_cast<const float4*>(svq_acquire<SVS>(sv, sq + ch, r));
                     TLW(300 + ch);
 #pragma unroll
@@ -854,7 +861,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                         }
                     }
                     svq_release<SVS>(sv, sq + ch);
-                    if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + (ch + CF::NPARTS) * 16, v);
+                    if (GB_BWD_SPLIT_LD && ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + (ch + CF::NPARTS) * 16, v);
                     TLW(320 + ch);
                     if constexpr (CF::AT) rg.put(2 * k + 1, ch, nchunks, lane_off, leader, x);
                     else rg.put_chunk2(2 * k + 1, ch >> 1, na, r, half, x);
@@ -895,10 +902,10 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                 const int piece = lane & 1, rsub = lane >> 1;
                 const int wsw = (lane >> 2) & 1;
                 float v[16];
-                if (part < nchunks) tmem_ld16_issue_f(lane_addr + CF::D2_COL + part * 16, v);
+                if (GB_BWD_SPLIT_LD && part < nchunks) tmem_ld16_issue_f(lane_addr + CF::D2_COL + part * 16, v);
                 auto e2_chunk = [&](auto tail_t, int ch) {
                     constexpr bool TAIL = decltype(tail_t)::value;
-                    tmem_ld_wait16(v);
+                    if (GB_BWD_SPLIT_LD) tmem_ld_wait16(v); else tmem_ld16(lane_addr + CF::D2_COL + ch * 16, v);
                     TLW(400 + ch);
                     const uint4* d1p = svq_acquire<SVS>(sv, sq + ch, r);
                     TLW(420 + ch);
@@ -916,7 +923,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                         pa2 = fma2(lo2(wa), gp[2 * c4], pa2); pa2 = fma2(hi2(wa), gp[2 * c4 + 1], pa2);
                     }
                     svq_release<SVS>(sv, sq + ch);
-                    if (ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + CF::D2_COL + (ch + CF::NPARTS) * 16, v);   // next chunk in flight during the stores
+                    if (GB_BWD_SPLIT_LD && ch + CF::NPARTS < nchunks) tmem_ld16_issue_f(lane_addr + CF::D2_COL + (ch + CF::NPARTS) * 16, v);   // next chunk in flight during the stores
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
                         if (TAIL && ch * 16 + 8 * hh >= H) break;      // (uniform: the partly filled chunk's halves beyond the hidden width)
