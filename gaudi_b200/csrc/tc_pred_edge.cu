@@ -16,7 +16,8 @@
 #define GB_BWD_SW 2         // backward: weight half-atom slots
 #endif
 #ifndef GB_BWD_SVS
-#define GB_BWD_SVS 5        // backward: saved-activation ring slots (8 KB each)
+#define GB_BWD_SVS 6        // backward: saved-activation ring slots (8 KB each).  5 -> 6 slots: -4 % (the stall attribution of the r2f
+                            // profile had 17 % of the samples in svq_acquire); sharing a slot between two 4 KB derivative chunks: no further gain
 #endif
 #ifndef GB_SV_D
 #define GB_SV_D SV_FX       // 16-bit code of the saved SiLU derivatives (tc_common.cuh)
@@ -490,7 +491,10 @@ struct TcBwdCfg : TcPredCfg<NP, GB_BWD_AT != 0> {
     static constexpr int GA_SCRATCH_ROWS = B::AT ? 32 : 0;                 // AT form: staged g_agg rows of a tile (else they borrow the A ring)
     // g_agg rows of the coming tile by bulk TMA (SV warp) into one of two blocks: tiles with more row nodes read g_agg from L2
     static constexpr bool GA_TMA = GB_BWD_GA_TMA && !B::AT && NP <= 208;
-    static constexpr int GA_TMA_ROWS = 16;
+#ifndef GB_GA_TMA_ROWS
+#define GB_GA_TMA_ROWS 15          // (15 rows of NP floats per block leave room for the sixth 8 KB slot of the saved-activation ring)
+#endif
+    static constexpr int GA_TMA_ROWS = GB_GA_TMA_ROWS;
     static constexpr int GA_BLOCK_BYTES = GA_TMA_ROWS * NP * 4;
     static constexpr int SCRATCH = 6 * NP * 4 + 2 * B::NPARTS * 128 * 4 + SV_SLOTS * B::SV_SLOT_BYTES + (B::NWORK / 32) * STG_WARP_FLOATS * 4 +
                                    2 * GEO_WORDS * 4 + GA_SCRATCH_ROWS * NP * 4 + (GA_TMA ? 2 * GA_BLOCK_BYTES : 0) + 64;
