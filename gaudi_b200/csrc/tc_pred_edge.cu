@@ -253,6 +253,14 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
         const uint32_t lane_off = (uint32_t)(group * 32) << 16;
         const bool leader = group == 0 && lane == 0;
         (void)lane_off; (void)leader;
+#ifndef GB_FWD_ROT
+#define GB_FWD_ROT 2
+#endif
+        // chunk ownership of the epilogues: part p owns the chunks ch == pv (mod 4).  In the GEMM-1 operand build the extra (7th) atom
+        // belongs to parts 0 / 1 (the pairs are tied to the staged P rows); rotating the epilogues' ownership by two gives the extra 13th
+        // chunk to part 2, so that no part is the slow one in every phase.  (Only with the operands in tensor memory: the shared-memory
+        // ring ties a chunk's atom to a pair.)
+        const int pv = CF::AT ? ((part + GB_FWD_ROT) & (CF::NPARTS - 1)) : part;
         float* my_ef = ef_s + part * 128 * CF::EF_STRIDE;
         float* red1 = red_s; float* red2 = red_s + CF::NPARTS * 128;
         const int tlr = (lane == 0 && group == 0) ? (part == 0 ? 0 : (part == 3 ? 1 : -1)) : -1;
@@ -349,7 +357,7 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
             };
 #pragma unroll
             for (int ci = 0; ci < CF::MYCH; ++ci) {
-                const int ch = part + CF::NPARTS * ci;
+                const int ch = pv + CF::NPARTS * ci;
                 if (ch < nfull) e1_chunk(std::false_type{}, q[ci], ch);
                 else if (ch < nchunks) e1_chunk(std::true_type{}, q[ci], ch);
             }
@@ -391,7 +399,7 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
             };
 #pragma unroll
             for (int ci = 0; ci < CF::MYCH; ++ci) {
-                const int ch = part + CF::NPARTS * ci;
+                const int ch = pv + CF::NPARTS * ci;
                 if (ch < nfull) g_chunk(std::false_type{}, q[ci], ch);
                 else if (ch < nchunks) g_chunk(std::true_type{}, q[ci], ch);
                 else if (!CF::AT && ch < 2 * na) {
@@ -437,8 +445,8 @@ __global__ void __launch_bounds__(TcFwdCfg<NP>::THREADS, 1) tc_pred_edge_fwd_ker
                 }
             };
 #pragma unroll 1
-            for (int ch = part; ch < nfull; ch += CF::NPARTS) e2_chunk(std::false_type{}, ch);
-            if (nfull < nchunks && part == (nfull & (CF::NPARTS - 1))) e2_chunk(std::true_type{}, nfull);
+            for (int ch = pv; ch < nfull; ch += CF::NPARTS) e2_chunk(std::false_type{}, ch);
+            if (nfull < nchunks && pv == (nfull & (CF::NPARTS - 1))) e2_chunk(std::true_type{}, nfull);
             fence_before_sync();
             mbar_arrive(d2_empty);
             red2[part * 128 + r] = phi_part;
@@ -704,6 +712,13 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
         const int r = group * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(group * 32) << 16);
         const int nchunks = (H + 15) / 16, nfull = H >> 4;       // all chunks / chunks whose 16 columns are all real
+#ifndef GB_BWD_ROT
+#define GB_BWD_ROT 0          // (2 = extra chunk of the epilogues on part 2 as in the forward kernel: no measurable gain here)
+#endif
+        // chunk ownership of the two EPILOGUES: ch == pv (mod 4).  The operand builds are tied to the part pairs of the activation ring
+        // (the extra chunk is part 0's there); the epilogues only read tensor memory and the saved-activation ring, so their extra chunk
+        // can go to part 2 (see the forward kernel)
+        const int pv = (part + GB_BWD_ROT) & (CF::NPARTS - 1);
         const int tlr = (lane == 0 && group == 0) ? (part == 0 ? 0 : (part == 3 ? 1 : -1)) : -1;
         (void)tlr;
         const uint32_t lane_off = (uint32_t)(group * 32) << 16;
@@ -793,7 +808,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
             //  last, partly filled chunk of a hidden width that is not a multiple of 16 only touches its real 4-column groups)
             {
                 float v[16];
-                if (GB_BWD_SPLIT_LD && part < nchunks) tmem_ld16_issue_f(lane_addr + part * 16, v);
+                if (GB_BWD_SPLIT_LD && pv < nchunks) tmem_ld16_issue_f(lane_addr + pv * 16, v);
                 auto e1_chunk = [&](auto tail_t, int ch) {
                     constexpr bool TAIL = decltype(tail_t)::value;
                     if (GB_BWD_SPLIT_LD) tmem_ld_wait16(v); else tmem_ld16(lane_addr + ch * 16, v);
@@ -823,8 +838,8 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                     tmem_st16(lane_addr + ch * 16, w);
                 };
 #pragma unroll 1
-                for (int ch = part; ch < nfull; ch += CF::NPARTS) e1_chunk(std::false_type{}, ch);
-                if (nfull < nchunks && part == (nfull & (CF::NPARTS - 1))) e1_chunk(std::true_type{}, nfull);
+                for (int ch = pv; ch < nfull; ch += CF::NPARTS) e1_chunk(std::false_type{}, ch);
+                if (nfull < nchunks && pv == (nfull & (CF::NPARTS - 1))) e1_chunk(std::true_type{}, nfull);
                 tmem_st_wait();
             }
             if constexpr (CF::GA_TMA) mbar_arrive(&ga_empty[k & 1]);      // this tile's g_agg block may be overwritten (two tiles from now)
@@ -906,7 +921,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                 const int piece = lane & 1, rsub = lane >> 1;
                 const int wsw = (lane >> 2) & 1;
                 float v[16];
-                if (GB_BWD_SPLIT_LD && part < nchunks) tmem_ld16_issue_f(lane_addr + CF::D2_COL + part * 16, v);
+                if (GB_BWD_SPLIT_LD && pv < nchunks) tmem_ld16_issue_f(lane_addr + CF::D2_COL + pv * 16, v);
                 auto e2_chunk = [&](auto tail_t, int ch) {
                     constexpr bool TAIL = decltype(tail_t)::value;
                     if (GB_BWD_SPLIT_LD) tmem_ld_wait16(v); else tmem_ld16(lane_addr + CF::D2_COL + ch * 16, v);
@@ -946,8 +961,8 @@ __global__ void __launch_bounds__(TcBwdCfg<NP>::THREADS, 1) tc_pred_edge_bwd_ker
                     }
                 };
 #pragma unroll 1
-                for (int ch = part; ch < nfull; ch += CF::NPARTS) e2_chunk(std::false_type{}, ch);
-                if (nfull < nchunks && part == (nfull & (CF::NPARTS - 1))) e2_chunk(std::true_type{}, nfull);
+                for (int ch = pv; ch < nfull; ch += CF::NPARTS) e2_chunk(std::false_type{}, ch);
+                if (nfull < nchunks && pv == (nfull & (CF::NPARTS - 1))) e2_chunk(std::true_type{}, nfull);
             }
             sq += nchunks;
             fence_before_sync();
